@@ -1,0 +1,171 @@
+/* pf_b200.h — C-ABI of libpf_b200.so: the sm_100a kernels behind the Pyramid-Flow sampler hot path.
+ *
+ * Boundary contract:
+ *   - plain C, raw device pointers + sizes + a cudaStream_t (passed as void*); no torch types;
+ *   - every function returns 0 on success, <0 on error; pf_last_error() gives the message;
+ *   - the caller owns every buffer; kernels are stream-ordered and hold no global mutable state;
+ *   - there is NO CPU fallback: on a machine without an sm_100 GPU every compute entry fails.
+ *
+ * Each entry cites the reference op site (file:line under jy0205/Pyramid-Flow @3040d71) it replaces.
+ * Abbreviations: F = pyramid_dit/flux_modules/modeling_pyramid_flux.py, B = .../modeling_flux_block.py,
+ * N = .../modeling_normalization.py, E = .../modeling_embedding.py, P = pyramid_dit/pyramid_dit_for_video_gen_pipeline.py,
+ * S = diffusion_schedulers/scheduling_flow_matching.py, C = video_vae/modeling_causal_conv.py,
+ * R = video_vae/modeling_resnet.py, K = video_vae/modeling_block.py, D = video_vae/modeling_enc_dec.py,
+ * V = video_vae/modeling_causal_vae.py.
+ */
+#ifndef PF_B200_H_
+#define PF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ misc */
+PF_API const char* pf_last_error(void);
+PF_API int pf_version(void);
+/* 0 if the current CUDA device is sm_100 (B200) and the driver exposes cuTensorMapEncodeTiled; <0 otherwise. */
+PF_API int pf_device_check(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
+PF_API int64_t pf_launch_count(void);
+
+/* ------------------------------------------------------------------ GEMM (tcgen05 + TMA)
+ * out = epilogue(A[rows, K] . W[N, K]^T + bias).  bf16 operands, fp32 accumulation in TMEM.
+ * Replaces every nn.Linear on the DiT path: x_embedder/context_embedder F:290,F:401; to_q/k/v, add_*_proj B:816-835;
+ * to_out/to_add_out B:868-872; FeedForward B:73-100; proj_mlp/proj_out B:923-938; norm_out+proj_out F:538-539;
+ * with the elementwise ops around them fused into the epilogue (bias, GELU-tanh, per-head RMSNorm N:66-79,
+ * RoPE B:34-39, gate*x + residual B:1019-1039).
+ *
+ * A is addressed as [batches][rows_per_batch][K] (row stride lda); only rows [row_begin, row_begin+row_count) of each
+ * batch are computed (the text / video ranges of the joint sequence).  Output row of (b, m) is
+ * b*out_batch_rows + out_row_begin + m.
+ */
+enum {
+  PF_EPI_STORE_BF16 = 0, /* out_bf16 = acc + bias                                         */
+  PF_EPI_GELU_BF16 = 1,  /* out_bf16 = gelu_tanh(acc + bias)          (diffusers GELU, B:73-75) */
+  PF_EPI_STORE_F32 = 2,  /* out_f32  = acc + bias                     (embedders into the fp32 residual stream) */
+  PF_EPI_GATE_RESID = 3, /* out_f32 += gate[b, n] * (acc + bias)      (B:1019-1020, 1027-1028, 1032-1039, 937-938) */
+  PF_EPI_QKV_ROPE = 4,   /* N = 3*H*hd: bias, RMSNorm(q,k) per head, RoPE(q,k); head-major Q/K/V stores */
+  PF_EPI_QKV_GELU = 5    /* N = 3*H*hd + n_mlp: columns < n_split as QKV_ROPE, the rest as GELU_BF16 (single block, B:923-936) */
+};
+
+typedef struct pf_gemm_desc {
+  const void* a; /* bf16 */
+  int64_t lda;   /* elements between rows of A */
+  int32_t batches, rows_per_batch, row_begin, row_count;
+  const void* w; /* bf16 [n, k] row-major (nn.Linear.weight) */
+  int32_t n, k;
+  const float* bias; /* fp32 [n] or NULL */
+  int32_t epilogue;
+  /* generic output (STORE_*, GELU, GATE_RESID, and the GELU half of QKV_GELU) */
+  void* out;
+  int64_t ldo;
+  int32_t out_batch_rows, out_row_begin, out_col_begin;
+  /* GATE_RESID: fp32 gate[b*gate_batch_stride + n] */
+  const float* gate;
+  int64_t gate_batch_stride;
+  /* QKV_*: outputs bf16 [batches, heads, seq_len, head_dim]; position of (b, m) is out_row_begin + m */
+  void* q_out;
+  void* k_out;
+  void* v_out;
+  const float* rope;     /* fp32 [seq_len, head_dim/2, 2] = (cos, sin) per rotation pair, or NULL (no rotation) */
+  const float* q_norm_w; /* fp32 [head_dim] */
+  const float* k_norm_w; /* fp32 [head_dim] */
+  float norm_eps;
+  int32_t heads, head_dim, seq_len;
+  int32_t n_split; /* QKV_GELU: first n_split (=3*H*hd) columns are q|k|v */
+} pf_gemm_desc;
+
+PF_API int pf_gemm_bf16(const pf_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------ masked joint attention (tcgen05 + TMA)
+ * softmax(Q K^T * scale + mask) V with mask(q, kv) = (seg[q] == seg[kv]) && (time[q] >= time[kv])  (F:318-350),
+ * replacing F.scaled_dot_product_attention with the dense bool mask at B:363-365 and B:596-598.
+ * q,k,v: bf16 [batch, heads, seq, 64]; out: bf16 [batch, seq, heads*64] with row stride ldo (elements).
+ * seg/time: int32 [batch, seq].  tile_sched: int32, built by pf_attn_build_schedule (host) from seg/time.
+ */
+typedef struct pf_attn_desc {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int64_t ldo;
+  int32_t batch, heads, seq, head_dim;
+  float scale;
+  const int32_t* seg;        /* device [batch, seq] */
+  const int32_t* time;       /* device [batch, seq] */
+  const int32_t* tile_sched; /* device; layout documented at pf_attn_build_schedule */
+  int32_t sched_stride;      /* int32 entries per (batch, q_tile) row */
+  int32_t variant;           /* 0 = default; other values select experimental data paths (see pf_attn.cu) */
+} pf_attn_desc;
+
+/* Host helper: from host copies of seg/time ids builds, for each (batch, 128-row q tile), the list of 128-wide kv
+ * tiles that contain at least one allowed pair, flagged full (no element mask needed) or partial.
+ * Row layout: [count, (kv_tile << 1) | needs_mask, ...].  Returns the number of int32 written per row
+ * (sched_stride) or <0 on error.  `out` may be NULL to query the size: stride = 1 + ceil(seq/128). */
+PF_API int pf_attn_build_schedule(const int32_t* seg_host, const int32_t* time_host, int32_t batch, int32_t seq,
+                                  int32_t* out, int64_t* allowed_pairs /* [batch] or NULL */);
+PF_API int pf_attn_fwd_masked(const pf_attn_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm + AdaLN modulate pre-pass (HBM-bound)
+ * y_bf16[r, :] = LN(x_f32[r, :], eps) * (1 + scale[b, :]) + shift[b, :]   (N:174, N:234, N:120, B:1022-1023, B:1035-1036)
+ * rows [row_begin, row_begin+row_count) of each batch of the joint [batches, rows_per_batch, dim] stream.
+ */
+PF_API int pf_ln_modulate(const float* x, void* y_bf16, int32_t batches, int32_t rows_per_batch, int32_t row_begin,
+                          int32_t row_count, int32_t dim, const float* shift, const float* scale,
+                          int64_t mod_batch_stride, float eps, void* stream);
+
+/* ------------------------------------------------------------------ small-M linear (HBM-bound GEMV)
+ * y[m, n] (+)= act_out( sum_k act_in(x[m, k]) * W[n, k] + bias[n] ), m <= 8; W bf16, x/y fp32.
+ * Used for the per-step AdaLN modulation of ALL layers in one launch (N:147,164,209,223,99,110) and the
+ * timestep/text conditioning MLPs (E:84-158, E:185-201).  act: 0 none, 1 SiLU.
+ */
+PF_API int pf_small_linear(const float* x, int32_t m, int32_t k, const void* w_bf16, const float* bias, int32_t n,
+                           float* y, int32_t act_in, int32_t act_out, int32_t accumulate, int32_t round_in_bf16,
+                           void* stream);
+
+/* sinusoidal timestep embedding, flip_sin_to_cos=True, downscale_freq_shift=0 (E:11-62): out fp32 [m, dim],
+ * out[:, :dim/2] = cos(t * f_i), out[:, dim/2:] = sin(t * f_i), f_i = exp(-ln(1e4) * i / (dim/2)); rounded to bf16
+ * values when round_bf16 != 0 (E:195).  t is fp32 [m] (already rounded to bf16 by the caller, P:750). */
+PF_API int pf_timestep_embedding(const float* t, int32_t m, int32_t dim, float* out, int32_t round_bf16,
+                                 void* stream);
+
+/* patchify one clip: latent bf16/fp32 [B, C, T, H, W] -> tokens bf16 [B, tok_begin + (t h w), (p1 p2 c)], p=2 (F:285-286).
+ * tokens row stride = 4*C; rows_per_batch = total tokens of all clips of the unit. */
+PF_API int pf_patchify(const void* latent, int32_t latent_is_f32, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w,
+                       void* tokens_bf16, int32_t rows_per_batch, int32_t tok_begin, void* stream);
+/* unpatchify: x fp32 [B, rows_per_batch, 4*C] rows [row_begin, +t*h/2*w/2) -> out [B, C, T, H, W] (F:383-387). */
+PF_API int pf_unpatchify(const float* x, int32_t rows_per_batch, int32_t row_begin, int32_t b, int32_t c, int32_t t,
+                         int32_t h, int32_t w, void* out, int32_t out_is_f32, void* stream);
+
+/* fused CFG combine + Euler step (P:771-776, S:278-286):
+ * v = vu + g*(vc - vu); x_out = x + dsigma * v.  v: fp32 [2, n] (uncond, cond); x fp32 [n]. */
+PF_API int pf_cfg_euler_step(const float* v2, float guidance, float dsigma, const float* x, float* x_out, int64_t n,
+                             void* stream);
+
+/* ------------------------------------------------------------------ debug probe (used only by tests/tools)
+ * One CTA, one 128 x N x K tcgen05.mma chain with host-chosen descriptor bits, so descriptor encodings can be
+ * pinned on hardware without recompiling.  a: bf16 [128, K] (K-major) or staged to TMEM when a_from_tmem;
+ * b: bf16, loaded by TMA as [rows_b, cols_b] boxes of 64 columns.  d: fp32 [128, N]. */
+typedef struct pf_umma_probe {
+  const void* a;
+  const void* b;
+  float* d;
+  int32_t n, k;
+  int32_t b_rows, b_cols;  /* global shape of b (row-major) */
+  int32_t b_box_rows;      /* TMA box rows for b (box cols fixed at 64 = 128 B) */
+  int32_t b_mn_major;      /* instruction-descriptor bit 16 */
+  uint32_t b_lbo, b_sbo;   /* bytes */
+  uint32_t b_k_step_bytes; /* descriptor start-address advance per UMMA_K=16 inside a 64-wide k block */
+  uint32_t b_kblock_bytes; /* descriptor start-address advance per 4 UMMA_K steps (one 64-wide k block) */
+  int32_t a_from_tmem;     /* 1: A is converted to packed bf16 pairs in TMEM (lane = row, 32-bit column = 2 k) */
+} pf_umma_probe;
+PF_API int pf_debug_umma(const pf_umma_probe* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_B200_H_ */

@@ -1,0 +1,477 @@
+// pf_gemm.cu — persistent warp-specialised bf16 GEMM on tcgen05 tensor cores with fused epilogues.
+//
+//   out = epilogue(A[rows, K] . W[N, K]^T + bias)
+//
+// One CTA per SM (persistent, static tile schedule), 256 threads:
+//   warp 0 (one lane)  TMA producer: A tile [128 x 64] + W tile [BN x 64] per stage, SWIZZLE_128B, mbarrier tx-count
+//   warp 1 (one lane)  MMA issuer  : 4 x tcgen05.mma (128 x BN x 16) per stage, fp32 accumulators in TMEM,
+//                                    tcgen05.commit releases the smem stage / publishes the accumulator
+//   warp 2             TMEM allocator (2 accumulator buffers -> epilogue of tile i overlaps MMA of tile i+1)
+//   warps 4..7         epilogue: tcgen05.ld (lane == output row), fused elementwise math, vectorised global stores
+//
+// Epilogues (include/pf_b200.h PF_EPI_*): bias / GELU-tanh / fp32 store / gate*x+residual / per-head RMSNorm + RoPE
+// with head-major Q,K,V stores / the single-block fused q|k|v|mlp split.
+// Reference op sites are listed in include/pf_b200.h at pf_gemm_bf16.
+#include "../../include/pf_b200.h"
+#include "pf_common.cuh"
+
+namespace pf {
+
+struct GemmArgs {
+  int batches, row_begin, row_count;
+  int n, k;
+  int m_tiles, n_tiles;
+  const float* bias;
+  void* out;
+  long long ldo;
+  int out_batch_rows, out_row_begin, out_col_begin;
+  const float* gate;
+  long long gate_batch_stride;
+  __nv_bfloat16* q_out;
+  __nv_bfloat16* k_out;
+  __nv_bfloat16* v_out;
+  const float* rope;
+  const float* q_norm_w;
+  const float* k_norm_w;
+  float norm_eps;
+  int heads, head_dim, seq_len;
+  int n_split;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192) ? 5 : (BN >= 128) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+// ---- epilogue helpers (one thread == one output row) -----------------------
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&x)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(x[8 * i + 0], x[8 * i + 1]);
+    u.y = pack_bf16x2(x[8 * i + 2], x[8 * i + 3]);
+    u.z = pack_bf16x2(x[8 * i + 4], x[8 * i + 5]);
+    u.w = pack_bf16x2(x[8 * i + 6], x[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+
+__device__ __forceinline__ void add_bias32(float (&x)[32], const uint32_t (&v)[32], const float* bias) {
+  if (bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(b4 + i);
+      x[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+      x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+      x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+  }
+}
+
+// One head (64 columns = two 32-column TMEM chunks) of q / k / v for one token.
+// section 0 = q, 1 = k (RMSNorm over the head N:66-79, then RoPE B:34-39), 2 = v (plain store).
+__device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t taddr, int n0, int b, int pos,
+                                                  bool valid) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(taddr, v0);
+  tmem_ld32(taddr + 32, v1);
+  tmem_ld_wait();
+  float x[64];
+  {
+    float lo[32], hi[32];
+    add_bias32(lo, v0, g.bias ? g.bias + n0 : nullptr);
+    add_bias32(hi, v1, g.bias ? g.bias + n0 + 32 : nullptr);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      x[i] = lo[i];
+      x[32 + i] = hi[i];
+    }
+  }
+  const int inner = g.heads * g.head_dim;
+  const int section = n0 / inner;
+  const int head = (n0 - section * inner) / g.head_dim;
+  __nv_bfloat16* base = section == 0 ? g.q_out : (section == 1 ? g.k_out : g.v_out);
+  if (section < 2) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) ss += x[i] * x[i];
+    const float r = rsqrtf(ss * (1.0f / 64.0f) + g.norm_eps);
+    const float4* w4 = reinterpret_cast<const float4*>(section == 0 ? g.q_norm_w : g.k_norm_w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 w = __ldg(w4 + i);
+      x[4 * i + 0] *= r * w.x;
+      x[4 * i + 1] *= r * w.y;
+      x[4 * i + 2] *= r * w.z;
+      x[4 * i + 3] *= r * w.w;
+    }
+    if (g.rope != nullptr && valid) {
+      const float4* cs4 = reinterpret_cast<const float4*>(g.rope + static_cast<size_t>(pos) * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 cs = __ldg(cs4 + i);  // (cos_{2i}, sin_{2i}, cos_{2i+1}, sin_{2i+1})
+        const float a0 = x[4 * i + 0], a1 = x[4 * i + 1], a2 = x[4 * i + 2], a3 = x[4 * i + 3];
+        x[4 * i + 0] = cs.x * a0 - cs.y * a1;
+        x[4 * i + 1] = cs.y * a0 + cs.x * a1;
+        x[4 * i + 2] = cs.z * a2 - cs.w * a3;
+        x[4 * i + 3] = cs.w * a2 + cs.z * a3;
+      }
+    }
+  }
+  if (valid) {
+    __nv_bfloat16* dst = base + ((static_cast<size_t>(b) * g.heads + head) * g.seq_len + pos) * 64;
+    float lo[32], hi[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      lo[i] = x[i];
+      hi[i] = x[32 + i];
+    }
+    store_bf16x32(dst, lo);
+    store_bf16x32(dst + 32, hi);
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                    const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int num_kb = (g.k + BK - 1) / BK;
+  const int tiles_per_batch = g.m_tiles * g.n_tiles;
+  const int total_tiles = g.batches * tiles_per_batch;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int mt = r / g.n_tiles;
+      const int nt = r - mt * g.n_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_3d(sa, &tm_a, &full_bar[stage], kb * BK, g.row_begin + mt * BM, b);
+        tma_load_2d(sb, &tm_b, &full_bar[stage], kb * BK, nt * BN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc_kmajor_sw128(sa);
+        const uint64_t db = make_smem_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          // +32 bytes (>>4 = 2) per UMMA_K = 16 bf16 inside the 128-byte swizzle row
+          umma_ss(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int mt = r / g.n_tiles;
+      const int nt = r - mt * g.n_tiles;
+      const int m = mt * BM + q * 32 + lane;
+      const bool valid = m < g.row_count;
+      const size_t out_row = static_cast<size_t>(b) * g.out_batch_rows + g.out_row_begin + m;
+      const int n_base = nt * BN;
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+      bool qkv_tile = (EPI == PF_EPI_QKV_ROPE);
+      if (EPI == PF_EPI_QKV_GELU) qkv_tile = n_base < g.n_split;
+
+      if (qkv_tile) {
+#pragma unroll 1
+        for (int h = 0; h < BN / 64; ++h) {
+          qkv_head_epilogue(g, taddr + h * 64, n_base + h * 64, b, g.out_row_begin + m, valid);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = n_base + c * 32;
+          float x[32];
+          add_bias32(x, v, g.bias ? g.bias + n0 : nullptr);
+          if (EPI == PF_EPI_GELU_BF16 || EPI == PF_EPI_QKV_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = gelu_tanh_f(x[i]);
+          }
+          if (EPI == PF_EPI_STORE_BF16 || EPI == PF_EPI_GELU_BF16 || EPI == PF_EPI_QKV_GELU) {
+            const int col = (EPI == PF_EPI_QKV_GELU) ? (g.out_col_begin + n0 - g.n_split) : (g.out_col_begin + n0);
+            if (valid) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + col, x);
+          } else if (EPI == PF_EPI_STORE_F32) {
+            if (valid) {
+              float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
+                                                     g.out_col_begin + n0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            }
+          } else if (EPI == PF_EPI_GATE_RESID) {
+            if (valid) {
+              float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
+                                                     g.out_col_begin + n0);
+              const float4* g4 = reinterpret_cast<const float4*>(g.gate + b * g.gate_batch_stride + n0);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 rr = d4[i];
+                const float4 gg = __ldg(g4 + i);
+                rr.x += gg.x * x[4 * i + 0];
+                rr.y += gg.y * x[4 * i + 1];
+                rr.z += gg.z * x[4 * i + 2];
+                rr.w += gg.w * x[4 * i + 3];
+                d4[i] = rr;
+              }
+            }
+          }
+        }
+      }
+      // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand the buffer back
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tc_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const int total = g.batches * g.m_tiles * g.n_tiles;
+  int grid = num_sms();
+  if (grid <= 0) grid = 148;
+  if (total < grid) grid = total;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, g);
+  return check_launch("pf_gemm_bf16");
+}
+
+template <int EPI>
+static int dispatch_bn(int bn, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmArgs& g,
+                       cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_gemm<256, EPI>(tm_a, tm_b, g, stream);
+    case 192: return launch_gemm<192, EPI>(tm_a, tm_b, g, stream);
+    case 128: return launch_gemm<128, EPI>(tm_a, tm_b, g, stream);
+    case 64: return launch_gemm<64, EPI>(tm_a, tm_b, g, stream);
+  }
+  set_error("unsupported BLOCK_N %d", bn);
+  return -1;
+}
+
+}  // namespace pf
+
+extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
+  using namespace pf;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PF_REQUIRE(d != nullptr, "pf_gemm_bf16: null descriptor");
+  PF_REQUIRE(d->a && d->w, "pf_gemm_bf16: null operand");
+  PF_REQUIRE(d->k > 0 && d->k % 8 == 0, "pf_gemm_bf16: k=%d must be a positive multiple of 8", d->k);
+  PF_REQUIRE(d->lda % 8 == 0 && d->lda >= d->k, "pf_gemm_bf16: lda=%lld must be >= k and a multiple of 8", (long long)d->lda);
+  PF_REQUIRE(d->batches > 0 && d->rows_per_batch > 0 && d->row_count > 0 && d->row_begin >= 0 &&
+                 d->row_begin + d->row_count <= d->rows_per_batch,
+             "pf_gemm_bf16: bad row range (batches %d rows %d begin %d count %d)", d->batches, d->rows_per_batch,
+             d->row_begin, d->row_count);
+  PF_REQUIRE((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0,
+             "pf_gemm_bf16: operands must be 16-byte aligned");
+  const int epi = d->epilogue;
+  PF_REQUIRE(epi >= 0 && epi <= PF_EPI_QKV_GELU, "pf_gemm_bf16: unknown epilogue %d", epi);
+
+  int bn = 0;
+  const bool qkv = (epi == PF_EPI_QKV_ROPE || epi == PF_EPI_QKV_GELU);
+  if (qkv) {
+    PF_REQUIRE(d->head_dim == 64, "pf_gemm_bf16: QKV epilogue supports head_dim 64 only (got %d)", d->head_dim);
+    const int inner = d->heads * d->head_dim;
+    const int nq = 3 * inner;
+    PF_REQUIRE(d->q_out && d->k_out && d->v_out && d->q_norm_w && d->k_norm_w, "pf_gemm_bf16: QKV epilogue needs q/k/v outputs and norm weights");
+    PF_REQUIRE(inner % 64 == 0, "pf_gemm_bf16: heads*head_dim must be a multiple of 64");
+    PF_REQUIRE(d->out_row_begin + d->row_count <= d->seq_len, "pf_gemm_bf16: QKV rows exceed seq_len");
+    if (epi == PF_EPI_QKV_ROPE) {
+      PF_REQUIRE(d->n == nq, "pf_gemm_bf16: QKV_ROPE needs n == 3*heads*head_dim");
+    } else {
+      PF_REQUIRE(d->n_split == nq && d->n > nq && d->out != nullptr, "pf_gemm_bf16: QKV_GELU needs n_split == 3*heads*head_dim < n and out");
+    }
+    bn = (inner % 192 == 0 && d->n % 192 == 0) ? 192 : ((inner % 128 == 0 && d->n % 128 == 0) ? 128 : 64);
+    PF_REQUIRE(d->n % bn == 0 && inner % bn == 0, "pf_gemm_bf16: n=%d / inner=%d not tileable", d->n, inner);
+  } else {
+    PF_REQUIRE(d->out != nullptr, "pf_gemm_bf16: null output");
+    if (d->n % 256 == 0) bn = 256;
+    else if (d->n % 192 == 0) bn = 192;
+    else if (d->n % 128 == 0) bn = 128;
+    else if (d->n % 64 == 0) bn = 64;
+    PF_REQUIRE(bn != 0, "pf_gemm_bf16: n=%d must be a multiple of 64", d->n);
+    if (epi == PF_EPI_GATE_RESID) PF_REQUIRE(d->gate != nullptr, "pf_gemm_bf16: GATE_RESID needs gate");
+    const int esz = (epi == PF_EPI_STORE_F32 || epi == PF_EPI_GATE_RESID) ? 4 : 2;
+    PF_REQUIRE((d->ldo * esz) % 16 == 0 && (d->out_col_begin * esz) % 16 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
+               "pf_gemm_bf16: output must be 16-byte aligned (ldo %lld col %d)", (long long)d->ldo, d->out_col_begin);
+  }
+
+  GemmArgs g{};
+  g.batches = d->batches;
+  g.row_begin = d->row_begin;
+  g.row_count = d->row_count;
+  g.n = d->n;
+  g.k = d->k;
+  g.m_tiles = (d->row_count + BM - 1) / BM;
+  g.n_tiles = d->n / bn;
+  g.bias = d->bias;
+  g.out = d->out;
+  g.ldo = d->ldo;
+  g.out_batch_rows = d->out_batch_rows;
+  g.out_row_begin = d->out_row_begin;
+  g.out_col_begin = d->out_col_begin;
+  g.gate = d->gate;
+  g.gate_batch_stride = d->gate_batch_stride;
+  g.q_out = static_cast<__nv_bfloat16*>(d->q_out);
+  g.k_out = static_cast<__nv_bfloat16*>(d->k_out);
+  g.v_out = static_cast<__nv_bfloat16*>(d->v_out);
+  g.rope = d->rope;
+  g.q_norm_w = d->q_norm_w;
+  g.k_norm_w = d->k_norm_w;
+  g.norm_eps = d->norm_eps;
+  g.heads = d->heads;
+  g.head_dim = d->head_dim;
+  g.seq_len = d->seq_len;
+  g.n_split = d->n_split;
+
+  CUtensorMap tm_a, tm_b;
+  {
+    const uint64_t dims[3] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->rows_per_batch),
+                              static_cast<uint64_t>(d->batches)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(d->lda) * 2,
+                                 static_cast<uint64_t>(d->lda) * 2 * static_cast<uint64_t>(d->rows_per_batch)};
+    const uint32_t box[3] = {BK, BM, 1};
+    int rc = encode_tensor_map(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->a, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->n)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(d->k) * 2};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    int rc = encode_tensor_map(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+
+  switch (epi) {
+    case PF_EPI_STORE_BF16: return dispatch_bn<PF_EPI_STORE_BF16>(bn, tm_a, tm_b, g, stream);
+    case PF_EPI_GELU_BF16: return dispatch_bn<PF_EPI_GELU_BF16>(bn, tm_a, tm_b, g, stream);
+    case PF_EPI_STORE_F32: return dispatch_bn<PF_EPI_STORE_F32>(bn, tm_a, tm_b, g, stream);
+    case PF_EPI_GATE_RESID: return dispatch_bn<PF_EPI_GATE_RESID>(bn, tm_a, tm_b, g, stream);
+    case PF_EPI_QKV_ROPE: return dispatch_bn<PF_EPI_QKV_ROPE>(bn, tm_a, tm_b, g, stream);
+    case PF_EPI_QKV_GELU: return dispatch_bn<PF_EPI_QKV_GELU>(bn, tm_a, tm_b, g, stream);
+  }
+  return -1;
+}

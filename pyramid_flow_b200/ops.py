@@ -1,0 +1,168 @@
+"""Tensor-level wrappers over the C-ABI (one function per entry point in include/pf_b200.h).
+
+Each wrapper validates dtypes/contiguity, passes raw pointers + the current stream, and raises on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (AttnDesc, GemmDesc, UmmaProbe, PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_QKV_GELU,
+                   PF_EPI_QKV_ROPE, PF_EPI_STORE_BF16, PF_EPI_STORE_F32)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int, *,
+         batches: int = 1, rows_per_batch: Optional[int] = None, row_begin: int = 0, row_count: Optional[int] = None,
+         out: Optional[torch.Tensor] = None, ldo: Optional[int] = None, out_batch_rows: Optional[int] = None,
+         out_row_begin: Optional[int] = None, out_col_begin: int = 0,
+         gate: Optional[torch.Tensor] = None, gate_batch_stride: int = 0,
+         q_out=None, k_out=None, v_out=None, rope=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
+         heads: int = 0, head_dim: int = 0, seq_len: int = 0, n_split: int = 0) -> None:
+    """epilogue(A . W^T + bias); see pf_gemm_bf16 in include/pf_b200.h for the addressing rules."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_cuda and w.is_cuda
+    assert a.stride(-1) == 1 and w.is_contiguous()
+    n, k = w.shape
+    lda = a.stride(-2)
+    if rows_per_batch is None:
+        rows_per_batch = a.numel() // (a.shape[-1] * batches) if a.is_contiguous() else a.shape[-2]
+    if row_count is None:
+        row_count = rows_per_batch - row_begin
+    d = GemmDesc()
+    d.a, d.lda = a.data_ptr(), lda
+    d.batches, d.rows_per_batch, d.row_begin, d.row_count = batches, rows_per_batch, row_begin, row_count
+    d.w, d.n, d.k = w.data_ptr(), n, k
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    d.bias = _ptr(bias)
+    d.epilogue = epilogue
+    d.out = _ptr(out)
+    if out is not None:
+        d.ldo = ldo if ldo is not None else out.stride(-2)
+    d.out_batch_rows = out_batch_rows if out_batch_rows is not None else rows_per_batch
+    d.out_row_begin = out_row_begin if out_row_begin is not None else row_begin
+    d.out_col_begin = out_col_begin
+    if gate is not None:
+        assert gate.dtype == torch.float32
+    d.gate, d.gate_batch_stride = _ptr(gate), gate_batch_stride
+    d.q_out, d.k_out, d.v_out = _ptr(q_out), _ptr(k_out), _ptr(v_out)
+    for t in (rope, q_norm_w, k_norm_w):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous()
+    d.rope, d.q_norm_w, d.k_norm_w = _ptr(rope), _ptr(q_norm_w), _ptr(k_norm_w)
+    d.norm_eps = norm_eps
+    d.heads, d.head_dim, d.seq_len, d.n_split = heads, head_dim, seq_len, n_split
+    _lib.check(_lib.load().pf_gemm_bf16(C.byref(d), _lib.stream_ptr()), "pf_gemm_bf16")
+
+
+def linear_bf16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False) -> torch.Tensor:
+    """Convenience: y_bf16[M, N] = (gelu)(x[M, K] . w[N, K]^T + bias)."""
+    m = x.shape[0]
+    out = torch.empty(m, w.shape[0], dtype=torch.bfloat16, device=x.device)
+    gemm(x, w, bias, PF_EPI_GELU_BF16 if gelu else PF_EPI_STORE_BF16, rows_per_batch=m, out=out)
+    return out
+
+
+def ln_modulate(x: torch.Tensor, y: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, mod_batch_stride: int, *,
+                batches: int, rows_per_batch: int, row_begin: int, row_count: int, eps: float = 1e-6) -> None:
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.is_contiguous() and y.is_contiguous()
+    dim = x.shape[-1]
+    _lib.check(_lib.load().pf_ln_modulate(x.data_ptr(), y.data_ptr(), batches, rows_per_batch, row_begin, row_count,
+                                          dim, shift.data_ptr(), scale.data_ptr(), mod_batch_stride, eps,
+                                          _lib.stream_ptr()), "pf_ln_modulate")
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, *, act_in: int = 0,
+                 act_out: int = 0, accumulate: bool = False, round_in_bf16: bool = False) -> None:
+    assert x.dtype == torch.float32 and y.dtype == torch.float32 and w.dtype == torch.bfloat16
+    assert x.is_contiguous() and w.is_contiguous() and y.is_contiguous()
+    m, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k and y.shape == (m, n)
+    _lib.check(_lib.load().pf_small_linear(x.data_ptr(), m, k, w.data_ptr(), _ptr(bias), n, y.data_ptr(), act_in,
+                                           act_out, int(accumulate), int(round_in_bf16), _lib.stream_ptr()),
+               "pf_small_linear")
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, round_bf16: bool = True) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty(t.shape[0], dim, dtype=torch.float32, device=t.device)
+    _lib.check(_lib.load().pf_timestep_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), int(round_bf16),
+                                                 _lib.stream_ptr()), "pf_timestep_embedding")
+    return out
+
+
+def patchify(latent: torch.Tensor, tokens: torch.Tensor, rows_per_batch: int, tok_begin: int) -> None:
+    assert latent.is_contiguous() and latent.dtype in (torch.float32, torch.bfloat16) and tokens.dtype == torch.bfloat16
+    b, c, t, h, w = latent.shape
+    _lib.check(_lib.load().pf_patchify(latent.data_ptr(), int(latent.dtype == torch.float32), b, c, t, h, w,
+                                       tokens.data_ptr(), rows_per_batch, tok_begin, _lib.stream_ptr()), "pf_patchify")
+
+
+def unpatchify(x: torch.Tensor, rows_per_batch: int, row_begin: int, out: torch.Tensor) -> None:
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    b, c, t, h, w = out.shape
+    _lib.check(_lib.load().pf_unpatchify(x.data_ptr(), rows_per_batch, row_begin, b, c, t, h, w, out.data_ptr(),
+                                         int(out.dtype == torch.float32), _lib.stream_ptr()), "pf_unpatchify")
+
+
+def cfg_euler_step(v2: torch.Tensor, guidance: float, dsigma: float, x: torch.Tensor, x_out: torch.Tensor) -> None:
+    assert v2.dtype == torch.float32 and x.dtype == torch.float32 and x_out.dtype == torch.float32
+    n = x.numel()
+    assert v2.numel() == 2 * n
+    _lib.check(_lib.load().pf_cfg_euler_step(v2.data_ptr(), guidance, dsigma, x.data_ptr(), x_out.data_ptr(), n,
+                                             _lib.stream_ptr()), "pf_cfg_euler_step")
+
+
+def attn_build_schedule(seg: torch.Tensor, time: torch.Tensor):
+    """seg/time: int32 CPU tensors [batch, seq] -> (schedule int32 CPU [batch, q_tiles, stride], allowed_pairs [batch])."""
+    seg = seg.to(torch.int32).contiguous().cpu()
+    time = time.to(torch.int32).contiguous().cpu()
+    batch, seq = seg.shape
+    lib = _lib.load()
+    stride = lib.pf_attn_build_schedule(None, None, batch, seq, None, None)
+    if stride < 0:
+        _lib.check(stride, "pf_attn_build_schedule")
+    qt = (seq + 127) // 128
+    sched = torch.zeros(batch, qt, stride, dtype=torch.int32)
+    pairs = torch.zeros(batch, dtype=torch.int64)
+    rc = lib.pf_attn_build_schedule(seg.data_ptr(), time.data_ptr(), batch, seq, sched.data_ptr(), pairs.data_ptr())
+    if rc < 0:
+        _lib.check(rc, "pf_attn_build_schedule")
+    return sched, pairs
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, seg: torch.Tensor,
+             time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0) -> None:
+    """q,k,v bf16 [B,H,S,64]; out bf16 [B,S,*] (row stride = out.stride(1)); seg/time/sched int32 on device."""
+    assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    b, h, s, hd = q.shape
+    d = AttnDesc()
+    d.q, d.k, d.v, d.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.ldo = out.stride(-2)
+    d.batch, d.heads, d.seq, d.head_dim = b, h, s, hd
+    d.scale = scale
+    d.seg, d.time, d.tile_sched = seg.data_ptr(), time.data_ptr(), sched.data_ptr()
+    d.sched_stride = sched.shape[-1]
+    d.variant = variant
+    _lib.check(_lib.load().pf_attn_fwd_masked(C.byref(d), _lib.stream_ptr()), "pf_attn_fwd_masked")
+
+
+def debug_umma(a: torch.Tensor, b: torch.Tensor, n: int, k: int, *, b_box_rows: int, b_mn_major: int, b_lbo: int,
+               b_sbo: int, b_k_step_bytes: int, b_kblock_bytes: int, a_from_tmem: int) -> torch.Tensor:
+    d = torch.zeros(128, n, dtype=torch.float32, device=a.device)
+    p = UmmaProbe()
+    p.a, p.b, p.d = a.data_ptr(), b.data_ptr(), d.data_ptr()
+    p.n, p.k = n, k
+    p.b_rows, p.b_cols = b.shape
+    p.b_box_rows, p.b_mn_major = b_box_rows, b_mn_major
+    p.b_lbo, p.b_sbo, p.b_k_step_bytes, p.b_kblock_bytes = b_lbo, b_sbo, b_k_step_bytes, b_kblock_bytes
+    p.a_from_tmem = a_from_tmem
+    _lib.check(_lib.load().pf_debug_umma(C.byref(p), _lib.stream_ptr()), "pf_debug_umma")
+    return d

@@ -1,0 +1,367 @@
+"""Hardware bring-up checks, run on the GPU box: `python tools/gpu_check.py [group ...]`.
+
+Each group runs in its own subprocess under a timeout so a hung kernel cannot take the others down.
+Results go to stdout and gpurun_out/gpu_check_<group>.log.  These are bring-up diagnostics; the parity tests
+proper live in tests/ (-m gpu).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+GROUPS = ["probe", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "attn_perf"]
+
+
+def _rel_err(a, b):
+    import torch
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-20)).item()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def group_probe():
+    import torch
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+
+    def run(name, a, b_glob, ref, **kw):
+        try:
+            d = ops.debug_umma(a, b_glob, **kw)
+            torch.cuda.synchronize()
+            err = _rel_err(d, ref)
+            print(f"[probe] {name}: rel_err={err:.3e} {'OK' if err < 2e-2 else 'MISMATCH'}", flush=True)
+            return err
+        except Exception as e:  # noqa: BLE001
+            print(f"[probe] {name}: EXC {e}", flush=True)
+            return None
+
+    for k in (64, 128):
+        for n in (64, 128, 256):
+            a = torch.randn(128, k, device=dev).bfloat16()
+            bt = torch.randn(n, k, device=dev).bfloat16()  # [N, K] K-major
+            ref = a.float() @ bt.float().t()
+            run(f"kmajor n={n} k={k}", a, bt, ref, n=n, k=k, b_box_rows=n, b_mn_major=0, b_lbo=16, b_sbo=1024,
+                b_k_step_bytes=32, b_kblock_bytes=n * 128, a_from_tmem=0)
+    # MN-major B: global [K, N] row-major (N contiguous) — V as stored [kv, hd]
+    for k in (64, 128):
+        for n in (64, 128):
+            a = torch.randn(128, k, device=dev).bfloat16()
+            b = torch.randn(k, n, device=dev).bfloat16()  # [K, N]
+            ref = a.float() @ b.float()
+            # boxes: [k rows x 64 cols], one per 64-wide n block, sequential in smem => n-atom stride = k*128 bytes
+            for lbo in (k * 128, 16, 1024):
+                for sbo in (1024, k * 128):
+                    run(f"mnmajor n={n} k={k} lbo={lbo} sbo={sbo}", a, b, ref, n=n, k=k, b_box_rows=k, b_mn_major=1,
+                        b_lbo=lbo, b_sbo=sbo, b_k_step_bytes=2048, b_kblock_bytes=8192, a_from_tmem=0)
+    # A from TMEM (packed bf16 pairs), B K-major
+    for k in (64, 128):
+        for n in (64, 128):
+            a = torch.randn(128, k, device=dev).bfloat16()
+            bt = torch.randn(n, k, device=dev).bfloat16()
+            ref = a.float() @ bt.float().t()
+            run(f"a_tmem n={n} k={k}", a, bt, ref, n=n, k=k, b_box_rows=n, b_mn_major=0, b_lbo=16, b_sbo=1024,
+                b_k_step_bytes=32, b_kblock_bytes=n * 128, a_from_tmem=1)
+    # A from TMEM + B MN-major (the P.V configuration)
+    k, n = 128, 64
+    a = torch.randn(128, k, device=dev).bfloat16()
+    b = torch.randn(k, n, device=dev).bfloat16()
+    ref = a.float() @ b.float()
+    run("a_tmem + mnmajor n=64 k=128", a, b, ref, n=n, k=k, b_box_rows=k, b_mn_major=1, b_lbo=k * 128, b_sbo=1024,
+        b_k_step_bytes=2048, b_kblock_bytes=8192, a_from_tmem=1)
+
+
+def group_gemm():
+    import torch
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    for (m, n, k) in [(128, 64, 64), (128, 256, 64), (256, 256, 128), (300, 1920, 1920), (1000, 192, 512),
+                      (4096, 7680, 1920), (777, 128, 4096), (2048, 1920, 9600)]:
+        x = (torch.randn(m, k, device=dev) * 0.5).bfloat16()
+        w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
+        bias = torch.randn(n, device=dev)
+        try:
+            y = ops.linear_bf16(x, w, bias)
+            torch.cuda.synchronize()
+            ref = x.float() @ w.float().t() + bias
+            err = _rel_err(y, ref)
+            print(f"[gemm] m={m} n={n} k={k}: rel_err={err:.3e} {'OK' if err < 1e-2 else 'MISMATCH'}", flush=True)
+            if err >= 1e-2:
+                diff = (y.float() - ref).abs()
+                bad = (diff > 0.05 * ref.abs().max()).nonzero()
+                print(f"        bad elements: {bad.shape[0]} first {bad[:8].tolist()}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"[gemm] m={m} n={n} k={k}: EXC {e}", flush=True)
+
+
+def group_epilogue():
+    import torch
+    import torch.nn.functional as F
+    from pyramid_flow_b200 import ops
+    from pyramid_flow_b200._lib import (PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_QKV_GELU, PF_EPI_QKV_ROPE,
+                                        PF_EPI_STORE_F32)
+    torch.manual_seed(1)
+    dev = "cuda"
+    B, S, D, H = 2, 300, 384, 6
+    T0 = 40  # "text" rows
+    x = (torch.randn(B, S, D, device=dev) * 0.5).bfloat16()
+    # ---- GELU, batched row range
+    w = (torch.randn(4 * D, D, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(4 * D, device=dev) * 0.1
+    out = torch.zeros(B, S, 4 * D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(x, w, bias, PF_EPI_GELU_BF16, batches=B, rows_per_batch=S, row_begin=T0, row_count=S - T0, out=out)
+    torch.cuda.synchronize()
+    ref = F.gelu(x[:, T0:].float() @ w.float().t() + bias, approximate="tanh")
+    print(f"[epi] gelu range: rel_err={_rel_err(out[:, T0:], ref):.3e}; untouched rows zero: {bool((out[:, :T0] == 0).all())}", flush=True)
+    # ---- STORE_F32
+    w2 = (torch.randn(D, D, device=dev) * 0.05).bfloat16()
+    b2 = torch.randn(D, device=dev) * 0.1
+    o32 = torch.zeros(B, S, D, device=dev)
+    ops.gemm(x, w2, b2, PF_EPI_STORE_F32, batches=B, rows_per_batch=S, row_begin=0, row_count=T0, out=o32)
+    torch.cuda.synchronize()
+    ref = x[:, :T0].float() @ w2.float().t() + b2
+    print(f"[epi] store_f32: rel_err={_rel_err(o32[:, :T0], ref):.3e}; rest zero: {bool((o32[:, T0:] == 0).all())}", flush=True)
+    # ---- GATE_RESID
+    resid = torch.randn(B, S, D, device=dev)
+    resid0 = resid.clone()
+    gate = torch.randn(B, 3 * D, device=dev)
+    ops.gemm(x, w2, b2, PF_EPI_GATE_RESID, batches=B, rows_per_batch=S, row_begin=T0, row_count=S - T0, out=resid,
+             gate=gate[:, D:], gate_batch_stride=3 * D)
+    torch.cuda.synchronize()
+    ref = resid0[:, T0:] + gate[:, None, D:2 * D] * (x[:, T0:].float() @ w2.float().t() + b2)
+    print(f"[epi] gate_resid: rel_err={_rel_err(resid[:, T0:], ref):.3e}; text rows untouched: {bool((resid[:, :T0] == resid0[:, :T0]).all())}", flush=True)
+    # ---- QKV_ROPE (+ QKV_GELU)
+    hd = 64
+    wq = (torch.randn(3 * D, D, device=dev) * 0.05).bfloat16()
+    bq = torch.randn(3 * D, device=dev) * 0.1
+    qn = 1 + 0.1 * torch.randn(hd, device=dev)
+    kn = 1 + 0.1 * torch.randn(hd, device=dev)
+    ang = torch.randn(S, hd // 2, device=dev)
+    rope = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()  # [S, 32, 2]
+
+    def ref_qkv(xr, pos0):
+        y = xr.float() @ wq.float().t() + bq
+        q, k, v = y.chunk(3, dim=-1)
+        n = xr.shape[1]
+
+        def nr(t, wn):
+            t = t.view(B, n, H, hd)
+            t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * wn
+            c = rope[pos0:pos0 + n, :, 0][None, :, None, :]
+            s = rope[pos0:pos0 + n, :, 1][None, :, None, :]
+            t2 = t.view(B, n, H, hd // 2, 2)
+            o = torch.stack([c * t2[..., 0] - s * t2[..., 1], s * t2[..., 0] + c * t2[..., 1]], dim=-1)
+            return o.view(B, n, H, hd).transpose(1, 2)
+        return nr(q, qn), nr(k, kn), v.view(B, n, H, hd).transpose(1, 2)
+
+    qo = torch.zeros(B, H, S, hd, device=dev, dtype=torch.bfloat16)
+    ko = torch.zeros_like(qo)
+    vo = torch.zeros_like(qo)
+    ops.gemm(x, wq, bq, PF_EPI_QKV_ROPE, batches=B, rows_per_batch=S, row_begin=T0, row_count=S - T0,
+             q_out=qo, k_out=ko, v_out=vo, rope=rope, q_norm_w=qn, k_norm_w=kn, heads=H, head_dim=hd, seq_len=S)
+    torch.cuda.synchronize()
+    rq, rk, rv = ref_qkv(x[:, T0:], T0)
+    print(f"[epi] qkv_rope: q={_rel_err(qo[:, :, T0:], rq):.3e} k={_rel_err(ko[:, :, T0:], rk):.3e} v={_rel_err(vo[:, :, T0:], rv):.3e}; text rows zero: {bool((qo[:, :, :T0] == 0).all())}", flush=True)
+    # fused q|k|v|mlp
+    wm = (torch.randn(4 * D, D, device=dev) * 0.05).bfloat16()
+    bm = torch.randn(4 * D, device=dev) * 0.1
+    wcat = torch.cat([wq, wm], 0).contiguous()
+    bcat = torch.cat([bq, bm], 0).contiguous()
+    cat = torch.zeros(B, S, 5 * D, device=dev, dtype=torch.bfloat16)
+    qo.zero_(); ko.zero_(); vo.zero_()
+    ops.gemm(x, wcat, bcat, PF_EPI_QKV_GELU, batches=B, rows_per_batch=S, row_begin=0, row_count=S, out=cat,
+             out_col_begin=D, q_out=qo, k_out=ko, v_out=vo, rope=rope, q_norm_w=qn, k_norm_w=kn, heads=H, head_dim=hd,
+             seq_len=S, n_split=3 * D)
+    torch.cuda.synchronize()
+    rq, rk, rv = ref_qkv(x, 0)
+    rm = F.gelu(x.float() @ wm.float().t() + bm, approximate="tanh")
+    print(f"[epi] qkv_gelu: q={_rel_err(qo, rq):.3e} k={_rel_err(ko, rk):.3e} v={_rel_err(vo, rv):.3e} mlp={_rel_err(cat[..., D:], rm):.3e}; attn cols zero: {bool((cat[..., :D] == 0).all())}", flush=True)
+
+
+def group_elementwise():
+    import torch
+    import torch.nn.functional as F
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(2)
+    dev = "cuda"
+    B, S, D = 2, 333, 1920
+    x = torch.randn(B, S, D, device=dev) * 2 + 0.3
+    mod = torch.randn(B, 6 * D, device=dev) * 0.3
+    y = torch.zeros(B, S, D, device=dev, dtype=torch.bfloat16)
+    ops.ln_modulate(x, y, mod[:, 0:], mod[:, D:], 6 * D, batches=B, rows_per_batch=S, row_begin=77, row_count=S - 77)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x[:, 77:], (D,), eps=1e-6) * (1 + mod[:, None, D:2 * D]) + mod[:, None, :D]
+    print(f"[elt] ln_modulate: rel_err={_rel_err(y[:, 77:], ref):.3e}; skipped rows zero: {bool((y[:, :77] == 0).all())}", flush=True)
+    # small linear
+    xm = torch.randn(2, 1920, device=dev)
+    w = (torch.randn(5000, 1920, device=dev) * 0.05).bfloat16()
+    b = torch.randn(5000, device=dev)
+    yo = torch.zeros(2, 5000, device=dev)
+    ops.small_linear(xm, w, b, yo, act_in=1)
+    torch.cuda.synchronize()
+    ref = F.silu(xm) @ w.float().t() + b
+    print(f"[elt] small_linear silu-in: rel_err={_rel_err(yo, ref):.3e}", flush=True)
+    ops.small_linear(xm, w, b, yo, act_out=1, accumulate=True)
+    torch.cuda.synchronize()
+    ref2 = ref + F.silu(xm @ w.float().t() + b)
+    print(f"[elt] small_linear accumulate: rel_err={_rel_err(yo, ref2):.3e}", flush=True)
+    # timestep embedding
+    t = torch.tensor([972.0, 3.5], device=dev)
+    e = ops.timestep_embedding(t, 256, round_bf16=False)
+    half = 128
+    freq = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(half, device=dev).float() / half)
+    arg = t[:, None] * freq[None]
+    ref = torch.cat([arg.cos(), arg.sin()], -1)
+    print(f"[elt] timestep_embedding: max_abs={float((e - ref).abs().max()):.3e}", flush=True)
+    # patchify / unpatchify
+    lat = torch.randn(2, 16, 2, 8, 12, device=dev).bfloat16()
+    L = 2 * 4 * 6
+    tok = torch.zeros(2, 10 + L, 64, device=dev, dtype=torch.bfloat16)
+    ops.patchify(lat, tok, 10 + L, 10)
+    from einops import rearrange
+    ref = rearrange(rearrange(lat, "b c t h w -> b t h w c"), "b t (h p1) (w p2) c -> b (t h w) (p1 p2 c)", p1=2, p2=2)
+    print(f"[elt] patchify exact: {bool((tok[:, 10:] == ref).all())}", flush=True)
+    out = torch.zeros(2, 16, 2, 8, 12, device=dev)
+    ops.unpatchify(tok.float().contiguous(), 10 + L, 10, out)
+    print(f"[elt] unpatchify roundtrip exact: {bool((out == lat.float()).all())}", flush=True)
+    v2 = torch.randn(2, 1000, device=dev)
+    xs = torch.randn(1000, device=dev)
+    xo = torch.zeros(1000, device=dev)
+    ops.cfg_euler_step(v2, 5.0, -0.05, xs, xo)
+    ref = xs + (-0.05) * (v2[0] + 5.0 * (v2[1] - v2[0]))
+    print(f"[elt] cfg_euler: max_abs={float((xo - ref).abs().max()):.3e}", flush=True)
+
+
+def _time_cuda(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def group_gemm_perf():
+    import torch
+    from pyramid_flow_b200 import ops
+    dev = "cuda"
+    for (m, n, k) in [(30976, 1920, 1920), (30976, 5760, 1920), (30976, 7680, 1920), (30976, 1920, 7680),
+                      (30976, 13440, 1920), (30976, 1920, 9600)]:
+        x = (torch.randn(m, k, device=dev) * 0.5).bfloat16()
+        w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
+        out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+        ms = _time_cuda(lambda: ops.gemm(x, w, None, 0, rows_per_batch=m, out=out))
+        ms_ref = _time_cuda(lambda: torch.matmul(x, w.t(), out=out))
+        tf = 2.0 * m * n * k / ms / 1e9
+        print(f"[gemm_perf] m={m} n={n} k={k}: {ms:.3f} ms = {tf:.0f} TFLOP/s (cuBLAS {ms_ref:.3f} ms = {2.0*m*n*k/ms_ref/1e9:.0f})", flush=True)
+
+
+def group_attn():
+    import torch
+    from pyramid_flow_b200 import ops
+    sys.path.insert(0, str(ROOT))
+    torch.manual_seed(3)
+    dev = "cuda"
+
+    def case(name, B, H, S, seg, tim, variant=0):
+        q = torch.randn(B, H, S, 64, device=dev).bfloat16()
+        k = torch.randn(B, H, S, 64, device=dev).bfloat16()
+        v = torch.randn(B, H, S, 64, device=dev).bfloat16()
+        out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
+        sched, pairs = ops.attn_build_schedule(seg, tim)
+        try:
+            ops.attn_fwd(q, k, v, out, seg.to(dev).int(), tim.to(dev).int(), sched.to(dev), 0.125, variant)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[attn] {name}: EXC {e}", flush=True)
+            return
+        sg = seg.to(dev)
+        tm = tim.to(dev)
+        mask = (sg[:, :, None] == sg[:, None, :]) & (tm[:, :, None] >= tm[:, None, :])
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=mask[:, None])
+        ref = ref.transpose(1, 2).reshape(B, S, H * 64)
+        err = (out.float() - ref).abs().max().item()
+        print(f"[attn] {name} (variant {variant}): max_abs_err={err:.3e} pairs={pairs.tolist()} {'OK' if err < 3e-2 else 'MISMATCH'}", flush=True)
+
+    for variant in (0,):
+        S = 256
+        case("dense S=256", 1, 2, S, torch.ones(1, S, dtype=torch.int32), torch.zeros(1, S, dtype=torch.int32), variant)
+        S = 384
+        tim = torch.cat([torch.zeros(128), torch.ones(128), 2 * torch.ones(128)]).int()[None]
+        case("tile-aligned causal S=384", 1, 2, S, torch.ones(1, S, dtype=torch.int32), tim, variant)
+        S = 128 + 60 * 5
+        tim = torch.cat([torch.zeros(128 + 60)] + [torch.full((60,), i + 1.0) for i in range(4)]).int()[None].repeat(2, 1)
+        seg = torch.ones(2, S, dtype=torch.int32)
+        seg[0, 37:128] = 0
+        case("ragged text + 5 frames of 60, S=428", 2, 3, S, seg, tim, variant)
+        S = 128 + 240 * 9
+        tim = torch.cat([torch.zeros(128 + 240)] + [torch.full((240,), i + 1.0) for i in range(8)]).int()[None].repeat(2, 1)
+        seg = torch.ones(2, S, dtype=torch.int32)
+        seg[0, 100:128] = 0
+        case("S=2288", 2, 4, S, seg, tim, variant)
+
+
+def group_attn_perf():
+    import torch
+    from pyramid_flow_b200 import ops
+    dev = "cuda"
+    B, H = 2, 30
+    # 768p last unit, stage 2: text 128 | 28 frames @240 | 1 @960 | 2 @3840  (S = 15488)
+    lens = [128 + 240] + [240] * 27 + [960, 3840, 3840]
+    tim = torch.cat([torch.full((n,), float(i)) for i, n in enumerate(lens)]).int()[None].repeat(B, 1)
+    S = tim.shape[1]
+    seg = torch.ones(B, S, dtype=torch.int32)
+    q = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    k = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    v = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
+    sched, pairs = ops.attn_build_schedule(seg, tim)
+    sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
+    ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125), iters=5)
+    flops = 4.0 * 64 * H * float(pairs.sum())
+    print(f"[attn_perf] S={S} B={B} H={H}: {ms:.3f} ms, allowed pairs {pairs.tolist()}, {flops/ms/1e9:.0f} TFLOP/s (masked-pair flops)", flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    args = sys.argv[1:]
+    if args and args[0] == "--child":
+        from pyramid_flow_b200 import _lib
+        _lib.require_device()
+        globals()["group_" + args[1]]()
+        return
+    groups = args or ["probe", "gemm", "epilogue", "elementwise"]
+    outdir = ROOT / "gpurun_out"
+    outdir.mkdir(exist_ok=True)
+    for g in groups:
+        t0 = time.time()
+        log = outdir / f"gpu_check_{g}.log"
+        with open(log, "w") as f:
+            try:
+                p = subprocess.run([sys.executable, __file__, "--child", g], stdout=subprocess.PIPE,
+                                   stderr=subprocess.STDOUT, text=True, timeout=int(os.environ.get("PF_CHECK_TIMEOUT", "240")))
+                out, rc = p.stdout, p.returncode
+            except subprocess.TimeoutExpired as e:
+                out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+                out += "\n[TIMEOUT]\n"
+                rc = -999
+            f.write(out)
+        print(f"===== {g}: rc={rc} ({time.time()-t0:.1f}s)\n{out}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
