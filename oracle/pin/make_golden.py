@@ -1,0 +1,121 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (imported from /root/reference through ref_shim).
+
+Run in the build container only:  python oracle/pin/make_golden.py [flux] [block] [sched] [vae] [loop]
+The GPU box has no /root/reference; it only sees the small fixtures this script commits under tests/golden/.
+Inputs and parameters are regenerated from seeds by the tests (torch CPU generators are deterministic), so the fixtures
+hold the reference OUTPUTS plus the exact inputs for safety.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle.pin import ref_shim  # noqa: E402
+
+ref_shim.install()
+from oracle import flux_oracle as FO  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+GOLD.mkdir(parents=True, exist_ok=True)
+
+SMALL_CFG = dict(num_layers=2, num_single_layers=2, num_attention_heads=4, attention_head_dim=64, in_channels=64,
+                 joint_attention_dim=128, pooled_projection_dim=64)
+
+
+def small_inputs(seed: int = 1, batch: int = 2, text_len: int = 24):
+    g = torch.Generator().manual_seed(seed)
+    clips = [torch.randn(batch, 16, 2, 4, 8, generator=g), torch.randn(batch, 16, 1, 8, 16, generator=g),
+             torch.randn(batch, 16, 1, 16, 32, generator=g)]
+    enc = torch.randn(batch, text_len, SMALL_CFG["joint_attention_dim"], generator=g) * 0.5
+    mask = torch.ones(batch, text_len, dtype=torch.long)
+    mask[0, 9:] = 0
+    pooled = torch.randn(batch, SMALL_CFG["pooled_projection_dim"], generator=g)
+    timestep = torch.tensor([972.0] * batch)
+    return clips, enc, mask, pooled, timestep
+
+
+def make_flux():
+    from pyramid_dit.flux_modules import PyramidFluxTransformer
+    cfg = FO.FluxConfig(**SMALL_CFG)
+    params = FO.synthetic_flux_params(cfg, seed=0)
+    model = PyramidFluxTransformer(**SMALL_CFG).eval()
+    missing = model.load_state_dict(params, strict=True)   # pins the key layout and shapes of flux_param_shapes()
+    print("load_state_dict:", missing)
+    clips, enc, mask, pooled, timestep = small_inputs()
+    with torch.no_grad():
+        out = model(sample=[clips], timestep_ratio=timestep, encoder_hidden_states=enc, encoder_attention_mask=mask,
+                    pooled_projections=pooled)[0]
+        # all-ones mask case too
+        out_full = model(sample=[clips], timestep_ratio=timestep, encoder_hidden_states=enc,
+                         encoder_attention_mask=torch.ones_like(mask), pooled_projections=pooled)[0]
+        # single-clip (first unit) case
+        out_first = model(sample=[[clips[-1]]], timestep_ratio=timestep * 0.5, encoder_hidden_states=enc,
+                          encoder_attention_mask=mask, pooled_projections=pooled)[0]
+    torch.save({"cfg": SMALL_CFG, "param_seed": 0, "input_seed": 1, "clips": clips, "enc": enc, "mask": mask,
+                "pooled": pooled, "timestep": timestep, "out": out, "out_full_mask": out_full, "out_first": out_first},
+               GOLD / "flux_small.pt")
+    print("flux_small:", out.shape, float(out.abs().mean()), float(out_first.abs().mean()))
+
+
+def make_block():
+    """BASELINE.json configs[0]: one miniFLUX double block + one single block, D=1920/H=30, 256 video + 77 text tokens."""
+    from pyramid_dit.flux_modules import FluxSingleTransformerBlock, FluxTransformerBlock
+    cfg = FO.FluxConfig(num_layers=1, num_single_layers=1)
+    params = FO.synthetic_flux_params(cfg, seed=0)
+    d, heads = cfg.inner_dim, cfg.num_attention_heads
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 256, d, generator=g)
+    ctx = torch.randn(1, 77, d, generator=g)
+    temb = torch.randn(1, d, generator=g)
+    ids = torch.cat([torch.zeros(77, 3), FO.clip_ids(1, 16, 16, 16, 16, 0)], 0)
+    cs = FO.rope_table(ids, cfg.axes_dims_rope)
+    rot = torch.stack([cs[..., 0], -cs[..., 1], cs[..., 1], cs[..., 0]], dim=-1).view(1, 333, 1, 32, 2, 2)
+    mask = torch.ones(1, 1, 333, 333, dtype=torch.bool)
+    blk = FluxTransformerBlock(dim=d, num_attention_heads=heads, attention_head_dim=64).eval()
+    blk.load_state_dict({k[len("transformer_blocks.0."):]: v for k, v in params.items() if k.startswith("transformer_blocks.0.")}, strict=True)
+    sblk = FluxSingleTransformerBlock(dim=d, num_attention_heads=heads, attention_head_dim=64).eval()
+    sblk.load_state_dict({k[len("single_transformer_blocks.0."):]: v for k, v in params.items() if k.startswith("single_transformer_blocks.0.")}, strict=True)
+    with torch.no_grad():
+        c_out, x_out = blk(hidden_states=x, encoder_hidden_states=ctx, encoder_attention_mask=None, temb=temb,
+                           attention_mask=[mask], hidden_length=[256], image_rotary_emb=[rot])
+        h = torch.cat([ctx, x], 1)
+        s_out = sblk(hidden_states=h, temb=temb, encoder_attention_mask=None, attention_mask=[mask],
+                     hidden_length=[333], image_rotary_emb=[rot])
+    torch.save({"x_out_rows": x_out[:, ::16].clone(), "c_out_rows": c_out[:, ::16].clone(),
+                "s_out_rows": s_out[:, ::16].clone(), "x_out_mean": x_out.mean(-1), "s_out_mean": s_out.mean(-1)},
+               GOLD / "flux_block_cfg1.pt")
+    print("block:", float(x_out.abs().mean()), float(c_out.abs().mean()), float(s_out.abs().mean()))
+
+
+def make_sched():
+    from diffusion_schedulers import PyramidFlowMatchEulerDiscreteScheduler
+    s = PyramidFlowMatchEulerDiscreteScheduler(shift=1.0, stages=3, stage_range=[0, 1 / 3, 2 / 3, 1], gamma=1 / 3)
+    out = {"start_sigmas": dict(s.start_sigmas), "end_sigmas": dict(s.end_sigmas), "ori_start_sigmas": dict(s.ori_start_sigmas),
+           "timestep_ratios": {k: list(v) for k, v in s.timestep_ratios.items()},
+           "timesteps_per_stage": {k: v.clone() for k, v in s.timesteps_per_stage.items()},
+           "sigmas_per_stage": {k: v.clone() for k, v in s.sigmas_per_stage.items()}}
+    for n in (10, 20):
+        for st in range(3):
+            s.set_timesteps(n, st)
+            out[f"timesteps_{n}_{st}"] = s.timesteps.clone()
+            out[f"sigmas_{n}_{st}"] = s.sigmas.clone()
+    # one Euler step in fp32
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 16, 1, 8, 8, generator=g)
+    v = torch.randn(1, 16, 1, 8, 8, generator=g)
+    s.set_timesteps(10, 1)
+    out["step_x"] = x
+    out["step_v"] = v
+    out["step_out"] = s.step(model_output=v, timestep=s.timesteps[0], sample=x).prev_sample.clone()
+    torch.save(out, GOLD / "scheduler.pt")
+    print("sched:", out["start_sigmas"], out["end_sigmas"])
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["flux", "block", "sched"]
+    for w in which:
+        globals()["make_" + w]()

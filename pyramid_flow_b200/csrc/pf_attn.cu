@@ -1,9 +1,288 @@
-// pf_attn.cu — masked joint text+video attention (placeholder kernel entry; host-side tile schedule is final).
+// pf_attn.cu — masked joint text+video attention forward on tcgen05 tensor cores (head_dim 64).
+//
+//   out[b, q, h, :] = softmax_kv( q.k * scale  | mask(q, kv) ) . v ,   mask = (seg_q == seg_kv) && (time_q >= time_kv)
+//
+// replaces F.scaled_dot_product_attention with the dense [B,1,S,S] bool mask (reference B:363-365, B:596-598; mask
+// built at F:318-350).  The mask is never materialised: a host-built tile schedule (pf_attn_build_schedule) lists, per
+// 128-row q tile, only the 128-wide kv tiles that contain an allowed pair and flags the few that need an element mask.
+//
+// One CTA = one (batch, head, 128-row q tile); 192 threads; two CTAs are co-resident per SM so that one CTA's softmax
+// (MUFU-bound at head_dim 64) overlaps the other CTA's tensor-core work:
+//   warps 0-3  softmax: thread == q row == TMEM lane.  S is read from TMEM twice (max pass, exp pass), P is written
+//              back to TMEM as packed bf16, O is rescaled in TMEM only when the running max moved by > 2^8 (lazy rescale)
+//   warp 4     MMA issuer (one lane): S = Q.K^T (SS: both operands in smem, K-major), O += P.V (TS: P from TMEM,
+//              V from smem MN-major — V is consumed in its natural [kv, hd] layout, no transpose)
+//   warp 5     TMA producer (one lane): Q once, then K/V tiles through a 2-stage mbarrier ring
+// TMEM map (256 columns): S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256).
 #include <algorithm>
 #include <vector>
 
 #include "../../include/pf_b200.h"
 #include "pf_common.cuh"
+
+namespace pf {
+
+constexpr int ATT_BM = 128;      // q rows per CTA
+constexpr int ATT_BN = 128;      // kv columns per tile
+constexpr int ATT_HD = 64;
+constexpr int ATT_STAGES = 2;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = ATT_BN * ATT_HD * 2;  // 16 KB
+constexpr int ATT_SMEM_BYTES = (1 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024;
+constexpr uint32_t ATT_TMEM_COLS = 256;
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192;
+
+struct AttnArgs {
+  __nv_bfloat16* out;
+  long long ldo;
+  int batch, heads, seq, q_tiles;
+  float scale_log2;
+  const int* seg;
+  const int* time;
+  const int* sched;
+  int sched_stride;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_kv = smem + ATT_TILE_BYTES;  // stage s: K at s*32K, V at s*32K + 16K
+
+  __shared__ __align__(8) uint64_t bar_q, bar_s_full, bar_p_full, bar_final;
+  __shared__ __align__(8) uint64_t kv_full[ATT_STAGES], kv_empty[ATT_STAGES];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // heavy (late) q tiles first: they own the longest kv lists
+  const int qt = a.q_tiles - 1 - static_cast<int>(blockIdx.x);
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * a.heads + h;
+  const int* sched = a.sched + (static_cast<size_t>(b) * a.q_tiles + qt) * a.sched_stride;
+  const int n_kv = sched[0];
+
+  if (warp == 5 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == 4 && lane == 0) {
+    mbar_init(&bar_q, 1);
+    mbar_init(&bar_s_full, 1);
+    mbar_init(&bar_p_full, 128);
+    mbar_init(&bar_final, 1);
+    for (int i = 0; i < ATT_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 5 && lane == 0) {
+    // ===== TMA producer =====
+    mbar_arrive_expect_tx(&bar_q, ATT_TILE_BYTES);
+    tma_load_3d(smem_q, &tm_q, &bar_q, 0, qt * ATT_BM, bh);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const int kt = sched[1 + j] >> 1;
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      uint8_t* sk = smem_kv + stage * 2 * ATT_TILE_BYTES;
+      mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+      tma_load_3d(sk, &tm_k, &kv_full[stage], 0, kt * ATT_BN, bh);
+      tma_load_3d(sk + ATT_TILE_BYTES, &tm_v, &kv_full[stage], 0, kt * ATT_BN, bh);
+      if (++stage == ATT_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 4 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // A = Q (K-major), B = K (K-major)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, 0, 1);  // A = P (TMEM),    B = V (MN-major)
+    mbar_wait(&bar_q, 0);
+    const uint64_t dq = make_smem_desc_kmajor_sw128(smem_u32(smem_q));
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      const uint32_t sk = smem_u32(smem_kv + stage * 2 * ATT_TILE_BYTES);
+      const uint64_t dk = make_smem_desc_kmajor_sw128(sk);
+#pragma unroll
+      for (int kk = 0; kk < ATT_HD / 16; ++kk) umma_ss(tmem_base + TM_S, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk != 0);
+      umma_commit(&bar_s_full);  // also covers P.V of the previous tile (commit tracks all prior MMAs)
+      mbar_wait(&bar_p_full, j & 1);
+      tc_fence_after();
+      // V tile [128 kv x 64 hd], 128-byte rows: MN-major, 8-row k groups 1024 B apart, 16 kv rows (2048 B) per MMA
+      const uint32_t sv = sk + ATT_TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+        const uint64_t dv = make_smem_desc(sv + kk * 2048, ATT_BN * 128, 1024);
+        umma_ts(tmem_base + TM_O, tmem_base + TM_P + kk * 8, dv, idesc_pv, (j | kk) != 0);
+      }
+      umma_commit(&kv_empty[stage]);
+      if (++stage == ATT_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit(&bar_final);
+  } else if (warp < 4) {
+    // ===== softmax + correction + epilogue =====
+    const int row = warp * 32 + lane;
+    const int qpos = qt * ATT_BM + row;
+    const bool q_valid = qpos < a.seq;
+    const int seg_q = q_valid ? a.seg[static_cast<size_t>(b) * a.seq + qpos] : -0x7fffffff;
+    const int time_q = q_valid ? a.time[static_cast<size_t>(b) * a.seq + qpos] : -0x7fffffff;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + TM_S;
+    const uint32_t t_o = tmem_base + lane_base + TM_O;
+    const uint32_t t_p = tmem_base + lane_base + TM_P;
+    const float c = a.scale_log2;
+    float m_run = -INFINITY;  // running reference max (raw score units)
+    float l_run = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int entry = sched[1 + j];
+      const int kt = entry >> 1;
+      const bool masked = (entry & 1) != 0;
+      uint32_t allow[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (masked) {
+        const int* sg = a.seg + static_cast<size_t>(b) * a.seq;
+        const int* tm = a.time + static_cast<size_t>(b) * a.seq;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t bits = 0;
+          for (int i = 0; i < 32; ++i) {
+            const int kv = kt * ATT_BN + w * 32 + i;
+            bool ok = false;
+            if (kv < a.seq) ok = (__ldg(sg + kv) == seg_q) && (__ldg(tm + kv) <= time_q);
+            bits |= (ok ? 1u : 0u) << i;
+          }
+          allow[w] = bits;
+        }
+      }
+      mbar_wait(&bar_s_full, j & 1);
+      tc_fence_after();
+
+      // ---- pass 1: row max over the tile
+      float m_tile = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        uint32_t v[32];
+        tmem_ld32(t_s + w * 32, v);
+        tmem_ld_wait();
+        const uint32_t bits = allow[w];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = ((bits >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY;
+          m_tile = fmaxf(m_tile, s);
+        }
+      }
+      // ---- lazy rescale decision (per row), correction is warp-collective
+      const float m_cand = fmaxf(m_run, m_tile);
+      float alpha = 1.f;
+      bool need = false;
+      if (m_cand > m_run) {
+        if (m_run == -INFINITY || (m_cand - m_run) * c > 8.f) {
+          need = true;
+          alpha = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_cand) * c);
+          m_run = m_cand;
+        }
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        uint32_t o[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld32(t_o + half * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(t_o + half * 32, o);
+        }
+      }
+      l_run *= alpha;
+      const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
+
+      // ---- pass 2: p = exp2(s*c - m_ref), P -> TMEM (bf16x2), row sum
+      float l_tile = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        uint32_t v[32];
+        tmem_ld32(t_s + w * 32, v);
+        tmem_ld_wait();
+        const uint32_t bits = allow[w];
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float s0 = ((bits >> (2 * i)) & 1u) ? __uint_as_float(v[2 * i]) : -INFINITY;
+          const float s1 = ((bits >> (2 * i + 1)) & 1u) ? __uint_as_float(v[2 * i + 1]) : -INFINITY;
+          const float p0 = ex2f(fmaf(s0, c, -m_ref));
+          const float p1 = ex2f(fmaf(s1, c, -m_ref));
+          l_tile += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(t_p + w * 16, pk);
+      }
+      l_run += l_tile;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> out[b, qpos, h*64 : h*64+64]
+    mbar_wait(&bar_final, 0);
+    tc_fence_after();
+    const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+    __nv_bfloat16* dst = a.out + (static_cast<size_t>(b) * a.seq + qpos) * a.ldo + h * ATT_HD;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t o[32];
+      tmem_ld32(t_o + half * 32, o);
+      tmem_ld_wait();
+      if (q_valid) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          d4[i] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+}  // namespace pf
 
 extern "C" int pf_attn_build_schedule(const int32_t* seg, const int32_t* time, int32_t batch, int32_t seq,
                                       int32_t* out, int64_t* allowed_pairs) {
@@ -16,7 +295,6 @@ extern "C" int pf_attn_build_schedule(const int32_t* seg, const int32_t* time, i
   for (int b = 0; b < batch; ++b) {
     const int32_t* sg = seg + static_cast<size_t>(b) * seq;
     const int32_t* tm = time + static_cast<size_t>(b) * seq;
-    // per-tile summaries
     std::vector<int32_t> tmin(tiles), tmax(tiles), smin(tiles), smax(tiles);
     for (int t = 0; t < tiles; ++t) {
       const int lo = t * 128, hi = std::min(seq, lo + 128);
@@ -36,9 +314,8 @@ extern "C" int pf_attn_build_schedule(const int32_t* seg, const int32_t* time, i
       const int qlo = qt * 128, qhi = std::min(seq, qlo + 128);
       for (int kt = 0; kt < tiles; ++kt) {
         const int klo = kt * 128, khi = std::min(seq, klo + 128);
-        // cheap rejections: no time-compatible pair, or disjoint segment ranges
-        if (tmax[qt] < tmin[kt]) continue;
-        if (smax[qt] < smin[kt] || smax[kt] < smin[qt]) continue;
+        if (tmax[qt] < tmin[kt]) continue;                              // no time-compatible pair
+        if (smax[qt] < smin[kt] || smax[kt] < smin[qt]) continue;       // disjoint segment ranges
         const bool uniform = (smin[qt] == smax[qt]) && (smin[kt] == smax[kt]) && (smin[qt] == smin[kt]);
         const bool full = uniform && (tmin[qt] >= tmax[kt]) && (khi - klo == 128);
         int64_t n_allowed = 0;
@@ -61,9 +338,49 @@ extern "C" int pf_attn_build_schedule(const int32_t* seg, const int32_t* time, i
   return stride;
 }
 
-extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream) {
-  (void)d;
-  (void)stream;
-  pf::set_error("pf_attn_fwd_masked: kernel not built yet");
-  return -1;
+extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
+  using namespace pf;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PF_REQUIRE(d && d->q && d->k && d->v && d->out && d->seg && d->time && d->tile_sched, "pf_attn_fwd_masked: null pointer");
+  PF_REQUIRE(d->head_dim == ATT_HD, "pf_attn_fwd_masked: head_dim %d unsupported (64 only)", d->head_dim);
+  PF_REQUIRE(d->batch > 0 && d->heads > 0 && d->seq > 0, "pf_attn_fwd_masked: bad shape");
+  const int q_tiles = (d->seq + ATT_BM - 1) / ATT_BM;
+  PF_REQUIRE(d->sched_stride >= 1 + q_tiles, "pf_attn_fwd_masked: schedule stride %d too small", d->sched_stride);
+  PF_REQUIRE(d->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pf_attn_fwd_masked: out must be 16-byte aligned");
+
+  CUtensorMap tm[3];
+  const void* ptrs[3] = {d->q, d->k, d->v};
+  for (int i = 0; i < 3; ++i) {
+    const uint64_t dims[3] = {ATT_HD, static_cast<uint64_t>(d->seq), static_cast<uint64_t>(d->batch) * d->heads};
+    const uint64_t strides[2] = {ATT_HD * 2, static_cast<uint64_t>(d->seq) * ATT_HD * 2};
+    const uint32_t box[3] = {ATT_HD, ATT_BN, 1};
+    int rc = encode_tensor_map(&tm[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptrs[i], dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnArgs a{};
+  a.out = static_cast<__nv_bfloat16*>(d->out);
+  a.ldo = d->ldo;
+  a.batch = d->batch;
+  a.heads = d->heads;
+  a.seq = d->seq;
+  a.q_tiles = q_tiles;
+  a.scale_log2 = d->scale * 1.4426950408889634f;
+  a.seg = d->seg;
+  a.time = d->time;
+  a.sched = d->tile_sched;
+  a.sched_stride = d->sched_stride;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("pf_attn_fwd_masked: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  dim3 grid(q_tiles, d->heads, d->batch);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  return check_launch("pf_attn_fwd_masked");
 }

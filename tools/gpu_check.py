@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-GROUPS = ["probe", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "attn_perf"]
+GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "attn_perf"]
 
 
 def _rel_err(a, b):
@@ -50,17 +50,29 @@ def group_probe():
             ref = a.float() @ bt.float().t()
             run(f"kmajor n={n} k={k}", a, bt, ref, n=n, k=k, b_box_rows=n, b_mn_major=0, b_lbo=16, b_sbo=1024,
                 b_k_step_bytes=32, b_kblock_bytes=n * 128, a_from_tmem=0)
-    # MN-major B: global [K, N] row-major (N contiguous) — V as stored [kv, hd]
+    # MN-major B: global [K, N] row-major (N contiguous) — V as stored [kv, hd]; boxes [k rows x 64 cols], one per
+    # 64-wide n block, sequential in smem => LBO (n-atom stride) = k*128 bytes, SBO (8-row k group stride) = 1024.
     for k in (64, 128):
         for n in (64, 128):
             a = torch.randn(128, k, device=dev).bfloat16()
             b = torch.randn(k, n, device=dev).bfloat16()  # [K, N]
             ref = a.float() @ b.float()
-            # boxes: [k rows x 64 cols], one per 64-wide n block, sequential in smem => n-atom stride = k*128 bytes
-            for lbo in (k * 128, 16, 1024):
-                for sbo in (1024, k * 128):
-                    run(f"mnmajor n={n} k={k} lbo={lbo} sbo={sbo}", a, b, ref, n=n, k=k, b_box_rows=k, b_mn_major=1,
-                        b_lbo=lbo, b_sbo=sbo, b_k_step_bytes=2048, b_kblock_bytes=8192, a_from_tmem=0)
+            run(f"mnmajor n={n} k={k}", a, b, ref, n=n, k=k, b_box_rows=k, b_mn_major=1, b_lbo=k * 128, b_sbo=1024,
+                b_k_step_bytes=2048, b_kblock_bytes=8192, a_from_tmem=0)
+
+
+def group_probe_ts():
+    import torch
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+
+    def run(name, a, b_glob, ref, **kw):
+        d = ops.debug_umma(a, b_glob, **kw)
+        torch.cuda.synchronize()
+        err = _rel_err(d, ref)
+        print(f"[probe] {name}: rel_err={err:.3e} {'OK' if err < 2e-2 else 'MISMATCH'}", flush=True)
+
     # A from TMEM (packed bf16 pairs), B K-major
     for k in (64, 128):
         for n in (64, 128):
