@@ -1,0 +1,387 @@
+"""B200FluxTransformer — drop-in for the reference `PyramidFluxTransformer` on the sampler hot path.
+
+Mirrors the call surface `PyramidDiTForVideoGeneration` uses (pyramid_dit/pyramid_dit_for_video_gen_pipeline.py:760-766):
+
+    dit(sample=[clips], timestep_ratio=t, encoder_hidden_states=e, encoder_attention_mask=m, pooled_projections=p)[0]
+
+plus `.config.in_channels`, `.parameters()`, `.device`, `.dtype`, `.to()`; weights are imported from a state-dict in the
+reference key layout.  The forward is a fixed sequence of libpf_b200 kernel launches on the current CUDA
+stream (no torch math on the path, no CPU fallback):
+
+  conditioning GEMVs -> all-layer AdaLN modulation GEMV -> embedders (GEMM, fp32 store into the joint residual stream)
+  8 x double block : LN+modulate pre-pass | QKV GEMM (+bias, RMSNorm, RoPE epilogue) | masked joint attention |
+                     out-proj GEMM (+gate*x+residual) | LN+modulate | FF1 GEMM (+GELU) | FF2 GEMM (+gate, residual)
+  16 x single block: LN+modulate | fused q|k|v|mlp GEMM (split epilogue) | attention | proj_out GEMM over [attn|mlp]
+  head             : LN+modulate (last-frame tokens only) | proj_out GEMM | unpatchify
+
+Data layout in HBM (B = CFG batch, S = text + all clip tokens, D = heads*64):
+  h    fp32 [B, S, D]      joint residual stream ([text ; clip_0 ; ... ; clip_n] per sample) — fp32 so that 48 residual
+                           adds do not accumulate bf16 rounding (the reference keeps it bf16)
+  xn   bf16 [B, S, D]      LN+modulated activations (GEMM A operand)
+  q,k,v bf16 [B, H, S, 64] head-major, written by the QKV epilogue, read by TMA in the attention kernel
+  cat  bf16 [B, S, 5D]     [attention out | MLP hidden] — proj_out of the single block reads it without a concat copy
+  mod  fp32 [B, N_mod]     every layer's (shift, scale, gate, ...) from ONE GEMV per step
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+from ._lib import (PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_QKV_GELU, PF_EPI_QKV_ROPE, PF_EPI_STORE_BF16,
+                   PF_EPI_STORE_F32)
+
+
+@dataclass
+class FluxConfigB200:
+    """Same fields as the reference model's `config` (modeling_pyramid_flux.py:80-96)."""
+    num_layers: int = 8
+    num_single_layers: int = 16
+    num_attention_heads: int = 30
+    attention_head_dim: int = 64
+    in_channels: int = 64
+    joint_attention_dim: int = 4096
+    pooled_projection_dim: int = 768
+    axes_dims_rope: Tuple[int, ...] = (16, 24, 24)
+    patch_size: int = 2
+
+    @property
+    def inner_dim(self) -> int:
+        return self.num_attention_heads * self.attention_head_dim
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# host-side sequence plan: ids, RoPE table, segment/time ids, attention tile schedule (cached per shape+mask)
+# ----------------------------------------------------------------------------------------------------------------------
+def _axis_positions(n: int, n_fine: int) -> torch.Tensor:
+    """Spatial positions of an n-wide clip on the finest clip's grid (reference: F.interpolate(arange, mode='linear'),
+    modeling_pyramid_flux.py:193-204)."""
+    if n == n_fine:
+        return torch.arange(n_fine, dtype=torch.float32)
+    return F.interpolate(torch.arange(n_fine, dtype=torch.float32)[None, None], n, mode="linear")[0, 0]
+
+
+def build_position_ids(clip_thw: Sequence[Tuple[int, int, int]], text_len: int) -> torch.Tensor:
+    """[S, 3] (time, y, x) ids for [text ; clips]; clip_thw are TOKEN grids (t, h/2, w/2) low-res -> high-res."""
+    hf, wf = clip_thw[-1][1], clip_thw[-1][2]
+    parts = [torch.zeros(text_len, 3)]
+    t0 = 0
+    for (t, h, w) in clip_thw:
+        ids = torch.zeros(t, h, w, 3)
+        ids[..., 0] = torch.arange(t0, t0 + t, dtype=torch.float32)[:, None, None]
+        ids[..., 1] = _axis_positions(h, hf)[None, :, None]
+        ids[..., 2] = _axis_positions(w, wf)[None, None, :]
+        parts.append(ids.reshape(-1, 3))
+        t0 += t
+    return torch.cat(parts, 0)
+
+
+def build_rope_table(ids: torch.Tensor, axes_dim: Sequence[int], theta: float = 10000.0) -> torch.Tensor:
+    """(cos, sin) per rotation pair, [S, sum(axes)/2, 2] fp32, angles in fp64 (reference rope(), F:28-41)."""
+    cols = []
+    for i, d in enumerate(axes_dim):
+        omega = 1.0 / (theta ** (torch.arange(0, d, 2, dtype=torch.float64) / d))
+        ang = ids[:, i].to(torch.float64)[:, None] * omega[None]
+        cols.append(torch.stack([ang.cos(), ang.sin()], -1))
+    return torch.cat(cols, 1).to(torch.float32).contiguous()
+
+
+@dataclass
+class SeqPlan:
+    text_len: int
+    video_len: int
+    seq: int
+    last_tokens: int          # tokens of the current (last) clip
+    clip_thw: Tuple[Tuple[int, int, int], ...]
+    rope: torch.Tensor        # device fp32 [S, 32, 2]
+    seg: torch.Tensor         # device int32 [B, S]
+    time: torch.Tensor        # device int32 [B, S]
+    sched: torch.Tensor       # device int32 [B, q_tiles, stride]
+    allowed_pairs: int        # sum over batch of allowed (q, kv) pairs (attention FLOP accounting)
+
+
+def build_seq_plan(clip_shapes: Sequence[Sequence[int]], mask_cpu: torch.Tensor, axes_dim, patch: int, device) -> SeqPlan:
+    b, text_len = mask_cpu.shape
+    clip_thw = tuple((int(s[-3]), int(s[-2]) // patch, int(s[-1]) // patch) for s in clip_shapes)
+    ids = build_position_ids(clip_thw, text_len)
+    video_len = sum(t * h * w for t, h, w in clip_thw)
+    seq = text_len + video_len
+    rope = build_rope_table(ids, axes_dim)
+    # segment id: sample index + 1 for valid tokens, 0 for padded text (reference F:318-330)
+    seg = torch.arange(1, b + 1, dtype=torch.int32)[:, None].repeat(1, seq)
+    seg[:, :text_len][mask_cpu == 0] = 0
+    time = ids[:, 0].to(torch.int32)[None].repeat(b, 1).contiguous()
+    sched, pairs = ops.attn_build_schedule(seg, time)
+    t, h, w = clip_thw[-1]
+    return SeqPlan(text_len, video_len, seq, t * h * w, clip_thw, rope.to(device), seg.to(device), time.to(device),
+                   sched.to(device), int(pairs.sum()))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+class B200FluxTransformer(torch.nn.Module):
+    """Holder of packed bf16 weights + the kernel-launch sequence of one DiT step."""
+
+    def __init__(self, config: FluxConfigB200, state_dict: Dict[str, torch.Tensor], device="cuda",
+                 emulate_bf16_rounding: bool = False):
+        super().__init__()
+        self.cfg = config
+        # True reproduces the reference's bf16 rounding of the sinusoidal projection (E:195); False keeps fp32
+        self.emulate_bf16_rounding = emulate_bf16_rounding
+        self.config = _Cfg(in_channels=config.in_channels, num_layers=config.num_layers,
+                           num_single_layers=config.num_single_layers,
+                           num_attention_heads=config.num_attention_heads,
+                           attention_head_dim=config.attention_head_dim,
+                           joint_attention_dim=config.joint_attention_dim,
+                           pooled_projection_dim=config.pooled_projection_dim)
+        assert config.attention_head_dim == 64, "kernels are specialised for head_dim 64"
+        self._plans: Dict[tuple, SeqPlan] = {}
+        self._ws: Dict[tuple, dict] = {}
+        self._import_state_dict(state_dict, torch.device(device))
+        self.last_plan: Optional[SeqPlan] = None
+        self._last_key = None
+        self.attn_events = None   # bench.py: list collecting (start, end) CUDA events around every attention launch
+
+    # -- weight import (reference key layout) -----------------------------------------------------------
+    def _import_state_dict(self, sd: Dict[str, torch.Tensor], device) -> None:
+        c = self.cfg
+        d = c.inner_dim
+
+        def W(*names):  # concatenated bf16 weight [sum(out), in]
+            return torch.cat([sd[n + ".weight"].float() for n in names], 0).to(device=device, dtype=torch.bfloat16).contiguous()
+
+        def Bv(*names):
+            return torch.cat([sd[n + ".bias"].float() for n in names], 0).to(device=device, dtype=torch.float32).contiguous()
+
+        def V(name):
+            return sd[name].float().to(device).contiguous()
+
+        reg = self.register_buffer
+        reg("w_t1", W("time_text_embed.timestep_embedder.linear_1")); reg("b_t1", Bv("time_text_embed.timestep_embedder.linear_1"))
+        reg("w_t2", W("time_text_embed.timestep_embedder.linear_2")); reg("b_t2", Bv("time_text_embed.timestep_embedder.linear_2"))
+        reg("w_p1", W("time_text_embed.text_embedder.linear_1")); reg("b_p1", Bv("time_text_embed.text_embedder.linear_1"))
+        reg("w_p2", W("time_text_embed.text_embedder.linear_2")); reg("b_p2", Bv("time_text_embed.text_embedder.linear_2"))
+        reg("w_ctx", W("context_embedder")); reg("b_ctx", Bv("context_embedder"))
+        reg("w_x", W("x_embedder")); reg("b_x", Bv("x_embedder"))
+        reg("w_out", W("proj_out")); reg("b_out", Bv("proj_out"))
+
+        # every AdaLN linear of the model, stacked: one GEMV per step
+        mod_names, self.mod_off = [], {}
+        off = 0
+        for i in range(c.num_layers):
+            for nm, k in ((f"transformer_blocks.{i}.norm1", 6), (f"transformer_blocks.{i}.norm1_context", 6)):
+                mod_names.append(nm + ".linear"); self.mod_off[nm] = off; off += k * d
+        for i in range(c.num_single_layers):
+            nm = f"single_transformer_blocks.{i}.norm"
+            mod_names.append(nm + ".linear"); self.mod_off[nm] = off; off += 3 * d
+        mod_names.append("norm_out.linear"); self.mod_off["norm_out"] = off; off += 2 * d
+        self.n_mod = off
+        reg("w_mod", W(*mod_names)); reg("b_mod", Bv(*mod_names))
+
+        self.dbl, self.sgl = [], []
+        for i in range(c.num_layers):
+            p = f"transformer_blocks.{i}"
+            blk = dict(
+                w_qkv=W(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"),
+                b_qkv=Bv(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"),
+                w_cqkv=W(p + ".attn.add_q_proj", p + ".attn.add_k_proj", p + ".attn.add_v_proj"),
+                b_cqkv=Bv(p + ".attn.add_q_proj", p + ".attn.add_k_proj", p + ".attn.add_v_proj"),
+                nq=V(p + ".attn.norm_q.weight"), nk=V(p + ".attn.norm_k.weight"),
+                cnq=V(p + ".attn.norm_added_q.weight"), cnk=V(p + ".attn.norm_added_k.weight"),
+                w_o=W(p + ".attn.to_out.0"), b_o=Bv(p + ".attn.to_out.0"),
+                w_co=W(p + ".attn.to_add_out"), b_co=Bv(p + ".attn.to_add_out"),
+                w_f1=W(p + ".ff.net.0.proj"), b_f1=Bv(p + ".ff.net.0.proj"),
+                w_f2=W(p + ".ff.net.2"), b_f2=Bv(p + ".ff.net.2"),
+                w_cf1=W(p + ".ff_context.net.0.proj"), b_cf1=Bv(p + ".ff_context.net.0.proj"),
+                w_cf2=W(p + ".ff_context.net.2"), b_cf2=Bv(p + ".ff_context.net.2"),
+            )
+            for k2, v2 in blk.items():
+                reg(f"dbl{i}_{k2}", v2)
+            self.dbl.append(blk)
+        for i in range(c.num_single_layers):
+            p = f"single_transformer_blocks.{i}"
+            blk = dict(
+                w_in=W(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v", p + ".proj_mlp"),
+                b_in=Bv(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v", p + ".proj_mlp"),
+                nq=V(p + ".attn.norm_q.weight"), nk=V(p + ".attn.norm_k.weight"),
+                w_out=W(p + ".proj_out"), b_out=Bv(p + ".proj_out"),
+            )
+            for k2, v2 in blk.items():
+                reg(f"sgl{i}_{k2}", v2)
+            self.sgl.append(blk)
+
+    @property
+    def device(self):
+        return self.w_x.device
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    def parameters(self, recurse: bool = True):  # the pipeline only asks next(self.dit.parameters()).device/.dtype
+        return iter([self.w_x])
+
+    # -- workspace -----------------------------------------------------------------------------------------------------
+    def _workspace(self, b: int, plan: SeqPlan) -> dict:
+        key = (b, plan.seq, plan.video_len, plan.last_tokens)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) >= 4:   # shapes change every unit/stage; keep the cache bounded
+                self._ws.clear()
+            c = self.cfg
+            d, hn, s, dev = c.inner_dim, c.num_attention_heads, plan.seq, self.device
+            ws = dict(
+                h=torch.empty(b, s, d, device=dev, dtype=torch.float32),
+                xn=torch.empty(b, s, d, device=dev, dtype=torch.bfloat16),
+                q=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
+                k=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
+                v=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
+                cat=torch.empty(b, s, 5 * d, device=dev, dtype=torch.bfloat16),
+                tok=torch.empty(b, plan.video_len, c.in_channels, device=dev, dtype=torch.bfloat16),
+                mod=torch.empty(b, self.n_mod, device=dev, dtype=torch.float32),
+                temb=torch.empty(b, d, device=dev, dtype=torch.float32),
+                tmp=torch.empty(b, d, device=dev, dtype=torch.float32),
+                head=torch.empty(b, plan.last_tokens, c.in_channels, device=dev, dtype=torch.float32),
+            )
+            self._ws[key] = ws
+        return ws
+
+    def plan_for(self, clip_shapes, mask: torch.Tensor) -> SeqPlan:
+        # fast path: same mask tensor (unchanged) and same clip shapes as the previous call -> no D2H sync
+        fast = (mask.data_ptr(), mask._version, tuple(mask.shape), tuple(tuple(int(x) for x in s) for s in clip_shapes))
+        if self._last_key is not None and self._last_key[0] == fast:
+            return self._last_key[1]
+        plan = self._plan_slow(clip_shapes, mask)
+        self._last_key = (fast, plan)
+        return plan
+
+    def _plan_slow(self, clip_shapes, mask: torch.Tensor) -> SeqPlan:
+        mask_cpu = mask.detach().to("cpu", torch.int64)
+        key = (tuple(tuple(int(x) for x in s) for s in clip_shapes), mask_cpu.shape, bytes(mask_cpu.numpy().tobytes()))
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 16:
+                self._plans.clear()
+            plan = build_seq_plan(clip_shapes, mask_cpu, self.cfg.axes_dims_rope, self.cfg.patch_size, self.device)
+            self._plans[key] = plan
+        return plan
+
+    # -- the step ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, sample, timestep_ratio=None, encoder_hidden_states=None, encoder_attention_mask=None,
+                pooled_projections=None):
+        _lib.require_device()
+        assert len(sample) == 1, "inference passes one stage per call (pipeline P:760-766)"
+        clips = sample[0] if isinstance(sample[0], (list, tuple)) else [sample[0]]
+        c = self.cfg
+        d, hn = c.inner_dim, c.num_attention_heads
+        b = clips[-1].shape[0]
+        plan = self.plan_for([cl.shape for cl in clips], encoder_attention_mask)
+        self.last_plan = plan
+        ws = self._workspace(b, plan)
+        t_len, s, lv = plan.text_len, plan.seq, plan.video_len
+        h, xn, q, k, v, cat, mod = ws["h"], ws["xn"], ws["q"], ws["k"], ws["v"], ws["cat"], ws["mod"]
+        nm = self.n_mod
+
+        # ---- conditioning (E:193-201): timestep arrives already rounded to bf16 by the pipeline (P:750)
+        t32 = timestep_ratio.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        tproj = ops.timestep_embedding(t32, 256, round_bf16=self.emulate_bf16_rounding)
+        ops.small_linear(tproj, self.w_t1, self.b_t1, ws["tmp"], act_out=1)
+        ops.small_linear(ws["tmp"], self.w_t2, self.b_t2, ws["temb"])
+        pooled = pooled_projections.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        ops.small_linear(pooled, self.w_p1, self.b_p1, ws["tmp"], act_out=1)
+        ops.small_linear(ws["tmp"], self.w_p2, self.b_p2, ws["temb"], accumulate=True)
+        # ---- every AdaLN modulation of the step in one GEMV: mod = Linear(SiLU(temb)) for all layers
+        ops.small_linear(ws["temb"], self.w_mod, self.b_mod, mod, act_in=1)
+
+        # ---- embedders write straight into the joint fp32 residual stream
+        enc = encoder_hidden_states.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        ops.gemm(enc, self.w_ctx, self.b_ctx, PF_EPI_STORE_F32, batches=b, rows_per_batch=t_len, row_begin=0,
+                 row_count=t_len, out=h, ldo=d, out_batch_rows=s, out_row_begin=0)
+        tok0 = 0
+        for cl, (ct, chh, cww) in zip(clips, plan.clip_thw):
+            cl = cl.detach()
+            if cl.dtype not in (torch.float32, torch.bfloat16):
+                cl = cl.float()
+            ops.patchify(cl.contiguous(), ws["tok"], lv, tok0)
+            tok0 += ct * chh * cww
+        ops.gemm(ws["tok"], self.w_x, self.b_x, PF_EPI_STORE_F32, batches=b, rows_per_batch=lv, row_begin=0,
+                 row_count=lv, out=h, ldo=d, out_batch_rows=s, out_row_begin=t_len)
+
+        def lnmod(off_shift, off_scale, r0, rc):
+            ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=s,
+                            row_begin=r0, row_count=rc)
+
+        def attention():
+            if self.attn_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, 1.0 / math.sqrt(64))
+                e1.record()
+                self.attn_events.append((e0, e1))
+            else:
+                ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, 1.0 / math.sqrt(64))
+
+        ranges = ((0, t_len), (t_len, lv))  # (row_begin, row_count): text, video
+        for i, w in enumerate(self.dbl):
+            ov = self.mod_off[f"transformer_blocks.{i}.norm1"]
+            oc = self.mod_off[f"transformer_blocks.{i}.norm1_context"]
+            offs = (oc, ov)
+            wq, bq, nq, nk = (w["w_cqkv"], w["w_qkv"]), (w["b_cqkv"], w["b_qkv"]), (w["cnq"], w["nq"]), (w["cnk"], w["nk"])
+            wo, bo = (w["w_co"], w["w_o"]), (w["b_co"], w["b_o"])
+            wf1, bf1 = (w["w_cf1"], w["w_f1"]), (w["b_cf1"], w["b_f1"])
+            wf2, bf2 = (w["w_cf2"], w["w_f2"]), (w["b_cf2"], w["b_f2"])
+            for j, (r0, rc) in enumerate(ranges):
+                lnmod(offs[j] + 0 * d, offs[j] + 1 * d, r0, rc)            # (shift_msa, scale_msa) N:173/191
+                ops.gemm(xn, wq[j], bq[j], PF_EPI_QKV_ROPE, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
+                         q_out=q, k_out=k, v_out=v, rope=plan.rope, q_norm_w=nq[j], k_norm_w=nk[j], heads=hn,
+                         head_dim=64, seq_len=s)
+            attention()
+            for j, (r0, rc) in enumerate(ranges):
+                ops.gemm(cat, wo[j], bo[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
+                         out=h, ldo=d, gate=mod[:, offs[j] + 2 * d:], gate_batch_stride=nm)      # gate_msa
+                lnmod(offs[j] + 3 * d, offs[j] + 4 * d, r0, rc)                                   # (shift_mlp, scale_mlp)
+                ops.gemm(xn, wf1[j], bf1[j], PF_EPI_GELU_BF16, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
+                         out=cat, ldo=5 * d, out_col_begin=d)
+                ops.gemm(cat[:, :, d:], wf2[j], bf2[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=r0,
+                         row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 5 * d:], gate_batch_stride=nm)  # gate_mlp
+
+        for i, w in enumerate(self.sgl):
+            o = self.mod_off[f"single_transformer_blocks.{i}.norm"]
+            lnmod(o, o + d, 0, s)                                                                  # (shift, scale) N:232
+            ops.gemm(xn, w["w_in"], w["b_in"], PF_EPI_QKV_GELU, batches=b, rows_per_batch=s, row_begin=0, row_count=s,
+                     out=cat, ldo=5 * d, out_col_begin=d, q_out=q, k_out=k, v_out=v, rope=plan.rope, q_norm_w=w["nq"],
+                     k_norm_w=w["nk"], heads=hn, head_dim=64, seq_len=s, n_split=3 * d)
+            attention()
+            ops.gemm(cat, w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=0,
+                     row_count=s, out=h, ldo=d, gate=mod[:, o + 2 * d:], gate_batch_stride=nm)
+
+        # ---- head: only the current clip's tokens are needed (F:380); AdaLN-continuous is (scale, shift) (N:119)
+        n_last = plan.last_tokens
+        o = self.mod_off["norm_out"]
+        lnmod(o + d, o, s - n_last, n_last)
+        ops.gemm(xn, self.w_out, self.b_out, PF_EPI_STORE_F32, batches=b, rows_per_batch=s, row_begin=s - n_last,
+                 row_count=n_last, out=ws["head"], ldo=c.in_channels, out_batch_rows=n_last, out_row_begin=0)
+        ct, chh, cww = plan.clip_thw[-1]
+        out = torch.empty(b, c.in_channels // 4, ct, chh * 2, cww * 2, device=self.device, dtype=clips[-1].dtype
+                          if clips[-1].dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        ops.unpatchify(ws["head"], n_last, 0, out)
+        return [out]
+
+    # accounting used by bench.py / DESIGN.md (SURVEY.md §8d "algorithmic work per unit")
+    def step_flops(self, b: int, plan: SeqPlan) -> Dict[str, float]:
+        c = self.cfg
+        d = c.inner_dim
+        per_tok = 24.0 * d * d
+        gemm = b * plan.seq * per_tok * (c.num_layers + c.num_single_layers)
+        gemm += 2.0 * b * (plan.video_len * c.in_channels * d + plan.text_len * c.joint_attention_dim * d +
+                           plan.last_tokens * d * c.in_channels)
+        attn = 4.0 * 64 * c.num_attention_heads * plan.allowed_pairs * (c.num_layers + c.num_single_layers)
+        return {"gemm": gemm, "attention": attn}

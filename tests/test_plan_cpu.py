@@ -1,0 +1,73 @@
+"""Host-side logic of the drop-in (no GPU): sequence plan vs the oracle's restatement of merge_input, C-ABI exports."""
+import re
+from pathlib import Path
+
+import torch
+
+from oracle import flux_oracle as FO
+from pyramid_flow_b200 import _lib, ops
+from pyramid_flow_b200.dit import build_position_ids, build_rope_table, build_seq_plan
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = (ROOT / "include" / "pf_b200.h").read_text()
+    declared = set(re.findall(r"PF_API\s+[\w\s\*]+?\b(pf_\w+)\s*\(", header))
+    assert declared, "no PF_API declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.pf_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        return
+    lib = _lib.load()
+    assert lib.pf_device_check() != 0
+    try:
+        _lib.require_device()
+    except RuntimeError as e:
+        assert "pf_device_check" in str(e)
+    else:
+        raise AssertionError("require_device must fail loudly without a GPU")
+
+
+def test_ids_and_rope_match_oracle():
+    shapes = [(2, 16, 3, 12, 20), (2, 16, 1, 24, 40), (2, 16, 1, 48, 80)]
+    ids_o = FO.sequence_ids(shapes, 128)
+    thw = [(s[2], s[3] // 2, s[4] // 2) for s in shapes]
+    ids = build_position_ids(thw, 128)
+    assert torch.equal(ids, ids_o)
+    # coarser clips sit at fractional positions of the finest grid (0.5, 2.5, ... at half resolution)
+    half = ids[128 + 3 * 6 * 10: 128 + 3 * 6 * 10 + 12 * 20].reshape(12, 20, 3)
+    assert half[0, 0, 1].item() == 0.5 and half[1, 0, 1].item() == 2.5 and half[0, 1, 2].item() == 2.5
+    assert torch.equal(build_rope_table(ids, (16, 24, 24)), FO.rope_table(ids_o, (16, 24, 24)))
+
+
+def test_plan_schedule_covers_exactly_the_allowed_pairs():
+    shapes = [(2, 16, 2, 12, 20), (2, 16, 1, 24, 40), (2, 16, 1, 48, 80)]
+    mask = torch.ones(2, 128, dtype=torch.long)
+    mask[0, 37:] = 0
+    plan = build_seq_plan(shapes, mask, (16, 24, 24), 2, "cpu")
+    seg_o = FO.token_segments(mask, plan.video_len)
+    ids_o = FO.sequence_ids(shapes, 128)
+    dense = FO.attention_mask(seg_o, ids_o[:, 0])[:, 0]
+    assert plan.allowed_pairs == int(dense.sum())
+    assert torch.equal(plan.seg.long(), seg_o)
+    # every allowed pair lies in a scheduled tile; every unflagged tile is fully allowed
+    b, s = plan.seg.shape
+    qt_n = (s + 127) // 128
+    for bi in range(b):
+        covered = torch.zeros(s, s, dtype=torch.bool)
+        for qt in range(qt_n):
+            row = plan.sched[bi, qt]
+            for e in row[1:1 + int(row[0])].tolist():
+                kt, flag = e >> 1, e & 1
+                q0, q1, k0, k1 = qt * 128, min(s, qt * 128 + 128), kt * 128, min(s, kt * 128 + 128)
+                covered[q0:q1, k0:k1] = True
+                if not flag:
+                    assert bool(dense[bi, q0:q1, k0:k1].all())
+        assert not bool((dense[bi] & ~covered).any())
