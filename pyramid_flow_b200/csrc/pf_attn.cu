@@ -49,6 +49,92 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// apply the element mask to 32 scores (bit i of `bits` = column i allowed)
+__device__ __forceinline__ void mask32(uint32_t (&v)[32], uint32_t bits) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (!((bits >> i) & 1u)) v[i] = 0xff800000u;  // -inf
+}
+
+// pass 1: row max over the 128 scores of this thread's row (two 64-column batches, 4 independent FMNMX3 chains)
+template <bool MASKED>
+__device__ __forceinline__ float tile_row_max(uint32_t t_s, const uint32_t (&allow)[4]) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_s + half * 64, va);
+    tmem_ld32(t_s + half * 64 + 32, vb);
+    tmem_ld_wait();
+    if (MASKED) {
+      mask32(va, allow[2 * half]);
+      mask32(vb, allow[2 * half + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      m0 = max3f(m0, __uint_as_float(va[i + 0]), __uint_as_float(va[i + 1]));
+      m1 = max3f(m1, __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
+      m2 = max3f(m2, __uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
+      m3 = max3f(m3, __uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      m0 = max3f(m0, __uint_as_float(vb[i + 0]), __uint_as_float(vb[i + 1]));
+      m1 = max3f(m1, __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
+      m2 = max3f(m2, __uint_as_float(vb[i + 4]), __uint_as_float(vb[i + 5]));
+      m3 = max3f(m3, __uint_as_float(vb[i + 6]), __uint_as_float(vb[i + 7]));
+    }
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// pass 2: p = exp2(s*c - m_ref) -> packed bf16 into TMEM P columns; returns the row sum (4 independent FADD chains)
+template <bool MASKED>
+__device__ __forceinline__ float tile_exp_store(uint32_t t_s, uint32_t t_p, const uint32_t (&allow)[4], float c,
+                                                float m_ref) {
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_s + half * 64, va);
+    tmem_ld32(t_s + half * 64 + 32, vb);
+    tmem_ld_wait();
+    if (MASKED) {
+      mask32(va, allow[2 * half]);
+      mask32(vb, allow[2 * half + 1]);
+    }
+    uint32_t pk[32];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float p0 = ex2f(fmaf(__uint_as_float(va[2 * i + 0]), c, -m_ref));
+      const float p1 = ex2f(fmaf(__uint_as_float(va[2 * i + 1]), c, -m_ref));
+      const float p2 = ex2f(fmaf(__uint_as_float(va[2 * i + 2]), c, -m_ref));
+      const float p3 = ex2f(fmaf(__uint_as_float(va[2 * i + 3]), c, -m_ref));
+      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+      pk[i] = pack_bf16x2(p0, p1);
+      pk[i + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float p0 = ex2f(fmaf(__uint_as_float(vb[2 * i + 0]), c, -m_ref));
+      const float p1 = ex2f(fmaf(__uint_as_float(vb[2 * i + 1]), c, -m_ref));
+      const float p2 = ex2f(fmaf(__uint_as_float(vb[2 * i + 2]), c, -m_ref));
+      const float p3 = ex2f(fmaf(__uint_as_float(vb[2 * i + 3]), c, -m_ref));
+      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+      pk[16 + i] = pack_bf16x2(p0, p1);
+      pk[16 + i + 1] = pack_bf16x2(p2, p3);
+    }
+    tmem_st32(t_p + half * 32, pk);
+  }
+  return (l0 + l1) + (l2 + l3);
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnArgs a) {
@@ -185,19 +271,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
 
       // ---- pass 1: row max over the tile
-      float m_tile = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        uint32_t v[32];
-        tmem_ld32(t_s + w * 32, v);
-        tmem_ld_wait();
-        const uint32_t bits = allow[w];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = ((bits >> i) & 1u) ? __uint_as_float(v[i]) : -INFINITY;
-          m_tile = fmaxf(m_tile, s);
-        }
-      }
+      const float m_tile = masked ? tile_row_max<true>(t_s, allow) : tile_row_max<false>(t_s, allow);
       // ---- lazy rescale decision (per row), correction is warp-collective
       const float m_cand = fmaxf(m_run, m_tile);
       float alpha = 1.f;
@@ -224,25 +298,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
 
       // ---- pass 2: p = exp2(s*c - m_ref), P -> TMEM (bf16x2), row sum
-      float l_tile = 0.f;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        uint32_t v[32];
-        tmem_ld32(t_s + w * 32, v);
-        tmem_ld_wait();
-        const uint32_t bits = allow[w];
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float s0 = ((bits >> (2 * i)) & 1u) ? __uint_as_float(v[2 * i]) : -INFINITY;
-          const float s1 = ((bits >> (2 * i + 1)) & 1u) ? __uint_as_float(v[2 * i + 1]) : -INFINITY;
-          const float p0 = ex2f(fmaf(s0, c, -m_ref));
-          const float p1 = ex2f(fmaf(s1, c, -m_ref));
-          l_tile += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(t_p + w * 16, pk);
-      }
+      const float l_tile = masked ? tile_exp_store<true>(t_s, t_p, allow, c, m_ref)
+                                  : tile_exp_store<false>(t_s, t_p, allow, c, m_ref);
       l_run += l_tile;
       tmem_st_wait();
       tc_fence_before();
