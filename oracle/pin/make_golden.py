@@ -115,6 +115,38 @@ def make_sched():
     print("sched:", out["start_sigmas"], out["end_sigmas"])
 
 
+VAE_SMALL = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=(2, 2, 2, 2))
+
+
+def make_vae():
+    """Tiny-width VAE decoder (all structural features: shortcut conv, spatial+temporal upsamplers, mid attention)."""
+    from video_vae import CausalVideoVAE
+    from oracle import vae_oracle as VO
+    cfg = VO.VaeDecoderConfig(**VAE_SMALL)
+    params = VO.synthetic_vae_params(cfg, seed=0)
+    vae = CausalVideoVAE(encoder_out_channels=16, decoder_in_channels=16, decoder_block_out_channels=cfg.block_out_channels,
+                         decoder_layers_per_block=cfg.layers_per_block).eval()
+    sd = vae.state_dict()
+    dec_keys = {k for k in sd if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
+    assert dec_keys == set(params.keys()), (dec_keys ^ set(params.keys()))
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    sd.update(params)
+    vae.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(1, 16, 3, 6, 10, generator=g)
+    with torch.no_grad():
+        full = vae.decode(z, temporal_chunk=False).sample
+        chunk1 = vae.decode(z, temporal_chunk=True, window_size=1).sample
+        chunk2 = vae.decode(z, temporal_chunk=True, window_size=2).sample
+        vae.enable_tiling()
+        tiled = vae.decode(z, temporal_chunk=True, window_size=1, tile_sample_min_size=32).sample
+    print("vae:", full.shape, float(full.abs().mean()), "chunk1 diff", float((full - chunk1).abs().max()),
+          "chunk2 diff", float((full - chunk2).abs().max()), "tiled diff", float((full - tiled).abs().max()))
+    torch.save({"cfg": VAE_SMALL, "param_seed": 0, "z": z, "full": full, "chunk1_maxdiff": float((full - chunk1).abs().max()),
+                "chunk2_maxdiff": float((full - chunk2).abs().max()), "tiled32": tiled}, GOLD / "vae_small.pt")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["flux", "block", "sched"]
     for w in which:

@@ -149,6 +149,17 @@ class B200FluxTransformer(torch.nn.Module):
         self._last_key = None
         self.attn_events = None   # bench.py: list collecting (start, end) CUDA events around every attention launch
 
+    @classmethod
+    def from_reference(cls, ref_module, device="cuda", **kw) -> "B200FluxTransformer":
+        """Build from a loaded reference `PyramidFluxTransformer` (its `.config` + `.state_dict()`)."""
+        rc = ref_module.config
+        cfg = FluxConfigB200(num_layers=rc.num_layers, num_single_layers=rc.num_single_layers,
+                             num_attention_heads=rc.num_attention_heads, attention_head_dim=rc.attention_head_dim,
+                             in_channels=rc.in_channels, joint_attention_dim=rc.joint_attention_dim,
+                             pooled_projection_dim=rc.pooled_projection_dim,
+                             axes_dims_rope=tuple(rc.axes_dims_rope))
+        return cls(cfg, ref_module.state_dict(), device=device, **kw)
+
     # -- weight import (reference key layout, SURVEY.md §8b) -----------------------------------------------------------
     def _import_state_dict(self, sd: Dict[str, torch.Tensor], device) -> None:
         c = self.cfg

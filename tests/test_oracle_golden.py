@@ -56,3 +56,19 @@ def test_mask_restatement_matches_dense_definition():
     assert m[1].tolist() == [False, True, True, False, False, False]
     assert m[5].tolist() == [False, True, True, True, True, True]
     assert m[0].tolist() == [True, False, False, False, False, False]
+
+
+def test_vae_decode_oracle_matches_reference(golden_dir):
+    from oracle import vae_oracle as VO
+    g = _load(golden_dir, "vae_small.pt")
+    cfg = VO.VaeDecoderConfig(**g["cfg"])
+    p = VO.synthetic_vae_params(cfg, seed=g["param_seed"])
+    with torch.no_grad():
+        out = VO.decode(p, cfg, g["z"])
+        tiled = VO.tiled_decode(p, cfg, g["z"], tile_sample_min_size=32)
+    assert out.shape == g["full"].shape == (1, 3, 17, 48, 80)
+    assert (out - g["full"]).abs().max().item() < 5e-5
+    # the reference's own temporal chunking (window 1 and 2) reproduces its un-chunked decode => one oracle serves both
+    assert g["chunk1_maxdiff"] < 1e-4 and g["chunk2_maxdiff"] < 1e-4
+    assert (tiled - g["tiled32"]).abs().max().item() < 5e-5
+    assert g["full"].abs().mean().item() > 0.05
