@@ -146,6 +146,51 @@ PF_API int pf_unpatchify(const float* x, int32_t rows_per_batch, int32_t row_beg
 PF_API int pf_cfg_euler_step(const float* v2, float guidance, float dsigma, const float* x, float* x_out, int64_t n,
                              void* stream);
 
+/* ------------------------------------------------------------------ causal 3-D convolution (VAE decode, tcgen05 + TMA)
+ * Replaces CausalConv3d -> nn.Conv3d (C:46-146), kernel 3x3x3 or 1x1x1, stride 1, on channels-last bf16 activations.
+ * x: [B, T + kt - 1, H, W, Cin]: the (kt-1) causal-padding frames are physically present in front (zeros for the first
+ * chunk, the previous chunk's last input frames afterwards = the reference's feature cache C:126-143); spatial zero
+ * padding is implicit (TMA out-of-bounds fill).  wgt: bf16 [Cout, kt*kh*kw*Cin], K index = tap*Cin + ci with
+ * tap = (dt*kh + dh)*kw + dw (re-laid out once at weight import).  Cin and Cout must be multiples of 64 (pad).
+ * store_mode: 0 plain [B, out_t_total, H, W, out_c] at frame t + out_t_offset (+ optional bf16 residual, R:148);
+ *             1 spatial depth-to-space 'b (c p1 p2) t h w -> b c t (h p1) (w p2)' (CausalUpsample2x R:616);
+ *             2 temporal depth-to-space 'b (c p) t h w -> b c (t p) h w' at frame 2t + p + out_t_offset, frames < 0
+ *               dropped (CausalTemporalUpsample2x R:724-727 with is_init_image => out_t_offset = -1).
+ */
+typedef struct pf_conv3d_desc {
+  const void* x;
+  int32_t b, t, h, w, cin; /* t = OUTPUT frames */
+  const void* wgt;
+  const float* bias; /* fp32 [cout] or NULL */
+  int32_t cout, kt, kh, kw;
+  int32_t store_mode;
+  void* out;
+  int32_t out_f32;
+  int32_t out_t_total, out_t_offset, out_c;
+  int32_t store_channels; /* first store_channels conv outputs are stored (the rest is filter padding) */
+  const void* residual;   /* bf16 [B, res_t_total, H, W, out_c] read at frame t + res_t_offset, plain mode only */
+  int32_t res_t_total, res_t_offset;
+} pf_conv3d_desc;
+PF_API int pf_causal_conv3d(const pf_conv3d_desc* desc, void* stream);
+
+/* per-frame GroupNorm (CausalGroupNorm C:36-43) on channels-last bf16 [frames, voxels, channels]:
+ * stats[frame, group] = (mean, rstd); workspace: >= frames * nsplit * channels * 2 floats (nsplit <= max(1, 2048/frames)). */
+PF_API int pf_groupnorm_stats(const void* x_bf16, int32_t frames, int64_t voxels, int32_t channels, int32_t groups,
+                              float eps, float* stats, float* workspace, int64_t workspace_floats, void* stream);
+/* y[b, t + y_t_offset, vox, c] = act((x[b, t, vox, c] - mean) * rstd * gamma[c] + beta[c]), act = SiLU if silu
+ * (R:127-129, R:139-141, D:362-363); y has y_t_total frames per batch (room for the next conv's causal halo). */
+PF_API int pf_groupnorm_apply(const void* x_bf16, void* y_bf16, int32_t b, int32_t t, int64_t voxels, int32_t channels,
+                              int32_t groups, const float* stats, const float* gamma, const float* beta, int32_t silu,
+                              int32_t y_t_total, int32_t y_t_offset, void* stream);
+/* in-place row softmax of bf16 scores [rows, ld]: softmax over the first `cols` columns of scale*s, zeros in the padding
+ * (mid-block attention, diffusers Attention used at K:454-460). */
+PF_API int pf_softmax_rows(void* s_bf16, int64_t rows, int32_t cols, int64_t ld, float scale, void* stream);
+/* latent [B, C, T, H, W] -> channels-last bf16 [B, y_t_total, H, W, cpad] at frame t + y_t_offset, channels >= C zero,
+ * optional per-frame affine z*scale[t] + shift[t] (decode_latent's un-normalisation, P:1226-1230). */
+PF_API int pf_pack_latent(const void* z, int32_t z_is_f32, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w,
+                          void* y_bf16, int32_t cpad, int32_t y_t_total, int32_t y_t_offset, const float* frame_scale,
+                          const float* frame_shift, void* stream);
+
 /* ------------------------------------------------------------------ debug probe (used only by tests/tools)
  * One CTA, one 128 x N x K tcgen05.mma chain with host-chosen descriptor bits, so descriptor encodings can be
  * pinned on hardware without recompiling.  a: bf16 [128, K] (K-major) or staged to TMEM when a_from_tmem;

@@ -19,6 +19,7 @@ SYMBOLS = [
     "pf_attn_build_schedule", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step",
+    "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent",
     "pf_debug_umma",
 ]
 
@@ -49,6 +50,20 @@ class AttnDesc(C.Structure):
         ("scale", C.c_float),
         ("seg", C.c_void_p), ("time", C.c_void_p), ("tile_sched", C.c_void_p),
         ("sched_stride", C.c_int32), ("variant", C.c_int32),
+    ]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("b", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32),
+        ("wgt", C.c_void_p), ("bias", C.c_void_p),
+        ("cout", C.c_int32), ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("store_mode", C.c_int32),
+        ("out", C.c_void_p), ("out_f32", C.c_int32),
+        ("out_t_total", C.c_int32), ("out_t_offset", C.c_int32), ("out_c", C.c_int32),
+        ("store_channels", C.c_int32),
+        ("residual", C.c_void_p), ("res_t_total", C.c_int32), ("res_t_offset", C.c_int32),
     ]
 
 
@@ -94,6 +109,14 @@ def load() -> C.CDLL:
                                   C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.pf_cfg_euler_step.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.pf_debug_umma.argtypes = [C.POINTER(UmmaProbe), C.c_void_p]
+    lib.pf_causal_conv3d.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
+    lib.pf_groupnorm_stats.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_void_p]
+    lib.pf_groupnorm_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.pf_softmax_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_float, C.c_void_p]
+    lib.pf_pack_latent.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -6,13 +6,15 @@
 // built at F:318-350).  The mask is never materialised: a host-built tile schedule (pf_attn_build_schedule) lists, per
 // 128-row q tile, only the 128-wide kv tiles that contain an allowed pair and flags the few that need an element mask.
 //
-// One CTA = one (batch, head, 128-row q tile); 192 threads; two CTAs are co-resident per SM so that one CTA's softmax
+// One CTA = one (batch, head, 128-row q tile); 320 threads; two CTAs are co-resident per SM so that one CTA's softmax
 // (MUFU-bound at head_dim 64) overlaps the other CTA's tensor-core work:
-//   warps 0-3  softmax: thread == q row == TMEM lane.  S is read from TMEM twice (max pass, exp pass), P is written
-//              back to TMEM as packed bf16, O is rescaled in TMEM only when the running max moved by > 2^8 (lazy rescale)
-//   warp 4     MMA issuer (one lane): S = Q.K^T (SS: both operands in smem, K-major), O += P.V (TS: P from TMEM,
+//   warps 0-7  softmax: thread == (q row == TMEM lane, 64-column half).  The thread's 64 scores are read from TMEM once
+//              and stay in registers for the FMNMX3 max pass and the ex2 pass; the two halves of a row exchange their
+//              partial max through shared memory (one named barrier per tile).  P is written back to TMEM as packed
+//              bf16; O is rescaled in TMEM only when the running max moved by > 2^8 (lazy rescale)
+//   warp 8     MMA issuer (one lane): S = Q.K^T (SS: both operands in smem, K-major), O += P.V (TS: P from TMEM,
 //              V from smem MN-major — V is consumed in its natural [kv, hd] layout, no transpose)
-//   warp 5     TMA producer (one lane): Q once, then K/V tiles through a 2-stage mbarrier ring
+//   warp 9     TMA producer (one lane): Q once, then K/V tiles through a 2-stage mbarrier ring
 // TMEM map (256 columns): S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256).
 #include <algorithm>
 #include <vector>
@@ -26,7 +28,8 @@ constexpr int ATT_BM = 128;      // q rows per CTA
 constexpr int ATT_BN = 128;      // kv columns per tile
 constexpr int ATT_HD = 64;
 constexpr int ATT_STAGES = 2;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_SOFTMAX_WARPS = 8;   // 2 warps per TMEM lane quarter: each owns 64 of the 128 kv columns of a row
+constexpr int ATT_THREADS = (ATT_SOFTMAX_WARPS + 2) * 32;
 constexpr int ATT_TILE_BYTES = ATT_BN * ATT_HD * 2;  // 16 KB
 constexpr int ATT_SMEM_BYTES = (1 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 256;
@@ -55,6 +58,10 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
   return r;
 }
 
+__device__ __forceinline__ void softmax_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(ATT_SOFTMAX_WARPS * 32) : "memory");
+}
+
 // apply the element mask to 32 scores (bit i of `bits` = column i allowed)
 __device__ __forceinline__ void mask32(uint32_t (&v)[32], uint32_t bits) {
 #pragma unroll
@@ -62,77 +69,30 @@ __device__ __forceinline__ void mask32(uint32_t (&v)[32], uint32_t bits) {
     if (!((bits >> i) & 1u)) v[i] = 0xff800000u;  // -inf
 }
 
-// pass 1: row max over the 128 scores of this thread's row (two 64-column batches, 4 independent FMNMX3 chains)
-template <bool MASKED>
-__device__ __forceinline__ float tile_row_max(uint32_t t_s, const uint32_t (&allow)[4]) {
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t va[32], vb[32];
-    tmem_ld32(t_s + half * 64, va);
-    tmem_ld32(t_s + half * 64 + 32, vb);
-    tmem_ld_wait();
-    if (MASKED) {
-      mask32(va, allow[2 * half]);
-      mask32(vb, allow[2 * half + 1]);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      m0 = max3f(m0, __uint_as_float(va[i + 0]), __uint_as_float(va[i + 1]));
-      m1 = max3f(m1, __uint_as_float(va[i + 2]), __uint_as_float(va[i + 3]));
-      m2 = max3f(m2, __uint_as_float(va[i + 4]), __uint_as_float(va[i + 5]));
-      m3 = max3f(m3, __uint_as_float(va[i + 6]), __uint_as_float(va[i + 7]));
-    }
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      m0 = max3f(m0, __uint_as_float(vb[i + 0]), __uint_as_float(vb[i + 1]));
-      m1 = max3f(m1, __uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3]));
-      m2 = max3f(m2, __uint_as_float(vb[i + 4]), __uint_as_float(vb[i + 5]));
-      m3 = max3f(m3, __uint_as_float(vb[i + 6]), __uint_as_float(vb[i + 7]));
-    }
+  for (int i = 0; i < 32; i += 8) {
+    m0 = max3f(m0, __uint_as_float(v[i + 0]), __uint_as_float(v[i + 1]));
+    m1 = max3f(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    m2 = max3f(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+    m3 = max3f(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
   }
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// pass 2: p = exp2(s*c - m_ref) -> packed bf16 into TMEM P columns; returns the row sum (4 independent FADD chains)
-template <bool MASKED>
-__device__ __forceinline__ float tile_exp_store(uint32_t t_s, uint32_t t_p, const uint32_t (&allow)[4], float c,
-                                                float m_ref) {
-  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+// p = exp2(s*c - m_ref) for 32 scores -> 16 packed bf16x2; accumulates the row sum into 4 independent chains
+__device__ __forceinline__ void exp32(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float m_ref, float (&l)[4]) {
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t va[32], vb[32];
-    tmem_ld32(t_s + half * 64, va);
-    tmem_ld32(t_s + half * 64 + 32, vb);
-    tmem_ld_wait();
-    if (MASKED) {
-      mask32(va, allow[2 * half]);
-      mask32(vb, allow[2 * half + 1]);
-    }
-    uint32_t pk[32];
-#pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float p0 = ex2f(fmaf(__uint_as_float(va[2 * i + 0]), c, -m_ref));
-      const float p1 = ex2f(fmaf(__uint_as_float(va[2 * i + 1]), c, -m_ref));
-      const float p2 = ex2f(fmaf(__uint_as_float(va[2 * i + 2]), c, -m_ref));
-      const float p3 = ex2f(fmaf(__uint_as_float(va[2 * i + 3]), c, -m_ref));
-      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-      pk[i] = pack_bf16x2(p0, p1);
-      pk[i + 1] = pack_bf16x2(p2, p3);
-    }
-#pragma unroll
-    for (int i = 0; i < 16; i += 2) {
-      const float p0 = ex2f(fmaf(__uint_as_float(vb[2 * i + 0]), c, -m_ref));
-      const float p1 = ex2f(fmaf(__uint_as_float(vb[2 * i + 1]), c, -m_ref));
-      const float p2 = ex2f(fmaf(__uint_as_float(vb[2 * i + 2]), c, -m_ref));
-      const float p3 = ex2f(fmaf(__uint_as_float(vb[2 * i + 3]), c, -m_ref));
-      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-      pk[16 + i] = pack_bf16x2(p0, p1);
-      pk[16 + i + 1] = pack_bf16x2(p2, p3);
-    }
-    tmem_st32(t_p + half * 32, pk);
+  for (int i = 0; i < 16; i += 2) {
+    const float p0 = ex2f(fmaf(__uint_as_float(v[2 * i + 0]), c, -m_ref));
+    const float p1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -m_ref));
+    const float p2 = ex2f(fmaf(__uint_as_float(v[2 * i + 2]), c, -m_ref));
+    const float p3 = ex2f(fmaf(__uint_as_float(v[2 * i + 3]), c, -m_ref));
+    l[0] += p0; l[1] += p1; l[2] += p2; l[3] += p3;
+    pk[i] = pack_bf16x2(p0, p1);
+    pk[i + 1] = pack_bf16x2(p2, p3);
   }
-  return (l0 + l1) + (l2 + l3);
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -146,6 +106,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_q, bar_s_full, bar_p_full, bar_final;
   __shared__ __align__(8) uint64_t kv_full[ATT_STAGES], kv_empty[ATT_STAGES];
   __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][2][ATT_BM];  // [tile parity][column half][row]: partial row max exchanged between paired warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,16 +117,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int bh = b * a.heads + h;
   const int* sched = a.sched + (static_cast<size_t>(b) * a.q_tiles + qt) * a.sched_stride;
   const int n_kv = sched[0];
+  constexpr int W_MMA = ATT_SOFTMAX_WARPS, W_TMA = ATT_SOFTMAX_WARPS + 1;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     mbar_init(&bar_q, 1);
     mbar_init(&bar_s_full, 1);
-    mbar_init(&bar_p_full, 128);
+    mbar_init(&bar_p_full, ATT_SOFTMAX_WARPS * 32);
     mbar_init(&bar_final, 1);
     for (int i = 0; i < ATT_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -182,97 +144,117 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 5 && lane == 0) {
-    // ===== TMA producer =====
-    mbar_arrive_expect_tx(&bar_q, ATT_TILE_BYTES);
-    tma_load_3d(smem_q, &tm_q, &bar_q, 0, qt * ATT_BM, bh);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      const int kt = sched[1 + j] >> 1;
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      uint8_t* sk = smem_kv + stage * 2 * ATT_TILE_BYTES;
-      mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-      tma_load_3d(sk, &tm_k, &kv_full[stage], 0, kt * ATT_BN, bh);
-      tma_load_3d(sk + ATT_TILE_BYTES, &tm_v, &kv_full[stage], 0, kt * ATT_BN, bh);
-      if (++stage == ATT_STAGES) {
-        stage = 0;
-        phase ^= 1;
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_arrive_expect_tx(&bar_q, ATT_TILE_BYTES);
+      tma_load_3d(smem_q, &tm_q, &bar_q, 0, qt * ATT_BM, bh);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const int kt = sched[1 + j] >> 1;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sk = smem_kv + stage * 2 * ATT_TILE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_3d(sk, &tm_k, &kv_full[stage], 0, kt * ATT_BN, bh);
+        tma_load_3d(sk + ATT_TILE_BYTES, &tm_v, &kv_full[stage], 0, kt * ATT_BN, bh);
+        if (++stage == ATT_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
-  } else if (warp == 4 && lane == 0) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // A = Q (K-major), B = K (K-major)
-    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, 0, 1);  // A = P (TMEM),    B = V (MN-major)
-    mbar_wait(&bar_q, 0);
-    const uint64_t dq = make_smem_desc_kmajor_sw128(smem_u32(smem_q));
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&kv_full[stage], phase);
-      tc_fence_after();
-      const uint32_t sk = smem_u32(smem_kv + stage * 2 * ATT_TILE_BYTES);
-      const uint64_t dk = make_smem_desc_kmajor_sw128(sk);
+  } else if (warp == W_MMA) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // A = Q (K-major), B = K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, 0, 1);  // A = P (TMEM),    B = V (MN-major)
+      mbar_wait(&bar_q, 0);
+      const uint64_t dq = make_smem_desc_kmajor_sw128(smem_u32(smem_q));
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&kv_full[stage], phase);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem_kv + stage * 2 * ATT_TILE_BYTES);
+        const uint64_t dk = make_smem_desc_kmajor_sw128(sk);
 #pragma unroll
-      for (int kk = 0; kk < ATT_HD / 16; ++kk) umma_ss(tmem_base + TM_S, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk != 0);
-      umma_commit(&bar_s_full);  // also covers P.V of the previous tile (commit tracks all prior MMAs)
-      mbar_wait(&bar_p_full, j & 1);
-      tc_fence_after();
-      // V tile [128 kv x 64 hd], 128-byte rows: MN-major, 8-row k groups 1024 B apart, 16 kv rows (2048 B) per MMA
-      const uint32_t sv = sk + ATT_TILE_BYTES;
+        for (int kk = 0; kk < ATT_HD / 16; ++kk)
+          umma_ss(tmem_base + TM_S, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk != 0);
+        umma_commit(&bar_s_full);  // also covers P.V of the previous tile (commit tracks all prior MMAs)
+        mbar_wait(&bar_p_full, j & 1);
+        tc_fence_after();
+        // V tile [128 kv x 64 hd], 128-byte rows: MN-major, 8-row k groups 1024 B apart, 16 kv rows (2048 B) per MMA
+        const uint32_t sv = sk + ATT_TILE_BYTES;
 #pragma unroll
-      for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-        const uint64_t dv = make_smem_desc(sv + kk * 2048, ATT_BN * 128, 1024);
-        umma_ts(tmem_base + TM_O, tmem_base + TM_P + kk * 8, dv, idesc_pv, (j | kk) != 0);
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+          const uint64_t dv = make_smem_desc(sv + kk * 2048, ATT_BN * 128, 1024);
+          umma_ts(tmem_base + TM_O, tmem_base + TM_P + kk * 8, dv, idesc_pv, (j | kk) != 0);
+        }
+        umma_commit(&kv_empty[stage]);
+        if (++stage == ATT_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
-      umma_commit(&kv_empty[stage]);
-      if (++stage == ATT_STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
+      umma_commit(&bar_final);
     }
-    umma_commit(&bar_final);
-  } else if (warp < 4) {
-    // ===== softmax + correction + epilogue =====
-    const int row = warp * 32 + lane;
+  } else {
+    // ===== softmax + correction + epilogue (8 warps; thread = (row, column half)) =====
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int row = quarter * 32 + lane;
     const int qpos = qt * ATT_BM + row;
     const bool q_valid = qpos < a.seq;
     const int seg_q = q_valid ? a.seg[static_cast<size_t>(b) * a.seq + qpos] : -0x7fffffff;
     const int time_q = q_valid ? a.time[static_cast<size_t>(b) * a.seq + qpos] : -0x7fffffff;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_base + TM_S;
-    const uint32_t t_o = tmem_base + lane_base + TM_O;
-    const uint32_t t_p = tmem_base + lane_base + TM_P;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + TM_S + half * 64;
+    const uint32_t t_o = tmem_base + lane_base + TM_O + half * 32;
+    const uint32_t t_p = tmem_base + lane_base + TM_P + half * 32;
     const float c = a.scale_log2;
-    float m_run = -INFINITY;  // running reference max (raw score units)
-    float l_run = 0.f;
+    float m_run = -INFINITY;  // running reference max (raw score units); identical in both column halves
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};  // this half's partial row sum (4 chains)
 
     for (int j = 0; j < n_kv; ++j) {
       const int entry = sched[1 + j];
       const int kt = entry >> 1;
       const bool masked = (entry & 1) != 0;
-      uint32_t allow[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      uint32_t allow0 = 0xffffffffu, allow1 = 0xffffffffu;
       if (masked) {
         const int* sg = a.seg + static_cast<size_t>(b) * a.seq;
         const int* tm = a.time + static_cast<size_t>(b) * a.seq;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          uint32_t bits = 0;
-          for (int i = 0; i < 32; ++i) {
-            const int kv = kt * ATT_BN + w * 32 + i;
-            bool ok = false;
-            if (kv < a.seq) ok = (__ldg(sg + kv) == seg_q) && (__ldg(tm + kv) <= time_q);
-            bits |= (ok ? 1u : 0u) << i;
-          }
-          allow[w] = bits;
+        uint32_t bits0 = 0, bits1 = 0;
+        for (int i = 0; i < 32; ++i) {
+          const int kv0 = kt * ATT_BN + half * 64 + i;
+          const int kv1 = kv0 + 32;
+          bool ok0 = false, ok1 = false;
+          if (kv0 < a.seq) ok0 = (__ldg(sg + kv0) == seg_q) && (__ldg(tm + kv0) <= time_q);
+          if (kv1 < a.seq) ok1 = (__ldg(sg + kv1) == seg_q) && (__ldg(tm + kv1) <= time_q);
+          bits0 |= (ok0 ? 1u : 0u) << i;
+          bits1 |= (ok1 ? 1u : 0u) << i;
         }
+        allow0 = bits0;
+        allow1 = bits1;
       }
       mbar_wait(&bar_s_full, j & 1);
       tc_fence_after();
 
-      // ---- pass 1: row max over the tile
-      const float m_tile = masked ? tile_row_max<true>(t_s, allow) : tile_row_max<false>(t_s, allow);
-      // ---- lazy rescale decision (per row), correction is warp-collective
+      // ---- this thread's 64 scores stay in registers for both the max and the exp
+      uint32_t va[32], vb[32];
+      tmem_ld32(t_s, va);
+      tmem_ld32(t_s + 32, vb);
+      tmem_ld_wait();
+      if (masked) {
+        mask32(va, allow0);
+        mask32(vb, allow1);
+      }
+      const float m_part = fmaxf(max32(va), max32(vb));
+      xch[j & 1][half][row] = m_part;
+      softmax_bar_sync();
+      const float m_tile = fmaxf(m_part, xch[j & 1][half ^ 1][row]);
+
+      // ---- lazy rescale decision (per row, same in both halves), correction is warp-collective
       const float m_cand = fmaxf(m_run, m_tile);
       float alpha = 1.f;
       bool need = false;
@@ -284,49 +266,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        uint32_t o[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tmem_ld32(t_o + half * 32, o);
+#pragma unroll 1
+        for (int cc = 0; cc < 32; cc += 16) {   // 16 columns at a time: the 64 scores stay live in registers
+          uint32_t o[16];
+          tmem_ld16(t_o + cc, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(t_o + half * 32, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(t_o + cc, o);
         }
       }
-      l_run *= alpha;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l4[i] *= alpha;
       const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
 
-      // ---- pass 2: p = exp2(s*c - m_ref), P -> TMEM (bf16x2), row sum
-      const float l_tile = masked ? tile_exp_store<true>(t_s, t_p, allow, c, m_ref)
-                                  : tile_exp_store<false>(t_s, t_p, allow, c, m_ref);
-      l_run += l_tile;
+      // ---- p = exp2(s*c - m_ref) -> P (bf16x2) in TMEM
+      uint32_t pk[16];
+      exp32(va, pk, c, m_ref, l4);
+      tmem_st16(t_p, pk);
+      exp32(vb, pk, c, m_ref, l4);
+      tmem_st16(t_p + 16, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_p_full);
     }
 
-    // ---- epilogue: O / l -> bf16 -> out[b, qpos, h*64 : h*64+64]
+    // ---- epilogue: combine the two halves' row sums, O / l -> bf16 -> out[b, qpos, h*64 + half*32 .. +32]
+    const float l_part = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    xch[n_kv & 1][half][row] = l_part;
+    softmax_bar_sync();
+    const float l_run = l_part + xch[n_kv & 1][half ^ 1][row];
     mbar_wait(&bar_final, 0);
     tc_fence_after();
     const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
-    __nv_bfloat16* dst = a.out + (static_cast<size_t>(b) * a.seq + qpos) * a.ldo + h * ATT_HD;
+    __nv_bfloat16* dst = a.out + (static_cast<size_t>(b) * a.seq + qpos) * a.ldo + h * ATT_HD + half * 32;
+    uint32_t o[32];
+    tmem_ld32(t_o, o);
+    tmem_ld_wait();
+    if (q_valid) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t o[32];
-      tmem_ld32(t_o + half * 32, o);
-      tmem_ld_wait();
-      if (q_valid) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + half * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          d4[i] = u;
-        }
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        d4[i] = u;
       }
     }
   }

@@ -1,0 +1,368 @@
+// pf_conv.cu — causal 3-D convolution (k = 3x3x3 or 1x1x1, stride 1) as an im2col-free implicit GEMM on tcgen05.
+//
+// Replaces CausalConv3d -> nn.Conv3d (reference video_vae/modeling_causal_conv.py:116-146, cuDNN conv3d on NCDHW) for
+// the VAE decoder.  Activations are channels-last bf16 [B, T, H, W, C]; an output tile is a TH x TW spatial patch of one
+// frame (128 voxels = the UMMA M), and the K loop walks (tap, 64-channel chunk):
+//   A tile  = ONE 5-D TMA box (64 ch, TW, TH, 1 frame, 1 batch) at the tap-shifted coordinate.  Out-of-bounds spatial
+//             coordinates are zero-filled by TMA => the conv's spatial zero padding costs nothing; the causal temporal
+//             padding is (kt-1) leading frames physically present in the input buffer (zeros for the first chunk, the
+//             previous chunk's last frames afterwards — the reference's feature cache, C:126-143).
+//   B tile  = weights re-laid out as [Cout, taps*Cin] (tap-major), a plain 2-D TMA box like the GEMM.
+// The box lands in shared memory as [TH][TW][64] = 128 rows of 128 B with SWIZZLE_128B, i.e. exactly the K-major UMMA
+// operand; no im2col buffer exists anywhere.  Pipeline / warp roles are the GEMM's (pf_gemm.cu).
+// Epilogue: bias (+ residual) -> bf16/fp32 channels-last store, optionally through the depth-to-space addressing of
+// CausalUpsample2x (R:616) / CausalTemporalUpsample2x (R:724-727) so the rearrange copy disappears.
+#include "../../include/pf_b200.h"
+#include "pf_common.cuh"
+
+namespace pf {
+
+struct ConvArgs {
+  int b, t, h, w, cin;
+  int cout;            // padded N actually computed (multiple of BN)
+  int taps, kt, kh, kw;
+  int th, tw, tiles_h, tiles_w;
+  int n_tiles;
+  const float* bias;
+  int store_mode;      // 0 plain, 1 spatial depth-to-space (c p1 p2), 2 temporal depth-to-space (c p)
+  void* out;
+  int out_f32;
+  int out_t_total, out_t_offset, out_h, out_w, out_c;   // geometry of the output buffer
+  int store_channels;  // channels of the conv output that are stored (<= cout; the rest is padding)
+  const __nv_bfloat16* residual;   // plain mode only; same geometry as out (bf16)
+  int res_t_total, res_t_offset;
+};
+
+constexpr int CBM = 128;
+constexpr int CBK = 64;
+constexpr int CONV_THREADS = 256;
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int A_BYTES = CBM * CBK * 2;
+  static constexpr int B_BYTES = BN * CBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const ConvArgs g) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int cchunks = g.cin / CBK;
+  const int num_kb = g.taps * cchunks;
+  // tile index -> (n tile fastest, then spatial tile, frame, batch): CTAs running together share the same input patch
+  const int sp_tiles = g.tiles_h * g.tiles_w;
+  const long long total_tiles = static_cast<long long>(g.b) * g.t * sp_tiles * g.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    const int ph = g.kh >> 1, pw = g.kw >> 1;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = static_cast<int>(tile % g.n_tiles);
+      long long r = tile / g.n_tiles;
+      const int sp = static_cast<int>(r % sp_tiles);
+      r /= sp_tiles;
+      const int tt = static_cast<int>(r % g.t);
+      const int bb = static_cast<int>(r / g.t);
+      const int h0 = (sp / g.tiles_w) * g.th, w0 = (sp % g.tiles_w) * g.tw;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / cchunks;
+        const int cc = kb - tap * cchunks;
+        const int dt = tap / (g.kh * g.kw);
+        const int rem = tap - dt * g.kh * g.kw;
+        const int dh = rem / g.kw, dw = rem - dh * g.kw;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        tma_load_5d(sa, &tm_x, &full_bar[stage], cc * CBK, w0 + dw - pw, h0 + dh - ph, tt + dt, bb);
+        tma_load_2d(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], kb * CBK, nt * BN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc_bf16(CBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc_kmajor_sw128(sa);
+        const uint64_t db = make_smem_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < CBK / 16; ++kk) umma_ss(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: thread == output voxel =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int rrow = q * 32 + lane;
+    const int lh = rrow / g.tw, lw = rrow - lh * g.tw;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = static_cast<int>(tile % g.n_tiles);
+      long long r = tile / g.n_tiles;
+      const int sp = static_cast<int>(r % sp_tiles);
+      r /= sp_tiles;
+      const int tt = static_cast<int>(r % g.t);
+      const int bb = static_cast<int>(r / g.t);
+      const int hh = (sp / g.tiles_w) * g.th + lh, ww = (sp % g.tiles_w) * g.tw + lw;
+      const bool valid = hh < g.h && ww < g.w;
+      const int n_base = nt * BN;
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        const int n0 = n_base + c * 16;
+        if (!valid || n0 >= g.store_channels) continue;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n0 + i) : 0.f);
+        if (g.store_mode == 0) {
+          const int to = tt + g.out_t_offset;
+          if (to < 0 || to >= g.out_t_total) continue;
+          const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + hh) * g.out_w + ww;
+          if (g.residual != nullptr) {
+            const size_t rvox = ((static_cast<size_t>(bb) * g.res_t_total + (tt + g.res_t_offset)) * g.out_h + hh) * g.out_w + ww;
+            const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + rvox * g.out_c + n0);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint4 rv = __ldg(r4 + u);
+              const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(hv[i]);
+                x[8 * u + 2 * i] += f.x;
+                x[8 * u + 2 * i + 1] += f.y;
+              }
+            }
+          }
+          const int nvalid = g.store_channels - n0;
+          if (g.out_f32) {
+            float* dst = reinterpret_cast<float*>(g.out) + vox * g.out_c + n0;
+            if (nvalid >= 16 && (g.out_c & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[i] = x[i];
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + vox * g.out_c + n0;
+            if (nvalid >= 16 && (g.out_c & 7) == 0) {
+              uint4 u0, u1;
+              u0.x = pack_bf16x2(x[0], x[1]); u0.y = pack_bf16x2(x[2], x[3]); u0.z = pack_bf16x2(x[4], x[5]); u0.w = pack_bf16x2(x[6], x[7]);
+              u1.x = pack_bf16x2(x[8], x[9]); u1.y = pack_bf16x2(x[10], x[11]); u1.z = pack_bf16x2(x[12], x[13]); u1.w = pack_bf16x2(x[14], x[15]);
+              reinterpret_cast<uint4*>(dst)[0] = u0;
+              reinterpret_cast<uint4*>(dst)[1] = u1;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[i] = __float2bfloat16(x[i]);
+            }
+          }
+        } else if (g.store_mode == 1) {
+          // 'b (c p1 p2) t h w -> b c t (h p1) (w p2)': conv channel n = 4c + 2 p1 + p2; 16 n = 4 output channels x 4 pixels
+          const int to = tt + g.out_t_offset;
+          if (to < 0 || to >= g.out_t_total) continue;
+          const int c0 = n0 >> 2;
+          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int p1 = p >> 1, p2 = p & 1;
+            const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + (2 * hh + p1)) * g.out_w + (2 * ww + p2);
+            uint2 u;
+            u.x = pack_bf16x2(x[0 + p], x[4 + p]);
+            u.y = pack_bf16x2(x[8 + p], x[12 + p]);
+            *reinterpret_cast<uint2*>(base + vox * g.out_c + c0) = u;
+          }
+        } else {
+          // 'b (c p) t h w -> b c (t p) h w': conv channel n = 2c + p; frame 2t + p (+offset; negative = dropped frame)
+          const int c0 = n0 >> 1;
+          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int to = 2 * tt + p + g.out_t_offset;
+            if (to < 0 || to >= g.out_t_total) continue;
+            const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + hh) * g.out_w + ww;
+            uint4 u;
+            u.x = pack_bf16x2(x[0 + p], x[2 + p]);
+            u.y = pack_bf16x2(x[4 + p], x[6 + p]);
+            u.z = pack_bf16x2(x[8 + p], x[10 + p]);
+            u.w = pack_bf16x2(x[12 + p], x[14 + p]);
+            *reinterpret_cast<uint4*>(base + vox * g.out_c + c0) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  auto kern = conv3d_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const long long total = static_cast<long long>(g.b) * g.t * g.tiles_h * g.tiles_w * g.n_tiles;
+  int grid = num_sms();
+  if (grid <= 0) grid = 148;
+  if (total < grid) grid = static_cast<int>(total);
+  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_x, tm_w, g);
+  return check_launch("pf_causal_conv3d");
+}
+
+}  // namespace pf
+
+extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
+  using namespace pf;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PF_REQUIRE(d && d->x && d->wgt && d->out, "pf_causal_conv3d: null pointer");
+  PF_REQUIRE(d->cin % 64 == 0 && d->cin > 0, "pf_causal_conv3d: cin=%d must be a multiple of 64 (pad the channels)", d->cin);
+  PF_REQUIRE(d->cout % 64 == 0 && d->cout > 0, "pf_causal_conv3d: cout=%d must be a multiple of 64 (pad the filters)", d->cout);
+  PF_REQUIRE((d->kt == 1 || d->kt == 3) && (d->kh == 1 || d->kh == 3) && d->kw == d->kh, "pf_causal_conv3d: kernel must be 1x1x1 or 3x3x3 (kt in {1,3})");
+  PF_REQUIRE(d->b > 0 && d->t > 0 && d->h > 0 && d->w > 0, "pf_causal_conv3d: bad shape");
+  PF_REQUIRE(d->store_mode >= 0 && d->store_mode <= 2, "pf_causal_conv3d: bad store_mode");
+  PF_REQUIRE(d->store_channels > 0 && d->store_channels <= d->cout, "pf_causal_conv3d: bad store_channels");
+  if (d->store_mode == 1) PF_REQUIRE(d->store_channels == d->cout && d->out_c * 4 == d->cout && !d->out_f32 && !d->residual, "pf_causal_conv3d: spatial depth-to-space needs out_c = cout/4, bf16, no residual");
+  if (d->store_mode == 2) PF_REQUIRE(d->store_channels == d->cout && d->out_c * 2 == d->cout && !d->out_f32 && !d->residual, "pf_causal_conv3d: temporal depth-to-space needs out_c = cout/2, bf16, no residual");
+  if (d->store_mode == 0) PF_REQUIRE(d->out_c >= d->store_channels, "pf_causal_conv3d: out_c < store_channels");
+
+  ConvArgs g{};
+  g.b = d->b; g.t = d->t; g.h = d->h; g.w = d->w; g.cin = d->cin; g.cout = d->cout;
+  g.kt = d->kt; g.kh = d->kh; g.kw = d->kw; g.taps = d->kt * d->kh * d->kw;
+  int tw = 128;
+  while (tw > 8 && tw / 2 >= d->w) tw >>= 1;   // smallest power of two >= w, clamped to [8, 128]
+  g.tw = tw; g.th = 128 / tw;
+  g.tiles_w = (d->w + g.tw - 1) / g.tw;
+  g.tiles_h = (d->h + g.th - 1) / g.th;
+  const int bn = (d->cout % 256 == 0) ? 256 : (d->cout % 128 == 0) ? 128 : 64;
+  g.n_tiles = d->cout / bn;
+  g.bias = d->bias;
+  g.store_mode = d->store_mode;
+  g.out = d->out; g.out_f32 = d->out_f32;
+  g.out_t_total = d->out_t_total; g.out_t_offset = d->out_t_offset;
+  g.out_h = d->store_mode == 1 ? 2 * d->h : d->h;
+  g.out_w = d->store_mode == 1 ? 2 * d->w : d->w;
+  g.out_c = d->out_c;
+  g.store_channels = d->store_channels;
+  g.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  g.res_t_total = d->res_t_total; g.res_t_offset = d->res_t_offset;
+
+  const int tin = d->t + d->kt - 1;
+  CUtensorMap tm_x, tm_w;
+  {
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->w), static_cast<uint64_t>(d->h),
+                              static_cast<uint64_t>(tin), static_cast<uint64_t>(d->b)};
+    const uint64_t s0 = static_cast<uint64_t>(d->cin) * 2;
+    const uint64_t strides[4] = {s0, s0 * d->w, s0 * d->w * d->h, s0 * d->w * d->h * tin};
+    const uint32_t box[5] = {CBK, static_cast<uint32_t>(g.tw), static_cast<uint32_t>(g.th), 1, 1};
+    int rc = encode_tensor_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->x, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t kdim = static_cast<uint64_t>(g.taps) * d->cin;
+    const uint64_t dims[2] = {kdim, static_cast<uint64_t>(d->cout)};
+    const uint64_t strides[1] = {kdim * 2};
+    const uint32_t box[2] = {CBK, static_cast<uint32_t>(bn)};
+    int rc = encode_tensor_map(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->wgt, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  switch (bn) {
+    case 256: return launch_conv<256>(tm_x, tm_w, g, stream);
+    case 128: return launch_conv<128>(tm_x, tm_w, g, stream);
+    default: return launch_conv<64>(tm_x, tm_w, g, stream);
+  }
+}

@@ -1,0 +1,364 @@
+"""B200CausalVAE — drop-in for the DECODE half of the reference `CausalVideoVAE` (video_vae/modeling_causal_vae.py).
+
+Call surface used by the pipeline (pyramid_dit_for_video_gen_pipeline.py:1221-1243):
+
+    self.vae.decode(latents, temporal_chunk=True, window_size=w, tile_sample_min_size=s).sample    # [B, 3, T', H', W']
+
+plus `.device`, `.dtype`, `.to()`, `.enable_tiling()`.  Weights come from a state-dict in the reference key layout
+(`decoder.*`, `post_quant_conv.*`).
+
+Execution model (all math in libpf_b200 kernels, channels-last bf16 activations `[T, H, W, C]`, batch handled one sample
+at a time as the pipeline does):
+  * every CausalConv3d  -> `pf_causal_conv3d` (tcgen05 implicit GEMM, TMA im2col-free, bias/residual/depth-to-space fused)
+  * every CausalGroupNorm(+SiLU) -> `pf_groupnorm_stats` + `pf_groupnorm_apply`, the apply writing straight into the next
+    conv's input buffer behind its 2-frame causal halo
+  * mid-block attention -> 1x1x1 convs for q/k/out, `pf_gemm_bf16` for V^T, QK^T and PV, `pf_softmax_rows`
+  * temporal chunking = the reference's feature cache (C:126-143): each 3x3x3 conv keeps the last two frames of its padded
+    input and they become the halo of the next chunk; chunking is exact, so the chunk length is a memory knob only.
+Spatial tiling (V:468-519) is reproduced by decoding tiles independently and cross-fading them (`tile_sample_min_size`),
+but on 180 GB the un-tiled path is the default unless `enable_tiling()` was called, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import ConvDesc, PF_EPI_STORE_BF16
+
+
+@dataclass
+class VaeConfigB200:
+    latent_channels: int = 16
+    out_channels: int = 3
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: Tuple[int, ...] = (3, 3, 3, 3)
+    spatial_up_sample: Tuple[bool, ...] = (True, True, True, False)
+    temporal_up_sample: Tuple[bool, ...] = (True, True, True, False)
+    norm_num_groups: int = 32
+    downsample_scale: int = 8
+
+
+class DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+class _Conv:
+    """One CausalConv3d: weights re-laid out to [Cout_pad, taps*Cin_pad] bf16 (tap-major), fp32 bias, halo cache."""
+
+    def __init__(self, sd, name: str, device):
+        w = sd[name + ".conv.weight"].float()
+        co, ci, kt, kh, kw = w.shape
+        self.cin, self.cout, self.kt, self.kh, self.kw = ci, co, kt, kh, kw
+        self.cin_p, self.cout_p = _pad64(ci), _pad64(co)
+        wp = torch.zeros(self.cout_p, kt, kh, kw, self.cin_p)
+        wp[:co, :, :, :, :ci] = w.permute(0, 2, 3, 4, 1)
+        self.w = wp.reshape(self.cout_p, kt * kh * kw * self.cin_p).to(device=device, dtype=torch.bfloat16).contiguous()
+        b = torch.zeros(self.cout_p)
+        if (name + ".conv.bias") in sd:
+            b[:co] = sd[name + ".conv.bias"].float()
+        self.bias = b.to(device)
+        self.cache: Optional[torch.Tensor] = None   # last (kt-1) frames of the previous chunk's padded input
+
+
+class B200CausalVAE(torch.nn.Module):
+    def __init__(self, config: VaeConfigB200, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        super().__init__()
+        self.cfg = config
+        self.use_tiling = False
+        self.decode_tile_overlap_factor = 0.25
+        dev = torch.device(device)
+        self._dev = dev
+        sd = state_dict
+        self.convs: Dict[str, _Conv] = {}
+        self.norms: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        for k in sd:
+            if k.endswith(".conv.weight") and (k.startswith("decoder.") or k.startswith("post_quant_conv.")):
+                name = k[: -len(".conv.weight")]
+                self.convs[name] = _Conv(sd, name, dev)
+        for k in sd:
+            if k.startswith("decoder.") and k.endswith(".weight") and sd[k].ndim == 1:
+                name = k[: -len(".weight")]
+                self.norms[name] = (sd[k].float().to(dev).contiguous(), sd[name + ".bias"].float().to(dev).contiguous())
+        # mid-block attention (diffusers Attention): q/k/out as 1x1x1 convs, v as a transposed GEMM
+        a = "decoder.mid_block.attentions.0"
+        c = sd[a + ".to_q.weight"].shape[0]
+        self.attn_c = c
+
+        def lin_as_conv(prefix, bias_override=None):
+            fake = {"x.conv.weight": sd[prefix + ".weight"].float().reshape(c, c, 1, 1, 1),
+                    "x.conv.bias": sd[prefix + ".bias"].float() if bias_override is None else bias_override}
+            return _Conv(fake, "x", dev)
+
+        self.attn_q = lin_as_conv(a + ".to_q")
+        self.attn_k = lin_as_conv(a + ".to_k")
+        wo, bo = sd[a + ".to_out.0.weight"].float(), sd[a + ".to_out.0.bias"].float()
+        bv = sd[a + ".to_v.bias"].float()
+        # softmax rows sum to 1 => P(V + 1 b_v^T) = PV + b_v^T: fold W_o b_v into the output bias
+        self.attn_o = lin_as_conv(a + ".to_out.0", bias_override=bo + wo @ bv)
+        self.attn_wv = sd[a + ".to_v.weight"].float().to(device=dev, dtype=torch.bfloat16).contiguous()
+        self.register_buffer("_anchor", torch.zeros(1, device=dev, dtype=torch.bfloat16))
+
+    @classmethod
+    def from_reference(cls, ref_vae, device="cuda") -> "B200CausalVAE":
+        rc = ref_vae.config
+        cfg = VaeConfigB200(latent_channels=rc.decoder_in_channels, out_channels=rc.decoder_out_channels,
+                            block_out_channels=tuple(rc.decoder_block_out_channels),
+                            layers_per_block=tuple(rc.decoder_layers_per_block),
+                            spatial_up_sample=tuple(rc.decoder_spatial_up_sample),
+                            temporal_up_sample=tuple(rc.decoder_temporal_up_sample),
+                            norm_num_groups=rc.decoder_norm_num_groups, downsample_scale=rc.downsample_scale)
+        return cls(cfg, ref_vae.state_dict(), device=device)
+
+    @property
+    def device(self):
+        return self._anchor.device
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    def enable_tiling(self, use_tiling: bool = True):
+        self.use_tiling = use_tiling
+
+    def disable_tiling(self):
+        self.use_tiling = False
+
+    # ---- kernel wrappers (single sample: tensors are [T, H, W, C]) ---------------------------------------------------
+    def _conv(self, cv: _Conv, x: torch.Tensor, t: int, h: int, w: int, *, out: torch.Tensor, out_t_offset: int = 0,
+              store_mode: int = 0, residual: Optional[torch.Tensor] = None, res_t_offset: int = 0,
+              store_channels: Optional[int] = None, out_f32: bool = False) -> None:
+        """x: [t + kt - 1, h, w, cin_p] (halo frames first); out: [out_t_total, H', W', out_c]."""
+        assert x.is_contiguous() and out.is_contiguous() and x.shape[-1] == cv.cin_p and x.shape[0] == t + cv.kt - 1
+        d = ConvDesc()
+        d.x = x.data_ptr()
+        d.b, d.t, d.h, d.w, d.cin = 1, t, h, w, cv.cin_p
+        d.wgt, d.bias = cv.w.data_ptr(), cv.bias.data_ptr()
+        d.cout, d.kt, d.kh, d.kw = cv.cout_p, cv.kt, cv.kh, cv.kw
+        d.store_mode = store_mode
+        d.out, d.out_f32 = out.data_ptr(), int(out_f32)
+        d.out_t_total, d.out_t_offset, d.out_c = out.shape[0], out_t_offset, out.shape[-1]
+        d.store_channels = store_channels if store_channels is not None else cv.cout_p
+        if residual is not None:
+            d.residual, d.res_t_total, d.res_t_offset = residual.data_ptr(), residual.shape[0], res_t_offset
+        _lib.check(_lib.load().pf_causal_conv3d(C.byref(d), _lib.stream_ptr()), "pf_causal_conv3d")
+
+    def _halo(self, cv: _Conv, buf: torch.Tensor, first: bool) -> None:
+        """Fill the 2 leading frames of a 3x3x3 conv's input buffer from its cache (zeros for the first chunk) and
+        remember the last 2 frames of the padded input for the next chunk (reference C:126-143)."""
+        if cv.kt == 1:
+            return
+        if first or cv.cache is None:
+            buf[:2].zero_()
+        else:
+            buf[:2].copy_(cv.cache)
+        cv.cache = buf[-2:].clone()
+
+    def _gn(self, name: str, x: torch.Tensor, y: torch.Tensor, y_t_offset: int, silu: bool) -> None:
+        """x [T, H, W, C] -> y [Ty, H, W, C] frames [y_t_offset, y_t_offset + T)."""
+        t, h, w, c = x.shape
+        groups = self.cfg.norm_num_groups
+        stats = torch.empty(t, groups, 2, device=x.device, dtype=torch.float32)
+        nsplit_cap = max(1, (2048 + t - 1) // t)
+        ws = torch.empty(t * nsplit_cap * c * 2, device=x.device, dtype=torch.float32)
+        lib = _lib.load()
+        _lib.check(lib.pf_groupnorm_stats(x.data_ptr(), t, h * w, c, groups, 1e-6, stats.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), _lib.stream_ptr()), "pf_groupnorm_stats")
+        g, b = self.norms[name]
+        _lib.check(lib.pf_groupnorm_apply(x.data_ptr(), y.data_ptr(), 1, t, h * w, c, groups, stats.data_ptr(),
+                                          g.data_ptr(), b.data_ptr(), int(silu), y.shape[0], y_t_offset,
+                                          _lib.stream_ptr()), "pf_groupnorm_apply")
+
+    def _resnet(self, pre: str, x: torch.Tensor, first: bool, halo_out: bool = False) -> torch.Tensor:
+        """CausalResnetBlock3D (R:115-150). x: [T, H, W, Cin] view; returns [T(+2 if halo_out), H, W, Cout]."""
+        t, h, w, cin = x.shape
+        c1, c2 = self.convs[pre + ".conv1"], self.convs[pre + ".conv2"]
+        dev = x.device
+        a = torch.empty(t + 2, h, w, cin, device=dev, dtype=torch.bfloat16)
+        self._gn(pre + ".norm1", x, a, 2, True)
+        self._halo(c1, a, first)
+        h1 = torch.empty(t, h, w, c1.cout_p, device=dev, dtype=torch.bfloat16)
+        self._conv(c1, a, t, h, w, out=h1)
+        del a
+        bbuf = torch.empty(t + 2, h, w, c1.cout_p, device=dev, dtype=torch.bfloat16)
+        self._gn(pre + ".norm2", h1, bbuf, 2, True)
+        del h1
+        self._halo(c2, bbuf, first)
+        if (pre + ".conv_shortcut") in self.convs:
+            sc_cv = self.convs[pre + ".conv_shortcut"]
+            sc = torch.empty(t, h, w, sc_cv.cout_p, device=dev, dtype=torch.bfloat16)
+            self._conv(sc_cv, x.contiguous(), t, h, w, out=sc)
+        else:
+            sc = x
+        off = 2 if halo_out else 0
+        out = torch.empty(t + off, h, w, c2.cout_p, device=dev, dtype=torch.bfloat16)
+        # `sc` may be a contiguous view into a halo'd buffer: its data_ptr already points at the first data frame
+        self._conv(c2, bbuf, t, h, w, out=out, out_t_offset=off, residual=sc, res_t_offset=0)
+        return out
+
+    def _mid_attention(self, x: torch.Tensor) -> torch.Tensor:
+        """Per-frame single-head attention over the h*w tokens (K:454-460 + diffusers Attention). x [T, H, W, C]."""
+        t, h, w, c = x.shape
+        dev = x.device
+        n = h * w
+        npad = _pad64(n)
+        slack = 128
+        xn = torch.zeros(t * n + slack, c, device=dev, dtype=torch.bfloat16)
+        self._gn("decoder.mid_block.attentions.0.group_norm", x, xn[: t * n].view(t, h, w, c), 0, False)
+        q = torch.empty(t, h, w, c, device=dev, dtype=torch.bfloat16)
+        k = torch.zeros(t * n + slack, c, device=dev, dtype=torch.bfloat16)
+        self._conv(self.attn_q, xn[: t * n].view(t, h, w, c), t, h, w, out=q)
+        self._conv(self.attn_k, xn[: t * n].view(t, h, w, c), t, h, w, out=k[: t * n].view(t, h, w, c))
+        o = torch.empty(t, h, w, c, device=dev, dtype=torch.bfloat16)
+        vt = torch.empty(c, npad, device=dev, dtype=torch.bfloat16)
+        s = torch.empty(n, npad, device=dev, dtype=torch.bfloat16)
+        qf, of = q.view(t, n, c), o.view(t, n, c)
+        for f in range(t):
+            xf = xn[f * n: f * n + npad]          # rows beyond n are the next frame / zero slack: finite, masked below
+            kf = k[f * n: f * n + npad]
+            ops.gemm(self.attn_wv, xf, None, PF_EPI_STORE_BF16, rows_per_batch=c, out=vt)       # V^T [C, npad]
+            ops.gemm(qf[f], kf, None, PF_EPI_STORE_BF16, rows_per_batch=n, out=s)               # S = Q K^T
+            _lib.check(_lib.load().pf_softmax_rows(s.data_ptr(), n, n, npad, float(c) ** -0.5, _lib.stream_ptr()),
+                       "pf_softmax_rows")
+            ops.gemm(s, vt, None, PF_EPI_STORE_BF16, rows_per_batch=n, out=of[f])               # O = P V
+        out = torch.empty(t, h, w, c, device=dev, dtype=torch.bfloat16)
+        self._conv(self.attn_o, o, t, h, w, out=out, residual=x, res_t_offset=0)
+        return out
+
+    def _reset_caches(self):
+        for cv in self.convs.values():
+            cv.cache = None
+
+    def _decode_chunk(self, z: torch.Tensor, first: bool) -> torch.Tensor:
+        """z: latent frames [1, C, T, h, w] of ONE chunk -> fp32 [T', 8h, 8w, 3]."""
+        cfg = self.cfg
+        dev = self.device
+        _, cl, t, h, w = z.shape
+        pq, cin = self.convs["post_quant_conv"], self.convs["decoder.conv_in"]
+        zin = torch.empty(t, h, w, pq.cin_p, device=dev, dtype=torch.bfloat16)
+        zz = z if z.dtype in (torch.float32, torch.bfloat16) else z.float()
+        _lib.check(_lib.load().pf_pack_latent(zz.contiguous().data_ptr(), int(zz.dtype == torch.float32), 1, cl, t, h, w,
+                                              zin.data_ptr(), pq.cin_p, t, 0, None, None, _lib.stream_ptr()), "pf_pack_latent")
+        a = torch.empty(t + 2, h, w, cin.cin_p, device=dev, dtype=torch.bfloat16)
+        self._conv(pq, zin, t, h, w, out=a, out_t_offset=2)                      # post_quant_conv (1x1x1), V:365/368
+        self._halo(cin, a, first)
+        x = torch.empty(t, h, w, cin.cout_p, device=dev, dtype=torch.bfloat16)
+        self._conv(cin, a, t, h, w, out=x)                                       # conv_in, D:310
+        x = self._resnet("decoder.mid_block.resnets.0", x, first)
+        x = self._mid_attention(x)
+        x = self._resnet("decoder.mid_block.resnets.1", x, first)
+        n_blocks = len(cfg.block_out_channels)
+        for i in range(n_blocks):
+            xb = None
+            has_up = cfg.spatial_up_sample[i] or cfg.temporal_up_sample[i]
+            for j in range(cfg.layers_per_block[i]):
+                last = j == cfg.layers_per_block[i] - 1
+                x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x, first, halo_out=last and has_up)
+                if last and has_up:
+                    xb = x               # [t+2, h, w, c]: data in frames [2:]
+            if cfg.spatial_up_sample[i]:
+                cv = self.convs[f"decoder.up_blocks.{i}.upsamplers.0.conv"]
+                self._halo(cv, xb, first)
+                off = 2 if cfg.temporal_up_sample[i] else 0
+                y = torch.empty(t + off, 2 * h, 2 * w, cv.cout_p // 4, device=dev, dtype=torch.bfloat16)
+                self._conv(cv, xb, t, h, w, out=y, out_t_offset=off, store_mode=1)
+                h, w = 2 * h, 2 * w
+                xb = y
+                x = y[off:]
+            if cfg.temporal_up_sample[i]:
+                cv = self.convs[f"decoder.up_blocks.{i}.temporal_upsamplers.0.conv"]
+                self._halo(cv, xb, first)
+                t_out = 2 * t - 1 if first else 2 * t
+                y = torch.empty(t_out, h, w, cv.cout_p // 2, device=dev, dtype=torch.bfloat16)
+                self._conv(cv, xb, t, h, w, out=y, out_t_offset=-1 if first else 0, store_mode=2)
+                t = t_out
+                x = y
+        co = self.convs["decoder.conv_out"]
+        a = torch.empty(t + 2, h, w, x.shape[-1], device=dev, dtype=torch.bfloat16)
+        self._gn("decoder.conv_norm_out", x, a, 2, True)
+        self._halo(co, a, first)
+        out = torch.empty(t, h, w, cfg.out_channels, device=dev, dtype=torch.float32)
+        self._conv(co, a, t, h, w, out=out, store_channels=cfg.out_channels, out_f32=True)
+        return out
+
+    def _decode_sample(self, z: torch.Tensor, window_size: int) -> torch.Tensor:
+        """chunk_decode (V:346-374) for one sample: first chunk window+1 latent frames, then `window` each."""
+        self._reset_caches()
+        n = z.shape[2]
+        init = min(n, window_size + 1)
+        bounds = [(0, init)]
+        f = init
+        while f < n:
+            bounds.append((f, min(n, f + window_size)))
+            f += window_size
+        outs = [self._decode_chunk(z[:, :, a:b], i == 0) for i, (a, b) in enumerate(bounds)]
+        self._reset_caches()
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, is_init_image: bool = True, temporal_chunk: bool = False, return_dict: bool = True,
+               window_size: int = 2, tile_sample_min_size: int = 256):
+        _lib.require_device()
+        assert is_init_image, "the sampler always decodes clips that start with the image frame"
+        z = z.to(self.device)
+        tile_latent = int(tile_sample_min_size / self.cfg.downsample_scale)
+        if self.use_tiling and (z.shape[-1] > tile_latent or z.shape[-2] > tile_latent):
+            dec = self._tiled_decode(z, window_size if temporal_chunk else z.shape[2], tile_sample_min_size)
+        else:
+            w = window_size if temporal_chunk else z.shape[2]
+            outs = [self._decode_sample(z[i:i + 1], w) for i in range(z.shape[0])]
+            dec = torch.stack(outs, 0).permute(0, 4, 1, 2, 3)      # [B, T, H, W, 3] -> view as [B, 3, T, H, W]
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(dec)
+
+    def _tiled_decode(self, z: torch.Tensor, window: int, tile_sample_min_size: int) -> torch.Tensor:
+        """tiled_decode (V:468-519): independent tiles, linear cross-fade with the tile above and to the left."""
+        tile_latent = int(tile_sample_min_size / self.cfg.downsample_scale)
+        overlap = int(tile_latent * (1 - self.decode_tile_overlap_factor))
+        extent = int(tile_sample_min_size * self.decode_tile_overlap_factor)
+        limit = tile_sample_min_size - extent
+        rows = []
+        for i in range(0, z.shape[3], overlap):
+            row = []
+            for j in range(0, z.shape[4], overlap):
+                tile = z[:, :, :, i:i + tile_latent, j:j + tile_latent]
+                outs = [self._decode_sample(tile[b:b + 1].contiguous(), window) for b in range(z.shape[0])]
+                row.append(torch.stack(outs, 0).permute(0, 4, 1, 2, 3).contiguous())
+            rows.append(row)
+        result_rows = []
+        for i, row in enumerate(rows):
+            res = []
+            for j, tile in enumerate(row):
+                if i > 0:
+                    tile = _blend(rows[i - 1][j], tile, extent, 3)
+                if j > 0:
+                    tile = _blend(row[j - 1], tile, extent, 4)
+                res.append(tile[:, :, :, :limit, :limit])
+            result_rows.append(torch.cat(res, dim=4))
+        return torch.cat(result_rows, dim=3)
+
+
+def _blend(a: torch.Tensor, b: torch.Tensor, extent: int, dim: int) -> torch.Tensor:
+    """blend_v / blend_h (V:397-407) vectorised: b[..., y, ...] = a[..., -extent+y, ...]*(1-y/extent) + b*(y/extent)."""
+    extent = min(a.shape[dim], b.shape[dim], extent)
+    if extent <= 0:
+        return b
+    wgt = (torch.arange(extent, device=b.device, dtype=b.dtype) / extent)
+    shape = [1] * b.ndim
+    shape[dim] = extent
+    wgt = wgt.view(shape)
+    sl_b = [slice(None)] * b.ndim
+    sl_b[dim] = slice(0, extent)
+    sl_a = [slice(None)] * a.ndim
+    sl_a[dim] = slice(a.shape[dim] - extent, a.shape[dim])
+    b[tuple(sl_b)] = a[tuple(sl_a)] * (1 - wgt) + b[tuple(sl_b)] * wgt
+    return b
