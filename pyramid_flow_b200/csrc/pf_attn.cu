@@ -14,7 +14,9 @@
 //              bf16; O is rescaled in TMEM only when the running max moved by > 2^8 (lazy rescale)
 //   warp 8     MMA issuer (one lane): S = Q.K^T (SS: both operands in smem, K-major), O += P.V (TS: P from TMEM,
 //              V from smem MN-major — V is consumed in its natural [kv, hd] layout, no transpose)
-//   warp 9     TMA producer (one lane): Q once, then K/V tiles through a 2-stage mbarrier ring
+//   warp 9     TMA producer (one lane): Q once, then K tiles through a 3-stage and V tiles through a 2-stage mbarrier ring
+// S(j+1) = Q.K(j+1)^T is issued as soon as softmax(j) has pulled S(j) into registers, so the tensor pipe works under the
+// softmax instead of after it.
 // TMEM map (256 columns): S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256).
 #include <algorithm>
 #include <vector>
@@ -27,11 +29,12 @@ namespace pf {
 constexpr int ATT_BM = 128;      // q rows per CTA
 constexpr int ATT_BN = 128;      // kv columns per tile
 constexpr int ATT_HD = 64;
-constexpr int ATT_STAGES = 2;
+constexpr int ATT_KSTAGES = 3;   // K is consumed one tile ahead (S(j+1) is issued during softmax(j)): deeper ring
+constexpr int ATT_VSTAGES = 2;
 constexpr int ATT_SOFTMAX_WARPS = 8;   // 2 warps per TMEM lane quarter: each owns 64 of the 128 kv columns of a row
 constexpr int ATT_THREADS = (ATT_SOFTMAX_WARPS + 2) * 32;
 constexpr int ATT_TILE_BYTES = ATT_BN * ATT_HD * 2;  // 16 KB
-constexpr int ATT_SMEM_BYTES = (1 + 2 * ATT_STAGES) * ATT_TILE_BYTES + 1024;
+constexpr int ATT_SMEM_BYTES = (1 + ATT_KSTAGES + ATT_VSTAGES) * ATT_TILE_BYTES + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192;
 
@@ -101,10 +104,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
-  uint8_t* smem_kv = smem + ATT_TILE_BYTES;  // stage s: K at s*32K, V at s*32K + 16K
+  uint8_t* smem_k = smem + ATT_TILE_BYTES;
+  uint8_t* smem_v = smem_k + ATT_KSTAGES * ATT_TILE_BYTES;
 
-  __shared__ __align__(8) uint64_t bar_q, bar_s_full, bar_p_full, bar_final;
-  __shared__ __align__(8) uint64_t kv_full[ATT_STAGES], kv_empty[ATT_STAGES];
+  __shared__ __align__(8) uint64_t bar_q, bar_s_full, bar_s_free, bar_p_full, bar_pv_done;
+  __shared__ __align__(8) uint64_t k_full[ATT_KSTAGES], k_empty[ATT_KSTAGES], v_full[ATT_VSTAGES], v_empty[ATT_VSTAGES];
   __shared__ uint32_t tmem_slot;
   __shared__ float xch[2][2][ATT_BM];  // [tile parity][column half][row]: partial row max exchanged between paired warps
 
@@ -127,11 +131,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == W_MMA && lane == 0) {
     mbar_init(&bar_q, 1);
     mbar_init(&bar_s_full, 1);
+    mbar_init(&bar_s_free, ATT_SOFTMAX_WARPS * 32);
     mbar_init(&bar_p_full, ATT_SOFTMAX_WARPS * 32);
-    mbar_init(&bar_final, 1);
-    for (int i = 0; i < ATT_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+    mbar_init(&bar_pv_done, 1);
+    for (int i = 0; i < ATT_KSTAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < ATT_VSTAGES; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -149,18 +158,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // ===== TMA producer =====
       mbar_arrive_expect_tx(&bar_q, ATT_TILE_BYTES);
       tma_load_3d(smem_q, &tm_q, &bar_q, 0, qt * ATT_BM, bh);
-      int stage = 0;
-      uint32_t phase = 0;
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
       for (int j = 0; j < n_kv; ++j) {
         const int kt = sched[1 + j] >> 1;
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sk = smem_kv + stage * 2 * ATT_TILE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_3d(sk, &tm_k, &kv_full[stage], 0, kt * ATT_BN, bh);
-        tma_load_3d(sk + ATT_TILE_BYTES, &tm_v, &kv_full[stage], 0, kt * ATT_BN, bh);
-        if (++stage == ATT_STAGES) {
-          stage = 0;
-          phase ^= 1;
+        mbar_wait(&k_empty[ks], kph ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], ATT_TILE_BYTES);
+        tma_load_3d(smem_k + ks * ATT_TILE_BYTES, &tm_k, &k_full[ks], 0, kt * ATT_BN, bh);
+        mbar_wait(&v_empty[vs], vph ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], ATT_TILE_BYTES);
+        tma_load_3d(smem_v + vs * ATT_TILE_BYTES, &tm_v, &v_full[vs], 0, kt * ATT_BN, bh);
+        if (++ks == ATT_KSTAGES) {
+          ks = 0;
+          kph ^= 1;
+        }
+        if (++vs == ATT_VSTAGES) {
+          vs = 0;
+          vph ^= 1;
         }
       }
     }
@@ -171,33 +185,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, 0, 1);  // A = P (TMEM),    B = V (MN-major)
       mbar_wait(&bar_q, 0);
       const uint64_t dq = make_smem_desc_kmajor_sw128(smem_u32(smem_q));
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&kv_full[stage], phase);
+      // S(j+1) = Q.K(j+1)^T is issued as soon as the softmax warps have pulled S(j) into registers (bar_s_free), i.e.
+      // it runs on the tensor pipe while softmax(j) is still computing; O += P(j).V(j) follows when P(j) arrives.
+      int ks = 0, vs = 0;          // ring positions of the NEXT K tile to multiply and the CURRENT V tile
+      uint32_t kph = 0, vph = 0;
+      auto issue_qk = [&]() {
+        mbar_wait(&k_full[ks], kph);
         tc_fence_after();
-        const uint32_t sk = smem_u32(smem_kv + stage * 2 * ATT_TILE_BYTES);
-        const uint64_t dk = make_smem_desc_kmajor_sw128(sk);
+        const uint64_t dk = make_smem_desc_kmajor_sw128(smem_u32(smem_k + ks * ATT_TILE_BYTES));
 #pragma unroll
         for (int kk = 0; kk < ATT_HD / 16; ++kk)
           umma_ss(tmem_base + TM_S, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk != 0);
-        umma_commit(&bar_s_full);  // also covers P.V of the previous tile (commit tracks all prior MMAs)
+        umma_commit(&k_empty[ks]);
+        umma_commit(&bar_s_full);
+        if (++ks == ATT_KSTAGES) {
+          ks = 0;
+          kph ^= 1;
+        }
+      };
+      issue_qk();
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) {
+          mbar_wait(&bar_s_free, j & 1);          // S(j) is in registers
+          issue_qk();
+        }
         mbar_wait(&bar_p_full, j & 1);
+        mbar_wait(&v_full[vs], vph);
         tc_fence_after();
         // V tile [128 kv x 64 hd], 128-byte rows: MN-major, 8-row k groups 1024 B apart, 16 kv rows (2048 B) per MMA
-        const uint32_t sv = sk + ATT_TILE_BYTES;
+        const uint32_t sv = smem_u32(smem_v + vs * ATT_TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
           const uint64_t dv = make_smem_desc(sv + kk * 2048, ATT_BN * 128, 1024);
           umma_ts(tmem_base + TM_O, tmem_base + TM_P + kk * 8, dv, idesc_pv, (j | kk) != 0);
         }
-        umma_commit(&kv_empty[stage]);
-        if (++stage == ATT_STAGES) {
-          stage = 0;
-          phase ^= 1;
+        umma_commit(&v_empty[vs]);
+        umma_commit(&bar_pv_done);
+        if (++vs == ATT_VSTAGES) {
+          vs = 0;
+          vph ^= 1;
         }
       }
-      umma_commit(&bar_final);
     }
   } else {
     // ===== softmax + correction + epilogue (8 warps; thread = (row, column half)) =====
@@ -245,6 +273,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld32(t_s, va);
       tmem_ld32(t_s + 32, vb);
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_s_free);   // S(j) now lives in registers: the tensor pipe may overwrite it with S(j+1)
       if (masked) {
         mask32(va, allow0);
         mask32(vb, allow1);
@@ -264,6 +294,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           alpha = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_cand) * c);
           m_run = m_cand;
         }
+      }
+      // P(j-1) / O must have been consumed / produced by P.V(j-1) before P is overwritten or O is rescaled
+      if (j > 0) {
+        mbar_wait(&bar_pv_done, (j - 1) & 1);
+        tc_fence_after();
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
 #pragma unroll 1
@@ -296,7 +331,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     xch[n_kv & 1][half][row] = l_part;
     softmax_bar_sync();
     const float l_run = l_part + xch[n_kv & 1][half ^ 1][row];
-    mbar_wait(&bar_final, 0);
+    mbar_wait(&bar_pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
     __nv_bfloat16* dst = a.out + (static_cast<size_t>(b) * a.seq + qpos) * a.ldo + h * ATT_HD + half * 32;

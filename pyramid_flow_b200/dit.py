@@ -11,7 +11,7 @@ stream (no torch math on the path, no CPU fallback):
   conditioning GEMVs -> all-layer AdaLN modulation GEMV -> embedders (GEMM, fp32 store into the joint residual stream)
   8 x double block : LN+modulate pre-pass | QKV GEMM (+bias, RMSNorm, RoPE epilogue) | masked joint attention |
                      out-proj GEMM (+gate*x+residual) | LN+modulate | FF1 GEMM (+GELU) | FF2 GEMM (+gate, residual)
-  16 x single block: LN+modulate | fused q|k|v|mlp GEMM (split epilogue) | attention | proj_out GEMM over [attn|mlp]
+  16 x single block: LN+modulate | QKV GEMM (+RMSNorm, RoPE) | proj_mlp GEMM (+GELU) | attention | proj_out GEMM over [attn|mlp]
   head             : LN+modulate (last-frame tokens only) | proj_out GEMM | unpatchify
 
 Data layout in HBM (B = CFG batch, S = text + all clip tokens, D = heads*64):
@@ -219,8 +219,9 @@ class B200FluxTransformer(torch.nn.Module):
         for i in range(c.num_single_layers):
             p = f"single_transformer_blocks.{i}"
             blk = dict(
-                w_in=W(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v", p + ".proj_mlp"),
-                b_in=Bv(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v", p + ".proj_mlp"),
+                w_qkv=W(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"),
+                b_qkv=Bv(p + ".attn.to_q", p + ".attn.to_k", p + ".attn.to_v"),
+                w_mlp=W(p + ".proj_mlp"), b_mlp=Bv(p + ".proj_mlp"),
                 nq=V(p + ".attn.norm_q.weight"), nk=V(p + ".attn.norm_k.weight"),
                 w_out=W(p + ".proj_out"), b_out=Bv(p + ".proj_out"),
             )
@@ -367,9 +368,13 @@ class B200FluxTransformer(torch.nn.Module):
         for i, w in enumerate(self.sgl):
             o = self.mod_off[f"single_transformer_blocks.{i}.norm"]
             lnmod(o, o + d, 0, s)                                                                  # (shift, scale) N:232
-            ops.gemm(xn, w["w_in"], w["b_in"], PF_EPI_QKV_GELU, batches=b, rows_per_batch=s, row_begin=0, row_count=s,
-                     out=cat, ldo=5 * d, out_col_begin=d, q_out=q, k_out=k, v_out=v, rope=plan.rope, q_norm_w=w["nq"],
-                     k_norm_w=w["nk"], heads=hn, head_dim=64, seq_len=s, n_split=3 * d)
+            # two launches sharing A: measured faster than the fused q|k|v|mlp GEMM (PF_EPI_QKV_GELU), whose 192-wide
+            # tiles slow the MLP half down (1.81 ms fused vs 0.60 + 0.62 ms split at S=15488)
+            ops.gemm(xn, w["w_qkv"], w["b_qkv"], PF_EPI_QKV_ROPE, batches=b, rows_per_batch=s, row_begin=0, row_count=s,
+                     q_out=q, k_out=k, v_out=v, rope=plan.rope, q_norm_w=w["nq"], k_norm_w=w["nk"], heads=hn,
+                     head_dim=64, seq_len=s)
+            ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=s, row_begin=0, row_count=s,
+                     out=cat, ldo=5 * d, out_col_begin=d)
             attention()
             ops.gemm(cat, w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=0,
                      row_count=s, out=h, ldo=d, gate=mod[:, o + 2 * d:], gate_batch_stride=nm)

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference sampler loop, so the hot path can be driven end-to-end without the reference tree.
+
+Mirrors `PyramidDiTForVideoGeneration.generate` / `generate_one_unit` / `get_pyramid_latent` / `sample_block_noise` /
+`decode_latent` (pyramid_dit/pyramid_dit_for_video_gen_pipeline.py:1006-1219, 706-788, 555-570, 697-703, 1221-1243) from
+the point where text embeddings exist (text encoders are out of scope: SURVEY.md §2 row 14).  In a reference checkout the
+pipeline itself stays the call surface; this mirror is what tests and bench.py drive on the GPU box, and
+it is pinned against the unmodified reference loop by tests/golden/sampler_small.pt (oracle/pin/make_golden.py).
+
+Only latent-space glue runs in torch here (bilinear/nearest resampling of `[1,16,T,h,w]` latents, CFG combine, Euler
+update — the reference's own host-side code); the DiT forward and the VAE decode are libpf_b200 kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+
+def _resize_frames(x: torch.Tensor, size, mode: str) -> torch.Tensor:
+    """'b c t h w -> (b t) c h w' -> interpolate -> back (P:561-565, P:731-733, P:1112-1116)."""
+    b, c, t, h, w = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    y = F.interpolate(y, size=size, mode=mode)
+    return y.reshape(b, t, c, size[0], size[1]).permute(0, 2, 1, 3, 4)
+
+
+def block_noise(bs: int, ch: int, temp: int, height: int, width: int, gamma: float,
+                generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """sample_block_noise (P:697-703): every 2x2 block ~ N(0, (1+g) I - g 11^T); vectorised (one Cholesky factor) instead
+    of the reference's python loop of `block_number` MultivariateNormal.sample() calls.  Same distribution, different RNG
+    consumption — parity tests inject the noise instead."""
+    cov = torch.eye(4) * (1 + gamma) - torch.ones(4, 4) * gamma
+    l = torch.linalg.cholesky(cov)
+    n = bs * ch * temp * (height // 2) * (width // 2)
+    z = torch.randn(n, 4, generator=generator) @ l.T
+    z = z.reshape(bs, ch, temp, height // 2, width // 2, 2, 2).permute(0, 1, 2, 3, 5, 4, 6)
+    return z.reshape(bs, ch, temp, height, width)
+
+
+class B200PyramidSampler:
+    def __init__(self, dit, scheduler, vae=None, stages: Sequence[int] = (1, 2, 4), frame_per_unit: int = 1,
+                 model_name: str = "pyramid_flux", downsample: int = 8,
+                 block_noise_fn: Optional[Callable[..., torch.Tensor]] = None):
+        self.dit, self.scheduler, self.vae = dit, scheduler, vae
+        self.stages = list(stages)
+        self.frame_per_unit = frame_per_unit
+        self.downsample = downsample
+        self.model_name = model_name
+        self.block_noise_fn = block_noise_fn
+        # latent normalisation constants (P:160-176)
+        if model_name == "pyramid_flux":
+            self.vae_shift_factor, self.vae_scale_factor = -0.04, 1 / 1.8726
+        else:
+            self.vae_shift_factor, self.vae_scale_factor = 0.1490, 1 / 1.8415
+        self.vae_video_shift_factor, self.vae_video_scale_factor = -0.2343, 1 / 3.0986
+        self.dit_calls = 0
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def get_pyramid_latent(self, x: torch.Tensor, stage_num: int) -> List[torch.Tensor]:
+        out = [x]
+        h, w = x.shape[-2], x.shape[-1]
+        for _ in range(stage_num):
+            h //= 2
+            w //= 2
+            x = _resize_frames(x, (h, w), "bilinear")
+            out.append(x)
+        return list(reversed(out))
+
+    @torch.no_grad()
+    def generate_one_unit(self, latents, past_conditions, prompt_embeds, prompt_attention_mask, pooled_prompt_embeds,
+                          num_inference_steps, height, width, temp, device, dtype, is_first_frame: bool,
+                          guidance_scale: float, video_guidance_scale: float, do_cfg: bool = True):
+        """P:706-788."""
+        inter = []
+        for i_s in range(len(self.stages)):
+            self.scheduler.set_timesteps(num_inference_steps[i_s], i_s, device=device)
+            timesteps = self.scheduler.timesteps
+            if i_s > 0:
+                height *= 2
+                width *= 2
+                latents = _resize_frames(latents, (height, width), "nearest")
+                ori_sigma = 1 - self.scheduler.ori_start_sigmas[i_s]
+                gamma = self.scheduler.config.gamma
+                alpha = 1 / (math.sqrt(1 + (1 / gamma)) * (1 - ori_sigma) + ori_sigma)
+                beta = alpha * (1 - ori_sigma) / math.sqrt(gamma)
+                bs, ch, temp, height, width = latents.shape
+                fn = self.block_noise_fn or (lambda *a: block_noise(*a, gamma))
+                noise = fn(bs, ch, temp, height, width).to(device=device, dtype=dtype)
+                latents = alpha * latents + beta * noise
+            for t in timesteps:
+                x_in = torch.cat([latents] * 2) if do_cfg else latents
+                timestep = t.expand(x_in.shape[0]).to(x_in.dtype)          # rounded to the latent dtype (bf16), P:750
+                clips = past_conditions[i_s] + [x_in]
+                v = self.dit(sample=[clips], timestep_ratio=timestep, encoder_hidden_states=prompt_embeds,
+                             encoder_attention_mask=prompt_attention_mask, pooled_projections=pooled_prompt_embeds)[0]
+                self.dit_calls += 1
+                if do_cfg:
+                    vu, vc = v.chunk(2)
+                    g = guidance_scale if is_first_frame else video_guidance_scale
+                    v = vu + g * (vc - vu)
+                latents = self.scheduler.step(model_output=v, timestep=timestep, sample=latents).prev_sample
+            inter.append(latents)
+        return inter
+
+    @torch.no_grad()
+    def generate(self, prompt_embeds, prompt_attention_mask, pooled_prompt_embeds, height: int, width: int, temp: int = 1,
+                 num_inference_steps=(20, 20, 20), video_num_inference_steps=(10, 10, 10), guidance_scale: float = 7.0,
+                 video_guidance_scale: float = 5.0, generator: Optional[torch.Generator] = None,
+                 output_type: str = "latent", save_memory: bool = True, latents: Optional[torch.Tensor] = None):
+        """P:1006-1219 after text encoding: `prompt_embeds` etc. are already the CFG batch [negative ; positive]."""
+        device, dtype = prompt_embeds.device, prompt_embeds.dtype
+        n_stage = len(self.stages)
+        num_inference_steps = [num_inference_steps] * n_stage if isinstance(num_inference_steps, int) else list(num_inference_steps)
+        video_num_inference_steps = [video_num_inference_steps] * n_stage if isinstance(video_num_inference_steps, int) else list(video_num_inference_steps)
+        assert (temp - 1) % self.frame_per_unit == 0
+        c_lat = (self.dit.config.in_channels // 4) if self.model_name == "pyramid_flux" else self.dit.config.in_channels
+        if latents is None:   # prepare_latents: CPU generator then move (randn_tensor semantics, P:676-695)
+            shape = (1, c_lat, int(temp), int(height) // self.downsample, int(width) // self.downsample)
+            latents = torch.randn(shape, generator=generator, dtype=dtype).to(device)
+        temp, h, w = latents.shape[-3:]
+        for _ in range(n_stage - 1):                              # P:1112-1116: start noise at the coarsest stage
+            h //= 2
+            w //= 2
+            latents = _resize_frames(latents, (h, w), "bilinear") * 2
+        num_units = 1 + (temp - 1) // self.frame_per_unit
+        generated = []
+        for unit in range(num_units):
+            if unit == 0:
+                past = [[] for _ in range(n_stage)]
+                inter = self.generate_one_unit(latents[:, :, :1], past, prompt_embeds, prompt_attention_mask,
+                                               pooled_prompt_embeds, num_inference_steps, h, w, 1, device, dtype, True,
+                                               guidance_scale, video_guidance_scale)
+            else:
+                past = []
+                clean = self.get_pyramid_latent(torch.cat(generated, dim=2), n_stage - 1)
+                fpu = self.frame_per_unit
+                for i_s in range(n_stage):                         # P:1159-1182: compressed history per stage
+                    last = clean[i_s][:, :, -fpu:]
+                    stage_input = [torch.cat([last] * 2)]
+                    cur_stage, ptx = i_s, 1
+                    while ptx < unit:
+                        cur_stage = max(cur_stage - 1, 0)
+                        if cur_stage == 0:
+                            break
+                        ptx += 1
+                        cond = clean[cur_stage][:, :, -(ptx * fpu): -((ptx - 1) * fpu)]
+                        stage_input.append(torch.cat([cond] * 2))
+                    if cur_stage == 0 and ptx < unit:
+                        cond = clean[0][:, :, :-(ptx * fpu)]
+                        stage_input.append(torch.cat([cond] * 2))
+                    past.append(list(reversed(stage_input)))
+                sl = slice(1 + (unit - 1) * fpu, 1 + unit * fpu)
+                inter = self.generate_one_unit(latents[:, :, sl], past, prompt_embeds, prompt_attention_mask,
+                                               pooled_prompt_embeds, video_num_inference_steps, h, w, fpu, device, dtype,
+                                               False, guidance_scale, video_guidance_scale)
+            generated.append(inter[-1])
+        out = torch.cat(generated, dim=2)
+        if output_type == "latent":
+            return out
+        return self.decode_latent(out, save_memory=save_memory)
+
+    @torch.no_grad()
+    def decode_latent(self, latents: torch.Tensor, save_memory: bool = True) -> torch.Tensor:
+        """P:1221-1243 up to the uint8 frames: returns uint8 `[(B T), H, W, C]` on the device."""
+        latents = latents.clone()
+        if latents.shape[2] == 1:
+            latents = (latents / self.vae_scale_factor) + self.vae_shift_factor
+        else:
+            latents[:, :, :1] = (latents[:, :, :1] / self.vae_scale_factor) + self.vae_shift_factor
+            latents[:, :, 1:] = (latents[:, :, 1:] / self.vae_video_scale_factor) + self.vae_video_shift_factor
+        if save_memory:
+            image = self.vae.decode(latents, temporal_chunk=True, window_size=1, tile_sample_min_size=256).sample
+        else:
+            image = self.vae.decode(latents, temporal_chunk=True, window_size=2, tile_sample_min_size=512).sample
+        image = image.float().mul(127.5).add(127.5).clamp(0, 255).byte()
+        b, c, t, h, w = image.shape
+        return image.permute(0, 2, 3, 4, 1).reshape(b * t, h, w, c)

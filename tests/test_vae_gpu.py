@@ -1,0 +1,119 @@
+"""Parity of the CUDA causal-VAE decode (through the C-ABI) against the oracle / the reference's golden output. B200."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# bf16 activations through ~60 convs + 30 GroupNorms; decoded samples are O(0.5) (|ref| mean ~0.43, range ~[-2, 2]).
+# Stated tolerance on the decoded sample vs the fp32 oracle: max-abs 0.1 (the max over ~2.6e5 values), MSE 1e-4
+# (RMS error 1e-2), and no worse than 1.5x the error of the reference's own dtype policy (oracle under bf16 autocast).
+TOL_MAX_ABS = 1e-1
+TOL_MSE = 1e-4
+
+
+def _conv_ref(x_cl, w, b, kt):
+    """x_cl [T, H, W, C] (no halo) -> causal conv, channels-last out."""
+    x = x_cl.permute(3, 0, 1, 2)[None].float()
+    k = w.shape[-1]
+    x = F.pad(x, (k // 2, k // 2, k // 2, k // 2, kt - 1, 0))
+    y = F.conv3d(x, w.float(), b.float())
+    return y[0].permute(1, 2, 3, 0)
+
+
+def test_conv3d_kernel_modes():
+    from pyramid_flow_b200.vae import B200CausalVAE, _Conv
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    holder = B200CausalVAE.__new__(B200CausalVAE)   # only the _conv wrapper is needed
+    for (ci, co, k, t, h, w) in [(64, 128, 3, 3, 6, 10), (128, 256, 3, 2, 17, 33), (256, 64, 1, 4, 9, 20), (64, 512, 3, 2, 12, 150)]:
+        wt = (torch.randn(co, ci, k, k, k) * (ci * k ** 3) ** -0.5).bfloat16().float()
+        bias = torch.randn(co) * 0.1
+        cv = _Conv({"c.conv.weight": wt, "c.conv.bias": bias}, "c", dev)
+        x = torch.randn(t, h, w, ci, device=dev).bfloat16()
+        xin = torch.zeros(t + k - 1, h, w, ci, device=dev, dtype=torch.bfloat16)
+        xin[k - 1:] = x
+        ref = _conv_ref(x, wt.to(dev), bias.to(dev), k)
+        out = torch.zeros(t, h, w, co, device=dev, dtype=torch.bfloat16)
+        B200CausalVAE._conv(holder, cv, xin, t, h, w, out=out)
+        torch.cuda.synchronize()
+        err = (out.float() - ref).abs().max().item()
+        assert err < 3e-2, (ci, co, k, err)
+        # residual + halo'd output
+        res = torch.randn(t, h, w, co, device=dev).bfloat16()
+        out2 = torch.zeros(t + 2, h, w, co, device=dev, dtype=torch.bfloat16)
+        B200CausalVAE._conv(holder, cv, xin, t, h, w, out=out2, out_t_offset=2, residual=res)
+        torch.cuda.synchronize()
+        assert (out2[2:].float() - (ref + res.float())).abs().max().item() < 4e-2
+        assert bool((out2[:2] == 0).all())
+        if co % 256 == 0 or co == 128:
+            # spatial depth-to-space: 'b (c p1 p2) t h w -> b c t (h p1) (w p2)'
+            o3 = torch.zeros(t, 2 * h, 2 * w, co // 4, device=dev, dtype=torch.bfloat16)
+            B200CausalVAE._conv(holder, cv, xin, t, h, w, out=o3, store_mode=1)
+            r3 = ref.reshape(t, h, w, co // 4, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(t, 2 * h, 2 * w, co // 4)
+            torch.cuda.synchronize()
+            assert (o3.float() - r3).abs().max().item() < 3e-2
+            # temporal depth-to-space with the first frame dropped
+            o4 = torch.zeros(2 * t - 1, h, w, co // 2, device=dev, dtype=torch.bfloat16)
+            B200CausalVAE._conv(holder, cv, xin, t, h, w, out=o4, out_t_offset=-1, store_mode=2)
+            r4 = ref.reshape(t, h, w, co // 2, 2).permute(0, 4, 1, 2, 3).reshape(2 * t, h, w, co // 2)[1:]
+            torch.cuda.synchronize()
+            assert (o4.float() - r4).abs().max().item() < 3e-2
+
+
+def _ours(cfg_kw, params, z, **dec_kw):
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    dev = torch.device("cuda:0")
+    vae = B200CausalVAE(VaeConfigB200(**cfg_kw), params, device=dev)
+    out = vae.decode(z.to(dev), **dec_kw).sample
+    torch.cuda.synchronize()
+    return out.float().cpu(), vae
+
+
+def test_small_vae_matches_reference_golden(golden_dir):
+    from oracle import vae_oracle as VO
+    g = torch.load(golden_dir / "vae_small.pt", weights_only=False)
+    cfg = VO.VaeDecoderConfig(**g["cfg"])
+    params = VO.synthetic_vae_params(cfg, seed=g["param_seed"])
+    z = g["z"].bfloat16().float()
+    with torch.no_grad():
+        ref = VO.decode(params, cfg, z)
+    out, vae = _ours(g["cfg"], params, z, temporal_chunk=False)
+    err, mse = (out - ref).abs().max().item(), ((out - ref) ** 2).mean().item()
+    err_gold = (out - g["full"]).abs().max().item()
+    print(f"vae small: max_abs vs oracle {err:.3e} mse {mse:.3e}; vs reference golden {err_gold:.3e}; |ref| mean {ref.abs().mean():.3f}")
+    assert out.shape == ref.shape
+    assert err < TOL_MAX_ABS and mse < TOL_MSE and err_gold < TOL_MAX_ABS
+    # temporal chunking with the 2-frame cache must reproduce the un-chunked result (the reference's property)
+    for wsz in (1, 2):
+        out_c = vae.decode(z.to("cuda:0"), temporal_chunk=True, window_size=wsz).sample.float().cpu()
+        assert (out_c - out).abs().max().item() < 2e-2, wsz
+    # tiled decode vs the reference's tiled golden
+    vae.enable_tiling()
+    out_t = vae.decode(z.to("cuda:0"), temporal_chunk=True, window_size=1, tile_sample_min_size=32).sample.float().cpu()
+    assert out_t.shape == g["tiled32"].shape
+    assert (out_t - g["tiled32"]).abs().max().item() < TOL_MAX_ABS
+
+
+def test_default_width_vae_matches_oracle():
+    from oracle import vae_oracle as VO
+    cfg = VO.VaeDecoderConfig()
+    params = VO.synthetic_vae_params(cfg, seed=1)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(1, 16, 3, 8, 12, generator=g).bfloat16().float()
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    pd = {k: v.to(dev) for k, v in params.items()}
+    with torch.no_grad():
+        ref = VO.decode(pd, cfg, z.to(dev)).float().cpu()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ref_bf16 = VO.decode(pd, cfg, z.to(dev).bfloat16()).float().cpu()
+    out, _ = _ours({}, params, z, temporal_chunk=True, window_size=1)
+    err, mse = (out - ref).abs().max().item(), ((out - ref) ** 2).mean().item()
+    e2, m2 = (ref_bf16 - ref).abs().max().item(), ((ref_bf16 - ref) ** 2).mean().item()
+    print(f"vae default width: ours vs fp32 oracle max_abs {err:.3e} mse {mse:.3e} | bf16-autocast oracle vs fp32 {e2:.3e} mse {m2:.3e} | |ref| mean {ref.abs().mean():.3f}")
+    assert out.shape == ref.shape == (1, 3, 17, 64, 96)
+    assert err < TOL_MAX_ABS and mse < TOL_MSE
+    assert err <= 1.5 * e2 + 1e-2 and mse <= 2.0 * m2 + 1e-5, "must be comparable to the reference's own bf16 error"
+    assert ref.abs().mean().item() > 0.05
