@@ -174,7 +174,8 @@ typedef struct pf_conv3d_desc {
 PF_API int pf_causal_conv3d(const pf_conv3d_desc* desc, void* stream);
 
 /* per-frame GroupNorm (CausalGroupNorm C:36-43) on channels-last bf16 [frames, voxels, channels]:
- * stats[frame, group] = (mean, rstd); workspace: >= frames * nsplit * channels * 2 floats (nsplit <= max(1, 2048/frames)). */
+ * stats[frame, group] = (mean, rstd); workspace: >= frames * 64 * channels * 2 floats.  Deterministic, and independent of
+ * how many frames are passed per call (chunk-invariant). */
 PF_API int pf_groupnorm_stats(const void* x_bf16, int32_t frames, int64_t voxels, int32_t channels, int32_t groups,
                               float eps, float* stats, float* workspace, int64_t workspace_floats, void* stream);
 /* y[b, t + y_t_offset, vox, c] = act((x[b, t, vox, c] - mean) * rstd * gamma[c] + beta[c]), act = SiLU if silu

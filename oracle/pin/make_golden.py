@@ -147,6 +147,63 @@ def make_vae():
                 "chunk2_maxdiff": float((full - chunk2).abs().max()), "tiled32": tiled}, GOLD / "vae_small.pt")
 
 
+def make_sampler():
+    """The UNMODIFIED reference generate() loop (P:1006-1219) on CPU fp32 with a tiny reference DiT, a fake text encoder and
+    injected block noise (the reference draws it from the global CPU RNG in a python loop, P:697-703)."""
+    from pyramid_dit import PyramidDiTForVideoGeneration
+    from pyramid_dit.flux_modules import PyramidFluxTransformer
+    from diffusion_schedulers import PyramidFlowMatchEulerDiscreteScheduler
+    cfg = FO.FluxConfig(**SMALL_CFG)
+    params = FO.synthetic_flux_params(cfg, seed=0)
+    dit = PyramidFluxTransformer(**SMALL_CFG).eval()
+    dit.load_state_dict(params, strict=True)
+    g = torch.Generator().manual_seed(7)
+    enc = torch.randn(2, 24, SMALL_CFG["joint_attention_dim"], generator=g) * 0.5      # [negative ; positive]
+    mask = torch.ones(2, 24, dtype=torch.long)
+    mask[0, 11:] = 0
+    pooled = torch.randn(2, SMALL_CFG["pooled_projection_dim"], generator=g)
+
+    class FakeText:
+        def __init__(self):
+            self.calls = 0
+
+        def __call__(self, prompt, device):   # generate() calls it for the prompt, then for the negative prompt
+            i = 1 if self.calls == 0 else 0
+            self.calls += 1
+            return enc[i:i + 1], mask[i:i + 1], pooled[i:i + 1]
+
+    pipe = object.__new__(PyramidDiTForVideoGeneration)
+    pipe.dit = dit
+    pipe.text_encoder = FakeText()
+    pipe.vae = None
+    pipe.scheduler = PyramidFlowMatchEulerDiscreteScheduler(shift=1.0, stages=3, stage_range=[0, 1 / 3, 2 / 3, 1], gamma=1 / 3)
+    pipe.stages = [1, 2, 4]
+    pipe.frame_per_unit = 1
+    pipe.model_name = "pyramid_flux"
+    pipe.sequential_offload_enabled = False
+    pipe.downsample = 8
+    pipe.vae_scale_factor = 1 / 1.8726
+    ng = torch.Generator().manual_seed(11)
+    noises = []
+
+    def fake_block_noise(bs, ch, temp, height, width):
+        n = torch.randn(bs, ch, temp, height, width, generator=ng)
+        noises.append(n)
+        return n
+
+    pipe.sample_block_noise = fake_block_noise
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        lat = pipe.generate(prompt="x", height=128, width=128, temp=4, num_inference_steps=[2, 2, 2],
+                            video_num_inference_steps=[2, 1, 2], guidance_scale=7.0, video_guidance_scale=5.0,
+                            generator=gen, output_type="latent", save_memory=True)
+    print("sampler:", lat.shape, float(lat.abs().mean()), "block-noise draws", len(noises))
+    torch.save({"cfg": SMALL_CFG, "param_seed": 0, "enc": enc, "mask": mask, "pooled": pooled, "noises": noises,
+                "latent_seed": 3, "latents": lat, "args": dict(height=128, width=128, temp=4, num_inference_steps=[2, 2, 2],
+                                                                video_num_inference_steps=[2, 1, 2], guidance_scale=7.0,
+                                                                video_guidance_scale=5.0)}, GOLD / "sampler_small.pt")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["flux", "block", "sched"]
     for w in which:

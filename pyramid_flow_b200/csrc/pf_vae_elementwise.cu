@@ -13,21 +13,21 @@ namespace pf {
 __global__ void __launch_bounds__(256)
 gn_partial_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, int channels, int nsplit,
                   float* __restrict__ partial /* [frames, nsplit, channels, 2] */) {
-  extern __shared__ float sh[];  // [channels][2]
+  // deterministic: per-thread partials are parked in shared memory [vstep][channels][2] and summed in a fixed order
+  extern __shared__ float sh[];
   const int frame = blockIdx.x / nsplit;
   const int split = blockIdx.x - frame * nsplit;
   const int cvecs = channels >> 3;
-  for (int i = threadIdx.x; i < 2 * channels; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const long long v0 = voxels * split / nsplit, v1 = voxels * (split + 1) / nsplit;
   const int cv = threadIdx.x % cvecs;
+  const int vlane = threadIdx.x / cvecs;
   const int vstep = blockDim.x / cvecs;
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-  if (threadIdx.x < vstep * cvecs) {
+  if (vlane < vstep) {
     const __nv_bfloat16* base = x + static_cast<size_t>(frame) * voxels * channels;
-    for (long long v = v0 + threadIdx.x / cvecs; v < v1; v += vstep) {
+    for (long long v = v0 + vlane; v < v1; v += vstep) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + v * channels) + cv);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -37,15 +37,20 @@ gn_partial_kernel(const __nv_bfloat16* __restrict__ x, long long voxels, int cha
         s[2 * i + 1] += f.y; ss[2 * i + 1] += f.y * f.y;
       }
     }
+    float* dst = sh + (static_cast<size_t>(vlane) * channels + cv * 8) * 2;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[2 * (cv * 8 + i)], s[i]);
-      atomicAdd(&sh[2 * (cv * 8 + i) + 1], ss[i]);
+      dst[2 * i] = s[i];
+      dst[2 * i + 1] = ss[i];
     }
   }
   __syncthreads();
-  float* dst = partial + (static_cast<size_t>(frame) * nsplit + split) * channels * 2;
-  for (int i = threadIdx.x; i < 2 * channels; i += blockDim.x) dst[i] = sh[i];
+  float* out = partial + (static_cast<size_t>(frame) * nsplit + split) * channels * 2;
+  for (int i = threadIdx.x; i < 2 * channels; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < vstep; ++l) acc += sh[static_cast<size_t>(l) * channels * 2 + i];
+    out[i] = acc;
+  }
 }
 
 // pass 2: (mean, rstd) per (frame, group), combined in double
@@ -171,15 +176,16 @@ int pf_groupnorm_stats(const void* x, int32_t frames, int64_t voxels, int32_t ch
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PF_REQUIRE(x && stats && workspace, "pf_groupnorm_stats: null pointer");
   PF_REQUIRE(channels % 8 == 0 && channels % groups == 0 && channels <= 2048, "pf_groupnorm_stats: channels=%d unsupported", channels);
-  PF_REQUIRE(256 % (channels / 8) == 0 || channels / 8 <= 256, "pf_groupnorm_stats: channel vectors must fit a block");
+  // the split count depends on the frame SIZE only, never on how many frames are in the call: per-frame statistics are
+  // bitwise identical whatever the temporal chunking
   long long nsplit = (voxels + 4095) / 4096;
   if (nsplit < 1) nsplit = 1;
-  const long long cap = (2048 + frames - 1) / frames;   // ~2k blocks are plenty
-  if (nsplit > cap) nsplit = cap;
-  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 64) nsplit = 64;
   PF_REQUIRE(static_cast<long long>(frames) * nsplit * channels * 2 <= workspace_floats, "pf_groupnorm_stats: workspace too small (need %lld floats)",
              static_cast<long long>(frames) * nsplit * channels * 2);
-  gn_partial_kernel<<<static_cast<int>(frames * nsplit), 256, 2 * channels * sizeof(float), stream>>>(
+  const int vstep = 256 / (channels / 8);
+  PF_REQUIRE(vstep >= 1, "pf_groupnorm_stats: too many channels for one block");
+  gn_partial_kernel<<<static_cast<int>(frames * nsplit), 256, static_cast<size_t>(vstep) * channels * 2 * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(x), voxels, channels, static_cast<int>(nsplit), workspace);
   int rc = check_launch("pf_groupnorm_stats(partial)");
   if (rc) return rc;

@@ -167,8 +167,8 @@ class B200CausalVAE(torch.nn.Module):
         t, h, w, c = x.shape
         groups = self.cfg.norm_num_groups
         stats = torch.empty(t, groups, 2, device=x.device, dtype=torch.float32)
-        nsplit_cap = max(1, (2048 + t - 1) // t)
-        ws = torch.empty(t * nsplit_cap * c * 2, device=x.device, dtype=torch.float32)
+        nsplit = min(64, max(1, (h * w + 4095) // 4096))
+        ws = torch.empty(t * nsplit * c * 2, device=x.device, dtype=torch.float32)
         lib = _lib.load()
         _lib.check(lib.pf_groupnorm_stats(x.data_ptr(), t, h * w, c, groups, 1e-6, stats.data_ptr(), ws.data_ptr(),
                                           ws.numel(), _lib.stream_ptr()), "pf_groupnorm_stats")

@@ -84,10 +84,11 @@ def test_small_vae_matches_reference_golden(golden_dir):
     print(f"vae small: max_abs vs oracle {err:.3e} mse {mse:.3e}; vs reference golden {err_gold:.3e}; |ref| mean {ref.abs().mean():.3f}")
     assert out.shape == ref.shape
     assert err < TOL_MAX_ABS and mse < TOL_MSE and err_gold < TOL_MAX_ABS
-    # temporal chunking with the 2-frame cache must reproduce the un-chunked result (the reference's property)
+    # temporal chunking with the 2-frame cache reproduces the un-chunked result BIT FOR BIT (all kernels deterministic,
+    # per-frame statistics independent of the chunking) — the reference's own property is 4.9e-6 in fp32
     for wsz in (1, 2):
         out_c = vae.decode(z.to("cuda:0"), temporal_chunk=True, window_size=wsz).sample.float().cpu()
-        assert (out_c - out).abs().max().item() < 2e-2, wsz
+        assert torch.equal(out_c, out), (wsz, (out_c - out).abs().max().item())
     # tiled decode vs the reference's tiled golden
     vae.enable_tiling()
     out_t = vae.decode(z.to("cuda:0"), temporal_chunk=True, window_size=1, tile_sample_min_size=32).sample.float().cpu()

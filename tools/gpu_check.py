@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "attn_perf"]
+GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "attn_perf", "vae_perf"]
 
 
 def _rel_err(a, b):
@@ -346,6 +346,67 @@ def group_attn_perf():
     ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125), iters=5)
     flops = 4.0 * 64 * H * float(pairs.sum())
     print(f"[attn_perf] S={S} B={B} H={H}: {ms:.3f} ms, allowed pairs {pairs.tolist()}, {flops/ms/1e9:.0f} TFLOP/s (masked-pair flops)", flush=True)
+
+
+def group_vae_perf():
+    import torch
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    from pyramid_flow_b200 import _lib
+    dev = torch.device("cuda:0")
+    cfg = VaeConfigB200()
+    # random decoder weights directly on the device (shapes from the reference key layout)
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    rev = list(reversed(cfg.block_out_channels))
+
+    def conv(name, co, ci, k):
+        sd[name + ".conv.weight"] = torch.randn(co, ci, k, k, k, device=dev, generator=g) * (ci * k ** 3) ** -0.5
+        sd[name + ".conv.bias"] = torch.randn(co, device=dev, generator=g) * 0.02
+
+    def norm(name, c):
+        sd[name + ".weight"] = 1 + 0.1 * torch.randn(c, device=dev, generator=g)
+        sd[name + ".bias"] = 0.05 * torch.randn(c, device=dev, generator=g)
+
+    def res(name, ci, co):
+        norm(name + ".norm1", ci); conv(name + ".conv1", co, ci, 3); norm(name + ".norm2", co); conv(name + ".conv2", co, co, 3)
+        if ci != co:
+            conv(name + ".conv_shortcut", co, ci, 1)
+
+    top = rev[0]
+    conv("post_quant_conv", 16, 16, 1); conv("decoder.conv_in", top, 16, 3)
+    res("decoder.mid_block.resnets.0", top, top); res("decoder.mid_block.resnets.1", top, top)
+    norm("decoder.mid_block.attentions.0.group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        sd[f"decoder.mid_block.attentions.0.{n}.weight"] = torch.randn(top, top, device=dev, generator=g) * top ** -0.5
+        sd[f"decoder.mid_block.attentions.0.{n}.bias"] = torch.randn(top, device=dev, generator=g) * 0.02
+    prev = top
+    for i, co in enumerate(rev):
+        for j in range(cfg.layers_per_block[i]):
+            res(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if cfg.spatial_up_sample[i]:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", 4 * co, co, 3)
+        if cfg.temporal_up_sample[i]:
+            conv(f"decoder.up_blocks.{i}.temporal_upsamplers.0.conv", 2 * co, co, 3)
+        prev = co
+    norm("decoder.conv_norm_out", cfg.block_out_channels[0]); conv("decoder.conv_out", 3, cfg.block_out_channels[0], 3)
+    sd = {k: v.cpu() for k, v in sd.items()}
+    vae = B200CausalVAE(cfg, sd, device=dev)
+    for (T, h, w, win) in [(3, 48, 80, 2), (5, 96, 160, 2)]:
+        z = torch.randn(1, 16, T, h, w, device=dev).bfloat16()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = vae.decode(z, temporal_chunk=True, window_size=win).sample   # warm-up (allocations)
+        torch.cuda.synchronize()
+        e0.record()
+        out = vae.decode(z, temporal_chunk=True, window_size=win).sample
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        frames = out.shape[2]
+        macs = 1.10e7 * frames * out.shape[3] * out.shape[4]
+        print(f"[vae_perf] latent {T}x{h}x{w} -> {tuple(out.shape)}: {ms:.1f} ms, {frames / (ms * 1e-3):.1f} frames/s, "
+              f"{2 * macs / (ms * 1e-3) / 1e12:.0f} TFLOP/s (1.10e7 MAC/px-frame), peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, launches {(_lib.launch_count() - n0) // 2}", flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------
