@@ -4,7 +4,8 @@
 A "step" is ONE DiT forward (the pipeline's `self.dit(...)` call, P:760-766) at the headline single-step shape of the
 768p / 10 s configuration: unit 30, stage 2 — CFG batch B=2, S = 128 text + 28x240 + 960 + 3840 history
 + 3840 current = 15488 tokens, full 8+16-block miniFLUX (D=1920, 30 heads), synthetic latents / text embeddings and
-random-init weights (no checkpoints offline).  tokens/s = n_gpus * B * S / t_step.
+random-init weights (no checkpoints offline).  tokens/s = B * S / t_step; with --gpus N the SAME step is sharded over
+the N GPUs (CFG pair first, then Ulysses sequence parallel; strong scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA kernels through the C-ABI)
   python bench.py --impl reference ...                           the reference algorithm's CPU path (oracle port), host cores
@@ -212,13 +213,20 @@ def run_ours(args):
     _lib.require_device()
 
     cfg_kw = dict(num_layers=args.layers[0], num_single_layers=args.layers[1])
-    cfg, sd = random_flux_state_dict(cfg_kw, dev, seed=rank)
+    # N > 1: ONE step sharded over the GPUs (CFG pair first, then the token sequence: pyramid_flow_b200/sp.py) — the same
+    # weights and inputs on every rank, strong scaling of the single step
+    cfg, sd = random_flux_state_dict(cfg_kw, dev, seed=0)
     model = B200FluxTransformer(cfg, sd, device=dev)
     del sd
     torch.cuda.empty_cache()
+    lay = None
+    if world > 1:
+        from pyramid_flow_b200 import sp as SP
+        lay = SP.make_layout()
+        model.set_parallel_layout(lay)
 
     b = 2
-    g = torch.Generator().manual_seed(100 + rank)
+    g = torch.Generator().manual_seed(100)
     shapes = step_clip_shapes(b)
     host = {
         "clips": [torch.randn(s, generator=g).bfloat16().pin_memory() for s in shapes],
@@ -299,22 +307,26 @@ def run_ours(args):
     fl = model.step_flops(b, plan)
     n_attn = cfg.num_layers + cfg.num_single_layers
     attn_flops_launch = fl["attention"] / n_attn
+    if lay is not None:   # per rank: one CFG branch, Hp/sp (padded) heads of the 30
+        attn_flops_launch = 4.0 * 64 * (model._hp // lay.sp) * (plan.allowed_pairs / b)
     achieved = attn_flops_launch / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else None
     peak = peaks["tflops_sustained"]
     h2d = sum(x.numel() * x.element_size() for x in host["clips"]) + sum(
         host[k].numel() * host[k].element_size() for k in ("enc", "mask", "pooled", "t"))
     d2h = out_host.numel() * out_host.element_size()
     line = {
-        "metric": METRIC, "value": world * tokens / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * b, "seq_len": plan.seq,
-                   "parallelism": f"dp{world} (independent replicas; sequence-parallel path not in this round)",
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": b, "seq_len": plan.seq,
+                   "parallelism": ("single GPU" if world == 1 else
+                                   f"cfg{lay.cfg_ways} x sp{lay.sp}: CFG pair split first, then Ulysses sequence parallel "
+                                   f"(heads 30 -> {model._hp}, one NCCL all-to-all each side of attention)"),
                    "layers": list(args.layers), "l2": "per-step working set (>1.5 GB of activations + 3.9 GB weights) exceeds the 126 MB L2; no explicit flush",
                    "step_tflop": {"gemm": fl["gemm"] / 1e12, "attention_masked": fl["attention"] / 1e12},
                    "step_tflops_achieved": (fl["gemm"] + fl["attention"]) / (ms_step * 1e-3) / 1e12},
         "clocks": clocks,
-        "e2e": {"value": world * tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+        "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "B200FluxTransformer.__call__(sample=[clips], timestep_ratio, encoder_hidden_states, encoder_attention_mask, pooled_projections) with pinned host inputs, result copied back to host"},
         "gpu_launches": launches,

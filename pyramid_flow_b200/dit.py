@@ -241,27 +241,33 @@ class B200FluxTransformer(torch.nn.Module):
         return iter([self.w_x])
 
     # -- workspace -----------------------------------------------------------------------------------------------------
-    def _workspace(self, b: int, plan: SeqPlan) -> dict:
-        key = (b, plan.seq, plan.video_len, plan.last_tokens)
+    def _workspace(self, b: int, plan: SeqPlan, sl: Optional[int] = None, hp: Optional[int] = None) -> dict:
+        c = self.cfg
+        sl = plan.seq if sl is None else sl
+        hp = c.num_attention_heads if hp is None else hp
+        key = (b, plan.seq, plan.video_len, plan.last_tokens, sl, hp)
         ws = self._ws.get(key)
         if ws is None:
             if len(self._ws) >= 4:   # shapes change every unit/stage; keep the cache bounded
                 self._ws.clear()
-            c = self.cfg
-            d, hn, s, dev = c.inner_dim, c.num_attention_heads, plan.seq, self.device
+            d, hn, dev = c.inner_dim, c.num_attention_heads, self.device
+            alloc = torch.zeros if hp != hn else torch.empty      # padded heads must read as zeros
             ws = dict(
-                h=torch.empty(b, s, d, device=dev, dtype=torch.float32),
-                xn=torch.empty(b, s, d, device=dev, dtype=torch.bfloat16),
-                q=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
-                k=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
-                v=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
-                cat=torch.empty(b, s, 5 * d, device=dev, dtype=torch.bfloat16),
+                h=torch.empty(b, sl, d, device=dev, dtype=torch.float32),
+                xn=torch.empty(b, sl, d, device=dev, dtype=torch.bfloat16),
+                q=alloc(b, hp, sl, 64, device=dev, dtype=torch.bfloat16),
+                k=alloc(b, hp, sl, 64, device=dev, dtype=torch.bfloat16),
+                v=alloc(b, hp, sl, 64, device=dev, dtype=torch.bfloat16),
+                cat=torch.empty(b, sl, hp * 64 + 4 * d, device=dev, dtype=torch.bfloat16),
                 tok=torch.empty(b, plan.video_len, c.in_channels, device=dev, dtype=torch.bfloat16),
                 mod=torch.empty(b, self.n_mod, device=dev, dtype=torch.float32),
                 temb=torch.empty(b, d, device=dev, dtype=torch.float32),
                 tmp=torch.empty(b, d, device=dev, dtype=torch.float32),
-                head=torch.empty(b, plan.last_tokens, c.in_channels, device=dev, dtype=torch.float32),
+                head=torch.zeros(b, plan.last_tokens, c.in_channels, device=dev, dtype=torch.float32),
             )
+            if sl != plan.seq:   # sequence parallel: attention output of my head group over the whole sequence
+                lay = self.layout
+                ws["of"] = torch.empty(plan.seq, (hp // lay.sp) * 64, device=dev, dtype=torch.bfloat16)
             self._ws[key] = ws
         return ws
 
@@ -285,6 +291,28 @@ class B200FluxTransformer(torch.nn.Module):
             self._plans[key] = plan
         return plan
 
+    # -- parallel layout (CFG x sequence parallel, sp.py) ---------------------------------------------------------------
+    def set_parallel_layout(self, layout) -> None:
+        """Attach a `sp.ParallelLayout` (after torch.distributed is initialised); weights are replicated."""
+        self.layout = layout
+        self._ws.clear()
+        hn = self.cfg.num_attention_heads
+        from .sp import padded_heads
+        hp = padded_heads(hn, layout.sp)
+        self._hp = hp
+        if hp != hn and not hasattr(self, "_padded"):
+            d, pad = self.cfg.inner_dim, (hp - hn) * 64
+
+            def padk(w):   # [N, D (+rest)] -> [N, Hp*64 (+rest)]: zero columns for the padded heads
+                z = torch.zeros(w.shape[0], pad, device=w.device, dtype=w.dtype)
+                return torch.cat([w[:, :d], z, w[:, d:]], dim=1).contiguous()
+
+            for blk in self.dbl:
+                blk["w_o_p"], blk["w_co_p"] = padk(blk["w_o"]), padk(blk["w_co"])
+            for blk in self.sgl:
+                blk["w_out_p"] = padk(blk["w_out"])
+            self._padded = True
+
     # -- the step ------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, sample, timestep_ratio=None, encoder_hidden_states=None, encoder_attention_mask=None,
@@ -294,101 +322,155 @@ class B200FluxTransformer(torch.nn.Module):
         clips = sample[0] if isinstance(sample[0], (list, tuple)) else [sample[0]]
         c = self.cfg
         d, hn = c.inner_dim, c.num_attention_heads
-        b = clips[-1].shape[0]
+        lay = getattr(self, "layout", None)
+        par = lay is not None and lay.enabled
+        bg = clips[-1].shape[0]                       # global (CFG) batch
         plan = self.plan_for([cl.shape for cl in clips], encoder_attention_mask)
         self.last_plan = plan
-        ws = self._workspace(b, plan)
         t_len, s, lv = plan.text_len, plan.seq, plan.video_len
+        if par:
+            from . import sp as SP
+            assert bg == lay.cfg_ways, "CFG-parallel layout expects the [uncond ; cond] batch"
+            b, b0 = 1, lay.cfg_rank                    # this rank's CFG branch
+            nsp, hp = lay.sp, self._hp
+            c0, c1 = SP.chunk_bounds(s, nsp, lay.sp_rank)
+        else:
+            b, b0, nsp, hp, c0, c1 = bg, 0, 1, hn, 0, s
+        sl = c1 - c0                                   # tokens of the joint sequence owned by this rank
+        wa = hp * 64                                   # width of the attention block in `cat`
+        ws = self._workspace(b, plan, sl, hp)
         h, xn, q, k, v, cat, mod = ws["h"], ws["xn"], ws["q"], ws["k"], ws["v"], ws["cat"], ws["mod"]
         nm = self.n_mod
+        ldc = wa + 4 * d
+        rope = plan.rope[c0:c1]
+        # local (row_begin, row_count) of the text / video ranges inside this rank's chunk, and their global starts
+        tb, te = max(0, c0), min(t_len, c1)
+        vb, ve = max(t_len, c0), min(s, c1)
+        ranges = ((tb - c0, max(0, te - tb)), (vb - c0, max(0, ve - vb)))
 
         # ---- conditioning (E:193-201): timestep arrives already rounded to bf16 by the pipeline (P:750)
-        t32 = timestep_ratio.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        t32 = timestep_ratio.detach().to(device=self.device, dtype=torch.float32)[b0:b0 + b].contiguous()
         tproj = ops.timestep_embedding(t32, 256, round_bf16=self.emulate_bf16_rounding)
         ops.small_linear(tproj, self.w_t1, self.b_t1, ws["tmp"], act_out=1)
         ops.small_linear(ws["tmp"], self.w_t2, self.b_t2, ws["temb"])
-        pooled = pooled_projections.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        pooled = pooled_projections.detach().to(device=self.device, dtype=torch.float32)[b0:b0 + b].contiguous()
         ops.small_linear(pooled, self.w_p1, self.b_p1, ws["tmp"], act_out=1)
         ops.small_linear(ws["tmp"], self.w_p2, self.b_p2, ws["temb"], accumulate=True)
         # ---- every AdaLN modulation of the step in one GEMV: mod = Linear(SiLU(temb)) for all layers
         ops.small_linear(ws["temb"], self.w_mod, self.b_mod, mod, act_in=1)
 
-        # ---- embedders write straight into the joint fp32 residual stream
-        enc = encoder_hidden_states.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
-        ops.gemm(enc, self.w_ctx, self.b_ctx, PF_EPI_STORE_F32, batches=b, rows_per_batch=t_len, row_begin=0,
-                 row_count=t_len, out=h, ldo=d, out_batch_rows=s, out_row_begin=0)
-        tok0 = 0
-        for cl, (ct, chh, cww) in zip(clips, plan.clip_thw):
-            cl = cl.detach()
-            if cl.dtype not in (torch.float32, torch.bfloat16):
-                cl = cl.float()
-            ops.patchify(cl.contiguous(), ws["tok"], lv, tok0)
-            tok0 += ct * chh * cww
-        ops.gemm(ws["tok"], self.w_x, self.b_x, PF_EPI_STORE_F32, batches=b, rows_per_batch=lv, row_begin=0,
-                 row_count=lv, out=h, ldo=d, out_batch_rows=s, out_row_begin=t_len)
+        # ---- embedders write straight into the joint fp32 residual stream (only this rank's rows)
+        if ranges[0][1] > 0:
+            enc = encoder_hidden_states.detach().to(device=self.device, dtype=torch.bfloat16)[b0:b0 + b].contiguous()
+            ops.gemm(enc, self.w_ctx, self.b_ctx, PF_EPI_STORE_F32, batches=b, rows_per_batch=t_len, row_begin=tb,
+                     row_count=te - tb, out=h, ldo=d, out_batch_rows=sl, out_row_begin=tb - c0)
+        if ranges[1][1] > 0:
+            tok0 = 0
+            for cl, (ct, chh, cww) in zip(clips, plan.clip_thw):
+                cl = cl.detach()[b0:b0 + b]
+                if cl.dtype not in (torch.float32, torch.bfloat16):
+                    cl = cl.float()
+                ops.patchify(cl.contiguous(), ws["tok"], lv, tok0)
+                tok0 += ct * chh * cww
+            ops.gemm(ws["tok"], self.w_x, self.b_x, PF_EPI_STORE_F32, batches=b, rows_per_batch=lv, row_begin=vb - t_len,
+                     row_count=ve - vb, out=h, ldo=d, out_batch_rows=sl, out_row_begin=vb - c0)
 
         def lnmod(off_shift, off_scale, r0, rc):
-            ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=s,
-                            row_begin=r0, row_count=rc)
+            if rc > 0:
+                ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=sl,
+                                row_begin=r0, row_count=rc)
+
+        def qkv(wq, bq, nq, nk, r0, rc):
+            if rc > 0:
+                ops.gemm(xn, wq, bq, PF_EPI_QKV_ROPE, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc, q_out=q,
+                         k_out=k, v_out=v, rope=rope, q_norm_w=nq, k_norm_w=nk, heads=hn, head_dim=64, seq_len=sl)
+
+        scale = 1.0 / math.sqrt(64)
+        seg, tim, sched = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b]
 
         def attention():
-            if self.attn_events is not None:
+            ev = self.attn_events is not None
+            if ev:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, 1.0 / math.sqrt(64))
-                e1.record()
-                self.attn_events.append((e0, e1))
+            if nsp == 1:
+                if ev:
+                    e0.record()
+                ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale)
+                if ev:
+                    e1.record()
             else:
-                ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, 1.0 / math.sqrt(64))
+                # Ulysses exchange: all (padded) heads of my token chunk -> my head group over the whole sequence
+                qf, kf, vf = (SP.heads_to_sequence(t_[0], lay) for t_ in (q, k, v))
+                of = ws["of"]
+                if ev:
+                    e0.record()
+                ops.attn_fwd(qf[None], kf[None], vf[None], of[None], seg, tim, sched, scale)
+                if ev:
+                    e1.record()
+                cat[0, :, :wa].copy_(SP.sequence_to_heads(of, lay))
+            if ev:
+                self.attn_events.append((e0, e1))
 
-        ranges = ((0, t_len), (t_len, lv))  # (row_begin, row_count): text, video
+        pad = hp != hn
         for i, w in enumerate(self.dbl):
             ov = self.mod_off[f"transformer_blocks.{i}.norm1"]
             oc = self.mod_off[f"transformer_blocks.{i}.norm1_context"]
             offs = (oc, ov)
             wq, bq, nq, nk = (w["w_cqkv"], w["w_qkv"]), (w["b_cqkv"], w["b_qkv"]), (w["cnq"], w["nq"]), (w["cnk"], w["nk"])
-            wo, bo = (w["w_co"], w["w_o"]), (w["b_co"], w["b_o"])
+            wo = (w["w_co_p"], w["w_o_p"]) if pad else (w["w_co"], w["w_o"])
+            bo = (w["b_co"], w["b_o"])
             wf1, bf1 = (w["w_cf1"], w["w_f1"]), (w["b_cf1"], w["b_f1"])
             wf2, bf2 = (w["w_cf2"], w["w_f2"]), (w["b_cf2"], w["b_f2"])
             for j, (r0, rc) in enumerate(ranges):
                 lnmod(offs[j] + 0 * d, offs[j] + 1 * d, r0, rc)            # (shift_msa, scale_msa) N:173/191
-                ops.gemm(xn, wq[j], bq[j], PF_EPI_QKV_ROPE, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
-                         q_out=q, k_out=k, v_out=v, rope=plan.rope, q_norm_w=nq[j], k_norm_w=nk[j], heads=hn,
-                         head_dim=64, seq_len=s)
+                qkv(wq[j], bq[j], nq[j], nk[j], r0, rc)
             attention()
             for j, (r0, rc) in enumerate(ranges):
-                ops.gemm(cat, wo[j], bo[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
-                         out=h, ldo=d, gate=mod[:, offs[j] + 2 * d:], gate_batch_stride=nm)      # gate_msa
+                if rc == 0:
+                    continue
+                ops.gemm(cat[:, :, :wa], wo[j], bo[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
+                         row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 2 * d:], gate_batch_stride=nm)   # gate_msa
                 lnmod(offs[j] + 3 * d, offs[j] + 4 * d, r0, rc)                                   # (shift_mlp, scale_mlp)
-                ops.gemm(xn, wf1[j], bf1[j], PF_EPI_GELU_BF16, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
-                         out=cat, ldo=5 * d, out_col_begin=d)
-                ops.gemm(cat[:, :, d:], wf2[j], bf2[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=r0,
+                ops.gemm(xn, wf1[j], bf1[j], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc,
+                         out=cat, ldo=ldc, out_col_begin=wa)
+                ops.gemm(cat[:, :, wa:], wf2[j], bf2[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
                          row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 5 * d:], gate_batch_stride=nm)  # gate_mlp
 
         for i, w in enumerate(self.sgl):
             o = self.mod_off[f"single_transformer_blocks.{i}.norm"]
-            lnmod(o, o + d, 0, s)                                                                  # (shift, scale) N:232
+            lnmod(o, o + d, 0, sl)                                                                 # (shift, scale) N:232
             # two launches sharing A: measured faster than the fused q|k|v|mlp GEMM (PF_EPI_QKV_GELU), whose 192-wide
             # tiles slow the MLP half down (1.81 ms fused vs 0.60 + 0.62 ms split at S=15488)
-            ops.gemm(xn, w["w_qkv"], w["b_qkv"], PF_EPI_QKV_ROPE, batches=b, rows_per_batch=s, row_begin=0, row_count=s,
-                     q_out=q, k_out=k, v_out=v, rope=plan.rope, q_norm_w=w["nq"], k_norm_w=w["nk"], heads=hn,
-                     head_dim=64, seq_len=s)
-            ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=s, row_begin=0, row_count=s,
-                     out=cat, ldo=5 * d, out_col_begin=d)
+            qkv(w["w_qkv"], w["b_qkv"], w["nq"], w["nk"], 0, sl)
+            ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=0, row_count=sl,
+                     out=cat, ldo=ldc, out_col_begin=wa)
             attention()
-            ops.gemm(cat, w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=0,
-                     row_count=s, out=h, ldo=d, gate=mod[:, o + 2 * d:], gate_batch_stride=nm)
+            ops.gemm(cat, w["w_out_p"] if pad else w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b,
+                     rows_per_batch=sl, row_begin=0, row_count=sl, out=h, ldo=d, gate=mod[:, o + 2 * d:],
+                     gate_batch_stride=nm)
 
         # ---- head: only the current clip's tokens are needed (F:380); AdaLN-continuous is (scale, shift) (N:119)
         n_last = plan.last_tokens
         o = self.mod_off["norm_out"]
-        lnmod(o + d, o, s - n_last, n_last)
-        ops.gemm(xn, self.w_out, self.b_out, PF_EPI_STORE_F32, batches=b, rows_per_batch=s, row_begin=s - n_last,
-                 row_count=n_last, out=ws["head"], ldo=c.in_channels, out_batch_rows=n_last, out_row_begin=0)
+        g0, g1 = max(s - n_last, c0), c1                 # my part of the last n_last tokens
+        head = ws["head"]
+        if par and nsp > 1:
+            head.zero_()
+        if g1 > g0:
+            lnmod(o + d, o, g0 - c0, g1 - g0)
+            ops.gemm(xn, self.w_out, self.b_out, PF_EPI_STORE_F32, batches=b, rows_per_batch=sl, row_begin=g0 - c0,
+                     row_count=g1 - g0, out=head, ldo=c.in_channels, out_batch_rows=n_last,
+                     out_row_begin=g0 - (s - n_last))
+        if par and nsp > 1:
+            torch.distributed.all_reduce(head, group=lay.sp_group)       # disjoint row blocks: sum == gather
         ct, chh, cww = plan.clip_thw[-1]
-        out = torch.empty(b, c.in_channels // 4, ct, chh * 2, cww * 2, device=self.device, dtype=clips[-1].dtype
-                          if clips[-1].dtype in (torch.float32, torch.bfloat16) else torch.float32)
-        ops.unpatchify(ws["head"], n_last, 0, out)
+        odt = clips[-1].dtype if clips[-1].dtype in (torch.float32, torch.bfloat16) else torch.float32
+        out = torch.empty(b, c.in_channels // 4, ct, chh * 2, cww * 2, device=self.device, dtype=odt)
+        ops.unpatchify(head, n_last, 0, out)
+        if par:
+            full = torch.empty(bg, *out.shape[1:], device=self.device, dtype=odt)
+            torch.distributed.all_gather_into_tensor(full, out, group=lay.cfg_group)   # [uncond ; cond]
+            out = full
         return [out]
 
     # accounting used by bench.py / DESIGN.md (SURVEY.md §8d "algorithmic work per unit")
