@@ -204,6 +204,43 @@ def make_sampler():
                                                                 video_guidance_scale=5.0)}, GOLD / "sampler_small.pt")
 
 
+MMDIT_SMALL = dict(num_layers=3, num_attention_heads=4, attention_head_dim=64, in_channels=16, patch_size=2,
+                   joint_attention_dim=128, pooled_projection_dim=64, pos_embed_max_size=24, sample_size=32)
+
+
+def make_mmdit():
+    from pyramid_dit.mmdit_modules import PyramidDiffusionMMDiT
+    from oracle import mmdit_oracle as MO
+    cfg = MO.MMDiTConfig(**MMDIT_SMALL)
+    params = MO.synthetic_mmdit_params(cfg, seed=0)
+    model = PyramidDiffusionMMDiT(sample_size=cfg.sample_size, patch_size=2, in_channels=16, num_layers=cfg.num_layers,
+                                  attention_head_dim=64, num_attention_heads=cfg.num_attention_heads,
+                                  caption_projection_dim=cfg.inner_dim, pooled_projection_dim=cfg.pooled_projection_dim,
+                                  pos_embed_max_size=cfg.pos_embed_max_size, joint_attention_dim=cfg.joint_attention_dim,
+                                  pos_embed_type="sincos", temp_pos_embed_type="rope", add_temp_pos_embed=True,
+                                  use_flash_attn=False, use_temporal_causal=True, use_t5_mask=True,
+                                  interp_condition_pos=True).eval()
+    sd = model.state_dict()
+    assert set(sd.keys()) == set(params.keys()), set(sd.keys()) ^ set(params.keys())
+    # the oracle's sincos table must equal the buffer the reference computed for itself
+    assert torch.allclose(sd["pos_embed.pos_embed"], params["pos_embed.pos_embed"], atol=1e-6)
+    model.load_state_dict(params, strict=True)
+    g = torch.Generator().manual_seed(1)
+    clips = [torch.randn(2, 16, 2, 4, 8, generator=g), torch.randn(2, 16, 1, 8, 16, generator=g),
+             torch.randn(2, 16, 1, 16, 32, generator=g)]
+    enc = torch.randn(2, 24, cfg.joint_attention_dim, generator=g) * 0.5
+    mask = torch.ones(2, 24, dtype=torch.long)
+    mask[0, 9:] = 0
+    pooled = torch.randn(2, cfg.pooled_projection_dim, generator=g)
+    t = torch.tensor([972.0, 972.0])
+    with torch.no_grad():
+        out = model(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask,
+                    pooled_projections=pooled)[0]
+    torch.save({"cfg": MMDIT_SMALL, "param_seed": 0, "clips": clips, "enc": enc, "mask": mask, "pooled": pooled,
+                "timestep": t, "out": out}, GOLD / "mmdit_small.pt")
+    print("mmdit_small:", out.shape, float(out.abs().mean()))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["flux", "block", "sched"]
     for w in which:

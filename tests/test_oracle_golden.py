@@ -72,3 +72,14 @@ def test_vae_decode_oracle_matches_reference(golden_dir):
     assert g["chunk1_maxdiff"] < 1e-4 and g["chunk2_maxdiff"] < 1e-4
     assert (tiled - g["tiled32"]).abs().max().item() < 5e-5
     assert g["full"].abs().mean().item() > 0.05
+
+
+def test_mmdit_small_forward_matches_reference(golden_dir):
+    from oracle import mmdit_oracle as MO
+    g = _load(golden_dir, "mmdit_small.pt")
+    cfg = MO.MMDiTConfig(**g["cfg"])
+    p = MO.synthetic_mmdit_params(cfg, seed=g["param_seed"])
+    with torch.no_grad():
+        out = MO.mmdit_forward(p, cfg, g["clips"], g["timestep"], g["enc"], g["mask"], g["pooled"])
+    assert (out - g["out"]).abs().max().item() < 2e-5
+    assert g["out"].abs().mean().item() > 0.1
