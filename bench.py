@@ -197,6 +197,47 @@ def random_flux_state_dict(cfg_kw, device, seed=0):
     return c, sd
 
 
+def random_vae_state_dict(device, seed=0, block_out_channels=(128, 256, 512, 512), layers_per_block=(3, 3, 3, 3),
+                          spatial_up=(True, True, True, False), temporal_up=(True, True, True, False), latent=16):
+    """Random-init causal-VAE decoder weights in the reference key layout (`decoder.*`, `post_quant_conv.*`)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    rev = list(reversed(block_out_channels))
+
+    def conv(name, co, ci, k):
+        sd[name + ".conv.weight"] = (torch.randn(co, ci, k, k, k, device=device, generator=g) * (ci * k ** 3) ** -0.5).cpu()
+        sd[name + ".conv.bias"] = (torch.randn(co, device=device, generator=g) * 0.02).cpu()
+
+    def norm(name, c):
+        sd[name + ".weight"] = (1 + 0.1 * torch.randn(c, device=device, generator=g)).cpu()
+        sd[name + ".bias"] = (0.05 * torch.randn(c, device=device, generator=g)).cpu()
+
+    def res(name, ci, co):
+        norm(name + ".norm1", ci); conv(name + ".conv1", co, ci, 3); norm(name + ".norm2", co); conv(name + ".conv2", co, co, 3)
+        if ci != co:
+            conv(name + ".conv_shortcut", co, ci, 1)
+
+    top = rev[0]
+    conv("post_quant_conv", latent, latent, 1); conv("decoder.conv_in", top, latent, 3)
+    res("decoder.mid_block.resnets.0", top, top); res("decoder.mid_block.resnets.1", top, top)
+    norm("decoder.mid_block.attentions.0.group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        sd[f"decoder.mid_block.attentions.0.{n}.weight"] = (torch.randn(top, top, device=device, generator=g) * top ** -0.5).cpu()
+        sd[f"decoder.mid_block.attentions.0.{n}.bias"] = (torch.randn(top, device=device, generator=g) * 0.02).cpu()
+    prev = top
+    for i, co in enumerate(rev):
+        for j in range(layers_per_block[i]):
+            res(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if spatial_up[i]:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", 4 * co, co, 3)
+        if temporal_up[i]:
+            conv(f"decoder.up_blocks.{i}.temporal_upsamplers.0.conv", 2 * co, co, 3)
+        prev = co
+    norm("decoder.conv_norm_out", block_out_channels[0]); conv("decoder.conv_out", 3, block_out_channels[0], 3)
+    return sd
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist

@@ -61,8 +61,14 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
   return r;
 }
 
-__device__ __forceinline__ void softmax_bar_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(ATT_SOFTMAX_WARPS * 32) : "memory");
+// the two warps that share a TMEM lane quarter (column halves 0/1 of the same 32 rows) meet on their own named barrier
+__device__ __forceinline__ void pair_bar_sync(int quarter) {
+  switch (quarter) {   // immediate barrier ids keep the CTA's barrier allocation at 5 instead of 16
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
 }
 
 // apply the element mask to 32 scores (bit i of `bits` = column i allowed)
@@ -281,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       const float m_part = fmaxf(max32(va), max32(vb));
       xch[j & 1][half][row] = m_part;
-      softmax_bar_sync();
+      pair_bar_sync(quarter);
       const float m_tile = fmaxf(m_part, xch[j & 1][half ^ 1][row]);
 
       // ---- lazy rescale decision (per row, same in both halves), correction is warp-collective
@@ -329,7 +335,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ---- epilogue: combine the two halves' row sums, O / l -> bf16 -> out[b, qpos, h*64 + half*32 .. +32]
     const float l_part = (l4[0] + l4[1]) + (l4[2] + l4[3]);
     xch[n_kv & 1][half][row] = l_part;
-    softmax_bar_sync();
+    pair_bar_sync(quarter);
     const float l_run = l_part + xch[n_kv & 1][half ^ 1][row];
     mbar_wait(&bar_pv_done, (n_kv - 1) & 1);
     tc_fence_after();

@@ -353,43 +353,9 @@ def group_vae_perf():
     from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
     from pyramid_flow_b200 import _lib
     dev = torch.device("cuda:0")
+    from bench import random_vae_state_dict
     cfg = VaeConfigB200()
-    # random decoder weights directly on the device (shapes from the reference key layout)
-    g = torch.Generator(device=dev).manual_seed(0)
-    sd = {}
-    rev = list(reversed(cfg.block_out_channels))
-
-    def conv(name, co, ci, k):
-        sd[name + ".conv.weight"] = torch.randn(co, ci, k, k, k, device=dev, generator=g) * (ci * k ** 3) ** -0.5
-        sd[name + ".conv.bias"] = torch.randn(co, device=dev, generator=g) * 0.02
-
-    def norm(name, c):
-        sd[name + ".weight"] = 1 + 0.1 * torch.randn(c, device=dev, generator=g)
-        sd[name + ".bias"] = 0.05 * torch.randn(c, device=dev, generator=g)
-
-    def res(name, ci, co):
-        norm(name + ".norm1", ci); conv(name + ".conv1", co, ci, 3); norm(name + ".norm2", co); conv(name + ".conv2", co, co, 3)
-        if ci != co:
-            conv(name + ".conv_shortcut", co, ci, 1)
-
-    top = rev[0]
-    conv("post_quant_conv", 16, 16, 1); conv("decoder.conv_in", top, 16, 3)
-    res("decoder.mid_block.resnets.0", top, top); res("decoder.mid_block.resnets.1", top, top)
-    norm("decoder.mid_block.attentions.0.group_norm", top)
-    for n in ("to_q", "to_k", "to_v", "to_out.0"):
-        sd[f"decoder.mid_block.attentions.0.{n}.weight"] = torch.randn(top, top, device=dev, generator=g) * top ** -0.5
-        sd[f"decoder.mid_block.attentions.0.{n}.bias"] = torch.randn(top, device=dev, generator=g) * 0.02
-    prev = top
-    for i, co in enumerate(rev):
-        for j in range(cfg.layers_per_block[i]):
-            res(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
-        if cfg.spatial_up_sample[i]:
-            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", 4 * co, co, 3)
-        if cfg.temporal_up_sample[i]:
-            conv(f"decoder.up_blocks.{i}.temporal_upsamplers.0.conv", 2 * co, co, 3)
-        prev = co
-    norm("decoder.conv_norm_out", cfg.block_out_channels[0]); conv("decoder.conv_out", 3, cfg.block_out_channels[0], 3)
-    sd = {k: v.cpu() for k, v in sd.items()}
+    sd = random_vae_state_dict(dev)
     vae = B200CausalVAE(cfg, sd, device=dev)
     for (T, h, w, win) in [(3, 48, 80, 2), (5, 96, 160, 2)]:
         z = torch.randn(1, 16, T, h, w, device=dev).bfloat16()
