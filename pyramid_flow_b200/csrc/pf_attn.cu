@@ -90,20 +90,37 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// p = exp2(s*c - m_ref) for 32 scores -> 16 packed bf16x2; accumulates the row sum into 4 independent chains
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic for 2^f (rel. err 6e-4,
+// well under bf16's 4e-3), n added into the exponent field.  Used for a fraction of the elements to unload the XU pipe,
+// which bounds this kernel at head_dim 64 (the trick of FlashAttention-4 on Blackwell).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;   // 1.5 * 2^23
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.0555041086648216f, 0.2402264923172690f);
+  p = fmaf(p, f, 0.6931471805599453f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// p = exp2(s*c - m_ref) for 32 scores -> 16 packed bf16x2; accumulates the row sum into 4 independent chains.
+// POLY = 1: every 4th element takes the polynomial path (25 % of the exponentials off the XU pipe).
+template <int POLY>
 __device__ __forceinline__ void exp32(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float m_ref, float (&l)[4]) {
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     const float p0 = ex2f(fmaf(__uint_as_float(v[2 * i + 0]), c, -m_ref));
     const float p1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -m_ref));
     const float p2 = ex2f(fmaf(__uint_as_float(v[2 * i + 2]), c, -m_ref));
-    const float p3 = ex2f(fmaf(__uint_as_float(v[2 * i + 3]), c, -m_ref));
+    const float x3 = fmaf(__uint_as_float(v[2 * i + 3]), c, -m_ref);
+    const float p3 = POLY ? ex2_poly(x3) : ex2f(x3);
     l[0] += p0; l[1] += p1; l[2] += p2; l[3] += p3;
     pk[i] = pack_bf16x2(p0, p1);
     pk[i + 1] = pack_bf16x2(p2, p3);
   }
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnArgs a) {
@@ -323,9 +340,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
       // ---- p = exp2(s*c - m_ref) -> P (bf16x2) in TMEM
       uint32_t pk[16];
-      exp32(va, pk, c, m_ref, l4);
-      tmem_st16(t_p, pk);
-      exp32(vb, pk, c, m_ref, l4);
+      if (POLY && !masked) {
+        exp32<1>(va, pk, c, m_ref, l4);
+        tmem_st16(t_p, pk);
+        exp32<1>(vb, pk, c, m_ref, l4);
+      } else {
+        exp32<0>(va, pk, c, m_ref, l4);
+        tmem_st16(t_p, pk);
+        exp32<0>(vb, pk, c, m_ref, l4);
+      }
       tmem_st16(t_p + 16, pk);
       tmem_st_wait();
       tc_fence_before();
@@ -457,7 +480,9 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("pf_attn_fwd_masked: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return -2;
@@ -465,6 +490,9 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
     attr_set = true;
   }
   dim3 grid(q_tiles, d->heads, d->batch);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  if (d->variant & 1)
+    attn_fwd_kernel<1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  else
+    attn_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked");
 }
