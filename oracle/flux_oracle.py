@@ -25,6 +25,7 @@ import torch
 import torch.nn.functional as F
 
 Params = Dict[str, torch.Tensor]
+HEAD_CHUNK = 0   # >0: run SDPA over this many heads at a time (bounds the S x S score memory at full size)
 
 
 @dataclass
@@ -162,9 +163,14 @@ def joint_attention(q, k, v, cs, mask, heads):
     q,k,v [B, S, H, hd] -> rope(q,k) -> SDPA(mask) -> [B, S, H*hd]."""
     q = apply_rope(q, cs)
     k = apply_rope(k, cs)
-    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), dropout_p=0.0,
-                                       is_causal=False, attn_mask=mask)
-    return o.transpose(1, 2).flatten(2, 3)
+    hc = HEAD_CHUNK or q.shape[2]          # memory knob for full-size runs (identical arithmetic per head)
+    outs = []
+    for h0 in range(0, q.shape[2], hc):
+        sl = slice(h0, h0 + hc)
+        outs.append(F.scaled_dot_product_attention(q[:, :, sl].transpose(1, 2), k[:, :, sl].transpose(1, 2),
+                                                   v[:, :, sl].transpose(1, 2), dropout_p=0.0, is_causal=False,
+                                                   attn_mask=mask).transpose(1, 2))
+    return torch.cat(outs, dim=2).flatten(2, 3)
 
 
 def double_block(p: Params, pre: str, x, ctx, temb, cs, mask, heads):

@@ -400,7 +400,7 @@ class B200FluxTransformer(torch.nn.Module):
                     e1.record()
             else:
                 # Ulysses exchange: all (padded) heads of my token chunk -> my head group over the whole sequence
-                qf, kf, vf = (SP.heads_to_sequence(t_[0], lay) for t_ in (q, k, v))
+                qf, kf, vf = SP.heads_to_sequence_qkv(q[0], k[0], v[0], lay)
                 of = ws["of"]
                 if ev:
                     e0.record()
@@ -465,6 +465,8 @@ class B200FluxTransformer(torch.nn.Module):
             torch.distributed.all_reduce(head, group=lay.sp_group)       # disjoint row blocks: sum == gather
         ct, chh, cww = plan.clip_thw[-1]
         odt = clips[-1].dtype if clips[-1].dtype in (torch.float32, torch.bfloat16) else torch.float32
+        if getattr(self, "output_fp32", False):       # fused CFG+Euler path of the sampler keeps the velocity in fp32
+            odt = torch.float32
         out = torch.empty(b, c.in_channels // 4, ct, chh * 2, cww * 2, device=self.device, dtype=odt)
         ops.unpatchify(head, n_last, 0, out)
         if par:

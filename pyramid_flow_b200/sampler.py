@@ -42,13 +42,17 @@ def block_noise(bs: int, ch: int, temp: int, height: int, width: int, gamma: flo
 class B200PyramidSampler:
     def __init__(self, dit, scheduler, vae=None, stages: Sequence[int] = (1, 2, 4), frame_per_unit: int = 1,
                  model_name: str = "pyramid_flux", downsample: int = 8,
-                 block_noise_fn: Optional[Callable[..., torch.Tensor]] = None):
+                 block_noise_fn: Optional[Callable[..., torch.Tensor]] = None, fused_step: bool = False):
         self.dit, self.scheduler, self.vae = dit, scheduler, vae
         self.stages = list(stages)
         self.frame_per_unit = frame_per_unit
         self.downsample = downsample
         self.model_name = model_name
         self.block_noise_fn = block_noise_fn
+        # fused_step: CFG combine + Euler update in ONE kernel on fp32 velocities (pf_cfg_euler_step, reference P:771-776 +
+        # S:278-286); the result is rounded to the latent dtype once.  Opt-in: it rounds less than the reference's bf16 chain
+        # (bf16 CFG combine, bf16 dsigma*v), so outputs differ from the reference at bf16 resolution.
+        self.fused_step = fused_step
         # latent normalisation constants (P:160-176)
         if model_name == "pyramid_flux":
             self.vae_shift_factor, self.vae_scale_factor = -0.04, 1 / 1.8726
@@ -96,6 +100,14 @@ class B200PyramidSampler:
                 v = self.dit(sample=[clips], timestep_ratio=timestep, encoder_hidden_states=prompt_embeds,
                              encoder_attention_mask=prompt_attention_mask, pooled_projections=pooled_prompt_embeds)[0]
                 self.dit_calls += 1
+                if self.fused_step and do_cfg and v.dtype == torch.float32:
+                    from . import ops
+                    g = guidance_scale if is_first_frame else video_guidance_scale
+                    x32 = latents.float().contiguous()
+                    ops.cfg_euler_step(v.contiguous(), float(g), self.scheduler.delta_sigma(), x32, x32)
+                    self.scheduler.advance()
+                    latents = x32.to(latents.dtype) if latents.dtype != torch.float32 else x32
+                    continue
                 if do_cfg:
                     vu, vc = v.chunk(2)
                     g = guidance_scale if is_first_frame else video_guidance_scale

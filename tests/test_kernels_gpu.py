@@ -1,0 +1,168 @@
+"""Per-kernel parity through the C-ABI on B200 (ragged shapes included): GEMM epilogues, attention mask cases,
+elementwise kernels.  The checker for a single floating-point kernel is a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-20)).item()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (1, 64, 64), (129, 256, 128), (300, 1920, 1920), (1000, 192, 512),
+                                   (777, 128, 4096), (2048, 1920, 9600), (5, 7680, 1920)])
+def test_gemm_bias_store(m, n, k):
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(m * 7 + n)
+    x = (torch.randn(m, k, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    b = torch.randn(n, device=DEV)
+    y = ops.linear_bf16(x, w, b)
+    torch.cuda.synchronize()
+    assert _rel(y, x.float() @ w.float().t() + b) < 8e-3      # bf16 output rounding: 2^-8 relative
+
+
+def test_gemm_rejects_bad_shapes():
+    from pyramid_flow_b200 import ops
+    x = torch.zeros(8, 60, device=DEV, dtype=torch.bfloat16)      # K not a multiple of 8 elements / N not a multiple of 64
+    w = torch.zeros(100, 60, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.linear_bf16(x, w, None)
+
+
+def test_gemm_epilogues_row_ranges():
+    from pyramid_flow_b200 import ops
+    from pyramid_flow_b200._lib import PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_QKV_GELU, PF_EPI_QKV_ROPE, PF_EPI_STORE_F32
+    torch.manual_seed(1)
+    B, S, D, H, T0, hd = 2, 300, 384, 6, 40, 64
+    x = (torch.randn(B, S, D, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(4 * D, D, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(4 * D, device=DEV) * 0.1
+    out = torch.zeros(B, S, 4 * D, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, w, bias, PF_EPI_GELU_BF16, batches=B, rows_per_batch=S, row_begin=T0, row_count=S - T0, out=out)
+    ref = F.gelu(x[:, T0:].float() @ w.float().t() + bias, approximate="tanh")
+    assert _rel(out[:, T0:], ref) < 8e-3 and bool((out[:, :T0] == 0).all())
+    w2 = (torch.randn(D, D, device=DEV) * 0.05).bfloat16()
+    b2 = torch.randn(D, device=DEV) * 0.1
+    o32 = torch.zeros(B, S, D, device=DEV)
+    ops.gemm(x, w2, b2, PF_EPI_STORE_F32, batches=B, rows_per_batch=S, row_begin=0, row_count=T0, out=o32)
+    assert _rel(o32[:, :T0], x[:, :T0].float() @ w2.float().t() + b2) < 1e-5 and bool((o32[:, T0:] == 0).all())
+    resid = torch.randn(B, S, D, device=DEV)
+    r0 = resid.clone()
+    gate = torch.randn(B, 3 * D, device=DEV)
+    ops.gemm(x, w2, b2, PF_EPI_GATE_RESID, batches=B, rows_per_batch=S, row_begin=T0, row_count=S - T0, out=resid,
+             gate=gate[:, D:], gate_batch_stride=3 * D)
+    ref = r0[:, T0:] + gate[:, None, D:2 * D] * (x[:, T0:].float() @ w2.float().t() + b2)
+    assert _rel(resid[:, T0:], ref) < 1e-5 and bool((resid[:, :T0] == r0[:, :T0]).all())
+    # QKV: bias + per-head RMSNorm + RoPE, head-major stores
+    wq = (torch.randn(3 * D, D, device=DEV) * 0.05).bfloat16()
+    bq = torch.randn(3 * D, device=DEV) * 0.1
+    qn, kn = 1 + 0.1 * torch.randn(hd, device=DEV), 1 + 0.1 * torch.randn(hd, device=DEV)
+    ang = torch.randn(S, hd // 2, device=DEV)
+    rope = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+
+    def ref_qkv(xr, pos0):
+        y = xr.float() @ wq.float().t() + bq
+        qq, kk, vv = y.chunk(3, dim=-1)
+        n = xr.shape[1]
+
+        def nr(t, wn):
+            t = t.view(B, n, H, hd)
+            t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + 1e-6) * wn
+            c, s_ = rope[pos0:pos0 + n, :, 0][None, :, None, :], rope[pos0:pos0 + n, :, 1][None, :, None, :]
+            t2 = t.view(B, n, H, hd // 2, 2)
+            return torch.stack([c * t2[..., 0] - s_ * t2[..., 1], s_ * t2[..., 0] + c * t2[..., 1]], -1).view(B, n, H, hd).transpose(1, 2)
+        return nr(qq, qn), nr(kk, kn), vv.view(B, n, H, hd).transpose(1, 2)
+
+    qo = torch.zeros(B, H, S, hd, device=DEV, dtype=torch.bfloat16)
+    ko, vo = torch.zeros_like(qo), torch.zeros_like(qo)
+    ops.gemm(x, wq, bq, PF_EPI_QKV_ROPE, batches=B, rows_per_batch=S, row_begin=T0, row_count=S - T0, q_out=qo, k_out=ko,
+             v_out=vo, rope=rope, q_norm_w=qn, k_norm_w=kn, heads=H, head_dim=hd, seq_len=S)
+    rq, rk, rv = ref_qkv(x[:, T0:], T0)
+    assert _rel(qo[:, :, T0:], rq) < 8e-3 and _rel(ko[:, :, T0:], rk) < 8e-3 and _rel(vo[:, :, T0:], rv) < 8e-3
+    assert bool((qo[:, :, :T0] == 0).all())
+    wm = (torch.randn(4 * D, D, device=DEV) * 0.05).bfloat16()
+    bm = torch.randn(4 * D, device=DEV) * 0.1
+    cat = torch.zeros(B, S, 5 * D, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, torch.cat([wq, wm], 0).contiguous(), torch.cat([bq, bm], 0).contiguous(), PF_EPI_QKV_GELU, batches=B,
+             rows_per_batch=S, row_begin=0, row_count=S, out=cat, out_col_begin=D, q_out=qo, k_out=ko, v_out=vo, rope=rope,
+             q_norm_w=qn, k_norm_w=kn, heads=H, head_dim=hd, seq_len=S, n_split=3 * D)
+    rq, rk, rv = ref_qkv(x, 0)
+    assert _rel(qo, rq) < 8e-3 and _rel(vo, rv) < 8e-3
+    assert _rel(cat[..., D:], F.gelu(x.float() @ wm.float().t() + bm, approximate="tanh")) < 8e-3
+
+
+def _attn_case(B, H, S, seg, tim):
+    from pyramid_flow_b200 import ops
+    q = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    k = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    v = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
+    sched, pairs = ops.attn_build_schedule(seg, tim)
+    ops.attn_fwd(q, k, v, out, seg.to(DEV).int(), tim.to(DEV).int(), sched.to(DEV), 0.125)
+    torch.cuda.synchronize()
+    sg, tm = seg.to(DEV), tim.to(DEV)
+    mask = (sg[:, :, None] == sg[:, None, :]) & (tm[:, :, None] >= tm[:, None, :])
+    assert int(pairs.sum()) == int(mask.sum())
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=mask[:, None]).transpose(1, 2).reshape(B, S, H * 64)
+    return (out.float() - ref).abs().max().item()
+
+
+def test_attention_mask_cases():
+    torch.manual_seed(3)
+    # shorter than one tile; dense; tile-aligned causal; ragged text + frames not aligned to tiles; sequence tail
+    assert _attn_case(1, 2, 77, torch.ones(1, 77, dtype=torch.int32), torch.zeros(1, 77, dtype=torch.int32)) < 2e-2
+    assert _attn_case(1, 2, 256, torch.ones(1, 256, dtype=torch.int32), torch.zeros(1, 256, dtype=torch.int32)) < 2e-2
+    tim = torch.cat([torch.zeros(128), torch.ones(128), 2 * torch.ones(128)]).int()[None]
+    assert _attn_case(1, 2, 384, torch.ones(1, 384, dtype=torch.int32), tim) < 2e-2
+    S = 128 + 60 * 5
+    tim = torch.cat([torch.zeros(128 + 60)] + [torch.full((60,), i + 1.0) for i in range(4)]).int()[None].repeat(2, 1)
+    seg = torch.ones(2, S, dtype=torch.int32)
+    seg[0, 37:128] = 0
+    assert _attn_case(2, 3, S, seg, tim) < 2e-2
+    S = 77 + 240 * 9 + 13
+    tim = torch.cat([torch.zeros(77 + 240)] + [torch.full((240,), i + 1.0) for i in range(8)] + [torch.full((13,), 9.0)]).int()[None].repeat(2, 1)
+    seg = torch.ones(2, S, dtype=torch.int32)
+    seg[1, 50:77] = 0
+    assert _attn_case(2, 4, S, seg, tim) < 2e-2
+
+
+def test_elementwise_kernels():
+    from einops import rearrange
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(2)
+    B, S, D = 2, 333, 1920
+    x = torch.randn(B, S, D, device=DEV) * 2 + 0.3
+    mod = torch.randn(B, 6 * D, device=DEV) * 0.3
+    y = torch.zeros(B, S, D, device=DEV, dtype=torch.bfloat16)
+    ops.ln_modulate(x, y, mod[:, 0:], mod[:, D:], 6 * D, batches=B, rows_per_batch=S, row_begin=77, row_count=S - 77)
+    ref = F.layer_norm(x[:, 77:], (D,), eps=1e-6) * (1 + mod[:, None, D:2 * D]) + mod[:, None, :D]
+    assert _rel(y[:, 77:], ref) < 8e-3 and bool((y[:, :77] == 0).all())
+    xm = torch.randn(2, 1920, device=DEV)
+    w = (torch.randn(5000, 1920, device=DEV) * 0.05).bfloat16()
+    b = torch.randn(5000, device=DEV)
+    yo = torch.zeros(2, 5000, device=DEV)
+    ops.small_linear(xm, w, b, yo, act_in=1)
+    ref = F.silu(xm) @ w.float().t() + b
+    assert _rel(yo, ref) < 1e-5
+    ops.small_linear(xm, w, b, yo, act_out=1, accumulate=True)
+    assert _rel(yo, ref + F.silu(xm @ w.float().t() + b)) < 1e-5
+    t = torch.tensor([972.0, 3.5], device=DEV)
+    e = ops.timestep_embedding(t, 256, round_bf16=False)
+    arg = t[:, None] * torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(128, device=DEV).float() / 128)[None]
+    assert (e - torch.cat([arg.cos(), arg.sin()], -1)).abs().max().item() < 2e-3     # |arg| ~ 1e3: fp32 sin/cos ulps
+    lat = torch.randn(2, 16, 2, 8, 12, device=DEV).bfloat16()
+    L = 2 * 4 * 6
+    tok = torch.zeros(2, 10 + L, 64, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(lat, tok, 10 + L, 10)
+    ref = rearrange(rearrange(lat, "b c t h w -> b t h w c"), "b t (h p1) (w p2) c -> b (t h w) (p1 p2 c)", p1=2, p2=2)
+    assert bool((tok[:, 10:] == ref).all())                                           # byte/index work: bit-exact
+    out = torch.zeros(2, 16, 2, 8, 12, device=DEV)
+    ops.unpatchify(tok.float().contiguous(), 10 + L, 10, out)
+    assert bool((out == lat.float()).all())
+    v2, xs, xo = torch.randn(2, 1000, device=DEV), torch.randn(1000, device=DEV), torch.zeros(1000, device=DEV)
+    ops.cfg_euler_step(v2, 5.0, -0.05, xs, xo)
+    assert (xo - (xs + (-0.05) * (v2[0] + 5.0 * (v2[1] - v2[0])))).abs().max().item() < 1e-5

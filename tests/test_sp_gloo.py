@@ -30,6 +30,10 @@ def _worker(rank, world, port, ret):
         mine = SP.heads_to_sequence(q_full[:, c0:c1].contiguous(), lay)
         hg = hp // lay.sp
         assert torch.equal(mine, q_full[lay.sp_rank * hg:(lay.sp_rank + 1) * hg])       # my head group, whole sequence
+        k_full, v_full = q_full * 2, q_full + 1
+        a, b_, c_ = SP.heads_to_sequence_qkv(*(t[:, c0:c1].contiguous() for t in (q_full, k_full, v_full)), lay)
+        sl_h = slice(lay.sp_rank * hg, (lay.sp_rank + 1) * hg)
+        assert torch.equal(a, q_full[sl_h]) and torch.equal(b_, k_full[sl_h]) and torch.equal(c_, v_full[sl_h])
         # inverse exchange on the token-major attention output [S, Hg*hd]
         o_full = torch.randn(seq, hp * hd, generator=g)                                  # all heads, token major
         o_mine = o_full[:, lay.sp_rank * hg * hd:(lay.sp_rank + 1) * hg * hd].contiguous()

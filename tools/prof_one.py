@@ -23,6 +23,25 @@ if which == "attn":
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
     for _ in range(reps):
         ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125)
+elif which == "conv":
+    # the widest full-resolution resnet conv of the VAE decode: 128 -> 128, 3x3x3, one 768x1280 frame chunk
+    from pyramid_flow_b200.vae import B200CausalVAE, _Conv
+    ci = co = 128
+    t, h, w = 2, 768, 1280
+    wt = (torch.randn(co, ci, 3, 3, 3) * (ci * 27) ** -0.5)
+    cv = _Conv({"c.conv.weight": wt, "c.conv.bias": torch.zeros(co)}, "c", torch.device(dev))
+    x = torch.randn(t + 2, h, w, ci, device=dev).bfloat16()
+    out = torch.empty(t, h, w, co, device=dev, dtype=torch.bfloat16)
+    holder = B200CausalVAE.__new__(B200CausalVAE)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(reps):
+        if i == reps - 1:
+            e0.record()
+        B200CausalVAE._conv(holder, cv, x, t, h, w, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    fl = 2.0 * 27 * ci * co * t * h * w
+    print(f"conv 128->128 3x3x3 on {t}x{h}x{w}: {e0.elapsed_time(e1):.3f} ms, {fl / e0.elapsed_time(e1) / 1e9:.0f} TFLOP/s")
 elif which == "gemm":
     m, n, k = 30976, 7680, 1920
     x = (torch.randn(m, k, device=dev) * 0.5).bfloat16()
