@@ -12,6 +12,8 @@
 // Epilogues (include/pf_b200.h PF_EPI_*): bias / GELU-tanh / fp32 store / gate*x+residual / per-head RMSNorm + RoPE
 // with head-major Q,K,V stores / the single-block fused q|k|v|mlp split.
 // Reference op sites are listed in include/pf_b200.h at pf_gemm_bf16.
+#include <cstdlib>
+
 #include "../../include/pf_b200.h"
 #include "pf_common.cuh"
 
@@ -146,6 +148,63 @@ __device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t ta
   }
 }
 
+// Epilogue of one 128-row accumulator slice: this thread owns output row `m` (TMEM lane), columns [n_base, n_base + BN).
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int b, int m, int n_base) {
+  const bool valid = m < g.row_count;
+  const size_t out_row = static_cast<size_t>(b) * g.out_batch_rows + g.out_row_begin + m;
+  bool qkv_tile = (EPI == PF_EPI_QKV_ROPE);
+  if (EPI == PF_EPI_QKV_GELU) qkv_tile = n_base < g.n_split;
+
+  if (qkv_tile) {
+#pragma unroll 1
+    for (int h = 0; h < BN / 64; ++h) {
+      qkv_head_epilogue(g, taddr + h * 64, n_base + h * 64, b, g.out_row_begin + m, valid);
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait();
+      const int n0 = n_base + c * 32;
+      float x[32];
+      add_bias32(x, v, g.bias ? g.bias + n0 : nullptr);
+      if (EPI == PF_EPI_GELU_BF16 || EPI == PF_EPI_QKV_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = gelu_tanh_f(x[i]);
+      }
+      if (EPI == PF_EPI_STORE_BF16 || EPI == PF_EPI_GELU_BF16 || EPI == PF_EPI_QKV_GELU) {
+        const int col = (EPI == PF_EPI_QKV_GELU) ? (g.out_col_begin + n0 - g.n_split) : (g.out_col_begin + n0);
+        if (valid) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + col, x);
+      } else if (EPI == PF_EPI_STORE_F32) {
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
+                                                 g.out_col_begin + n0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        }
+      } else if (EPI == PF_EPI_GATE_RESID) {
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
+                                                 g.out_col_begin + n0);
+          const float4* g4 = reinterpret_cast<const float4*>(g.gate + b * g.gate_batch_stride + n0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 rr = d4[i];
+            const float4 gg = __ldg(g4 + i);
+            rr.x += gg.x * x[4 * i + 0];
+            rr.y += gg.y * x[4 * i + 1];
+            rr.z += gg.z * x[4 * i + 2];
+            rr.w += gg.w * x[4 * i + 3];
+            d4[i] = rr;
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -259,64 +318,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int mt = r / g.n_tiles;
       const int nt = r - mt * g.n_tiles;
       const int m = mt * BM + q * 32 + lane;
-      const bool valid = m < g.row_count;
-      const size_t out_row = static_cast<size_t>(b) * g.out_batch_rows + g.out_row_begin + m;
       const int n_base = nt * BN;
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      bool qkv_tile = (EPI == PF_EPI_QKV_ROPE);
-      if (EPI == PF_EPI_QKV_GELU) qkv_tile = n_base < g.n_split;
-
-      if (qkv_tile) {
-#pragma unroll 1
-        for (int h = 0; h < BN / 64; ++h) {
-          qkv_head_epilogue(g, taddr + h * 64, n_base + h * 64, b, g.out_row_begin + m, valid);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          const int n0 = n_base + c * 32;
-          float x[32];
-          add_bias32(x, v, g.bias ? g.bias + n0 : nullptr);
-          if (EPI == PF_EPI_GELU_BF16 || EPI == PF_EPI_QKV_GELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = gelu_tanh_f(x[i]);
-          }
-          if (EPI == PF_EPI_STORE_BF16 || EPI == PF_EPI_GELU_BF16 || EPI == PF_EPI_QKV_GELU) {
-            const int col = (EPI == PF_EPI_QKV_GELU) ? (g.out_col_begin + n0 - g.n_split) : (g.out_col_begin + n0);
-            if (valid) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + col, x);
-          } else if (EPI == PF_EPI_STORE_F32) {
-            if (valid) {
-              float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
-                                                     g.out_col_begin + n0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) d4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            }
-          } else if (EPI == PF_EPI_GATE_RESID) {
-            if (valid) {
-              float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
-                                                     g.out_col_begin + n0);
-              const float4* g4 = reinterpret_cast<const float4*>(g.gate + b * g.gate_batch_stride + n0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 rr = d4[i];
-                const float4 gg = __ldg(g4 + i);
-                rr.x += gg.x * x[4 * i + 0];
-                rr.y += gg.y * x[4 * i + 1];
-                rr.z += gg.z * x[4 * i + 2];
-                rr.w += gg.w * x[4 * i + 3];
-                d4[i] = rr;
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, EPI>(g, taddr, b, m, n_base);
       // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand the buffer back
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -333,6 +341,188 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA pair (one cluster, one TPC) computes a 256 x BN tile.  Each CTA loads its own 128 A
+// rows and HALF of the W tile; the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs'
+// shared memory, so per-CTA smem/L2 traffic for W halves and the stages get deeper.  Barrier protocol:
+//   full[s]  (leader): 2 arrivals (each CTA's producer; the leader's carries expect_tx for BOTH CTAs' bytes); both CTAs'
+//                      TMA loads credit the leader's barrier (peer-bit-masked address)
+//   empty[s], tmem_full[a] (both CTAs): signalled by ONE multicast tcgen05.commit from the leader
+//   tmem_empty[a] (leader): 256 arrivals — the 128 epilogue threads of each CTA (the peer's arrive remotely)
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 192) ? 7 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     const GemmArgs g) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 256);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();          // barriers of both CTAs are initialised before anyone touches a remote one
+  if (warp == 2) {
+    tmem_alloc2(&tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int num_kb = (g.k + BK - 1) / BK;
+  const int m2_tiles = (g.row_count + 2 * BM - 1) / (2 * BM);
+  const int tiles_per_batch = m2_tiles * g.n_tiles;
+  const int total_tiles = g.batches * tiles_per_batch;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer (both CTAs) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int mt = r / g.n_tiles;
+      const int nt = r - mt * g.n_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+        else mbar_arrive_remote(&full_bar[stage], 0);
+        tma_load_3d_2cta(sa, &tm_a, &full_bar[stage], kb * BK, g.row_begin + mt * 2 * BM + static_cast<int>(rank) * BM, b);
+        tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_b, &full_bar[stage], kb * BK, nt * BN + static_cast<int>(rank) * (BN / 2));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===== MMA issuer (leader CTA only) =====
+    constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc_kmajor_sw128(sa);
+        const uint64_t db = make_smem_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk)
+          umma_ss_2cta(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+        umma_commit_2cta(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit_2cta(&tmem_full_bar[acc]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs: each drains its own 128 rows from its own TMEM) =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int mt = r / g.n_tiles;
+      const int nt = r - mt * g.n_tiles;
+      const int m = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
+      const int n_base = nt * BN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      epilogue_tile<BN, EPI>(g, taddr, b, m, n_base);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // nobody frees TMEM / exits while the peer may still reference this CTA's smem or barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm2(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm2_bf16_tc_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gemm2 smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const int m2_tiles = (g.row_count + 2 * BM - 1) / (2 * BM);
+  const int total = g.batches * m2_tiles * g.n_tiles;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  int clusters = sms / 2;
+  if (total < clusters) clusters = total;
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_b, g);
+  return check_launch("pf_gemm_bf16(2cta)");
 }
 
 template <int BN, int EPI>
@@ -358,7 +548,14 @@ static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const G
 
 template <int EPI>
 static int dispatch_bn(int bn, const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmArgs& g,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool two_cta) {
+  if (two_cta) {
+    switch (bn) {
+      case 256: return launch_gemm2<256, EPI>(tm_a, tm_b, g, stream);
+      case 192: return launch_gemm2<192, EPI>(tm_a, tm_b, g, stream);
+      case 128: return launch_gemm2<128, EPI>(tm_a, tm_b, g, stream);
+    }
+  }
   switch (bn) {
     case 256: return launch_gemm<256, EPI>(tm_a, tm_b, g, stream);
     case 192: return launch_gemm<192, EPI>(tm_a, tm_b, g, stream);
@@ -445,6 +642,14 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   g.seq_len = d->seq_len;
   g.n_split = d->n_split;
 
+  // 2-CTA tiles (256 x BN) when the problem is big enough to feed 74 CTA pairs; PF_GEMM_2CTA=0/1 overrides
+  static const int env_2cta = [] {
+    const char* e = getenv("PF_GEMM_2CTA");
+    return e ? atoi(e) : -1;
+  }();
+  bool two_cta = bn >= 128 && d->row_count >= 1024;
+  if (env_2cta == 0) two_cta = false;
+  if (env_2cta == 1 && bn >= 128) two_cta = true;
   CUtensorMap tm_a, tm_b;
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->rows_per_batch),
@@ -459,19 +664,19 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->n)};
     const uint64_t strides[1] = {static_cast<uint64_t>(d->k) * 2};
-    const uint32_t box[2] = {BK, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(two_cta ? bn / 2 : bn)};
     int rc = encode_tensor_map(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 
   switch (epi) {
-    case PF_EPI_STORE_BF16: return dispatch_bn<PF_EPI_STORE_BF16>(bn, tm_a, tm_b, g, stream);
-    case PF_EPI_GELU_BF16: return dispatch_bn<PF_EPI_GELU_BF16>(bn, tm_a, tm_b, g, stream);
-    case PF_EPI_STORE_F32: return dispatch_bn<PF_EPI_STORE_F32>(bn, tm_a, tm_b, g, stream);
-    case PF_EPI_GATE_RESID: return dispatch_bn<PF_EPI_GATE_RESID>(bn, tm_a, tm_b, g, stream);
-    case PF_EPI_QKV_ROPE: return dispatch_bn<PF_EPI_QKV_ROPE>(bn, tm_a, tm_b, g, stream);
-    case PF_EPI_QKV_GELU: return dispatch_bn<PF_EPI_QKV_GELU>(bn, tm_a, tm_b, g, stream);
+    case PF_EPI_STORE_BF16: return dispatch_bn<PF_EPI_STORE_BF16>(bn, tm_a, tm_b, g, stream, two_cta);
+    case PF_EPI_GELU_BF16: return dispatch_bn<PF_EPI_GELU_BF16>(bn, tm_a, tm_b, g, stream, two_cta);
+    case PF_EPI_STORE_F32: return dispatch_bn<PF_EPI_STORE_F32>(bn, tm_a, tm_b, g, stream, two_cta);
+    case PF_EPI_GATE_RESID: return dispatch_bn<PF_EPI_GATE_RESID>(bn, tm_a, tm_b, g, stream, two_cta);
+    case PF_EPI_QKV_ROPE: return dispatch_bn<PF_EPI_QKV_ROPE>(bn, tm_a, tm_b, g, stream, two_cta);
+    case PF_EPI_QKV_GELU: return dispatch_bn<PF_EPI_QKV_GELU>(bn, tm_a, tm_b, g, stream, two_cta);
   }
   return -1;
 }
