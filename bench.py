@@ -376,7 +376,11 @@ def run_ours(args):
                      "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
                      "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg,
                      "share_of_step": (attn_avg * n_attn / ms_step) if ms_step else None,
-                     "algorithmic_flops_per_launch": attn_flops_launch, "traffic": None},
+                     "algorithmic_flops_per_launch": attn_flops_launch,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
+                     # shape (profiles/r01_attn_v1_6_ncu.txt: 357.3 MB + 104.2 MB) = the algorithmic Q+K+V+O bytes
+                     "traffic": 461.5e6 if lay is None else None, "traffic_unit": "B/launch",
+                     "algorithmic_bytes_per_launch": 4.0 * b * plan.seq * cfg.inner_dim * 2},
     }
     if args.no_cpu:
         line["cpu_baseline"] = None

@@ -12,6 +12,8 @@
 // operand; no im2col buffer exists anywhere.  Pipeline / warp roles are the GEMM's (pf_gemm.cu).
 // Epilogue: bias (+ residual) -> bf16/fp32 channels-last store, optionally through the depth-to-space addressing of
 // CausalUpsample2x (R:616) / CausalTemporalUpsample2x (R:724-727) so the rearrange copy disappears.
+#include <cstdlib>
+
 #include "../../include/pf_b200.h"
 #include "pf_common.cuh"
 
@@ -46,6 +48,100 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
+
+// Epilogue of one 128-voxel accumulator slice: this thread owns voxel (bb, tt, hh, ww), conv channels [n_base, n_base+BN).
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& g, uint32_t taddr, int bb, int tt, int hh, int ww,
+                                                   bool valid, int n_base) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 16; ++c) {
+    uint32_t v[16];
+    tmem_ld16(taddr + c * 16, v);
+    tmem_ld_wait();
+    const int n0 = n_base + c * 16;
+    if (!valid || n0 >= g.store_channels) continue;
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n0 + i) : 0.f);
+    if (g.store_mode == 0) {
+      const int to = tt + g.out_t_offset;
+      if (to < 0 || to >= g.out_t_total) continue;
+      const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + hh) * g.out_w + ww;
+      if (g.residual != nullptr) {
+        const size_t rvox = ((static_cast<size_t>(bb) * g.res_t_total + (tt + g.res_t_offset)) * g.out_h + hh) * g.out_w + ww;
+        const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + rvox * g.out_c + n0);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint4 rv = __ldg(r4 + u);
+          const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(hv[i]);
+            x[8 * u + 2 * i] += f.x;
+            x[8 * u + 2 * i + 1] += f.y;
+          }
+        }
+      }
+      const int nvalid = g.store_channels - n0;
+      if (g.out_f32) {
+        float* dst = reinterpret_cast<float*>(g.out) + vox * g.out_c + n0;
+        if (nvalid >= 16 && (g.out_c & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < nvalid) dst[i] = x[i];
+        }
+      } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + vox * g.out_c + n0;
+        if (nvalid >= 16 && (g.out_c & 7) == 0) {
+          uint4 u0, u1;
+          u0.x = pack_bf16x2(x[0], x[1]); u0.y = pack_bf16x2(x[2], x[3]); u0.z = pack_bf16x2(x[4], x[5]); u0.w = pack_bf16x2(x[6], x[7]);
+          u1.x = pack_bf16x2(x[8], x[9]); u1.y = pack_bf16x2(x[10], x[11]); u1.z = pack_bf16x2(x[12], x[13]); u1.w = pack_bf16x2(x[14], x[15]);
+          reinterpret_cast<uint4*>(dst)[0] = u0;
+          reinterpret_cast<uint4*>(dst)[1] = u1;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < nvalid) dst[i] = __float2bfloat16(x[i]);
+        }
+      }
+    } else if (g.store_mode == 1) {
+      // 'b (c p1 p2) t h w -> b c t (h p1) (w p2)': conv channel n = 4c + 2 p1 + p2; 16 n = 4 output channels x 4 pixels
+      const int to = tt + g.out_t_offset;
+      if (to < 0 || to >= g.out_t_total) continue;
+      const int c0 = n0 >> 2;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int p1 = p >> 1, p2 = p & 1;
+        const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + (2 * hh + p1)) * g.out_w + (2 * ww + p2);
+        uint2 u;
+        u.x = pack_bf16x2(x[0 + p], x[4 + p]);
+        u.y = pack_bf16x2(x[8 + p], x[12 + p]);
+        *reinterpret_cast<uint2*>(base + vox * g.out_c + c0) = u;
+      }
+    } else {
+      // 'b (c p) t h w -> b c (t p) h w': conv channel n = 2c + p; frame 2t + p (+offset; negative = dropped frame)
+      const int c0 = n0 >> 1;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.out);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int to = 2 * tt + p + g.out_t_offset;
+        if (to < 0 || to >= g.out_t_total) continue;
+        const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + hh) * g.out_w + ww;
+        uint4 u;
+        u.x = pack_bf16x2(x[0 + p], x[2 + p]);
+        u.y = pack_bf16x2(x[4 + p], x[6 + p]);
+        u.z = pack_bf16x2(x[8 + p], x[10 + p]);
+        u.w = pack_bf16x2(x[12 + p], x[14 + p]);
+        *reinterpret_cast<uint4*>(base + vox * g.out_c + c0) = u;
+      }
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -176,94 +272,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c * 16, v);
-        tmem_ld_wait();
-        const int n0 = n_base + c * 16;
-        if (!valid || n0 >= g.store_channels) continue;
-        float x[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]) + (g.bias ? __ldg(g.bias + n0 + i) : 0.f);
-        if (g.store_mode == 0) {
-          const int to = tt + g.out_t_offset;
-          if (to < 0 || to >= g.out_t_total) continue;
-          const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + hh) * g.out_w + ww;
-          if (g.residual != nullptr) {
-            const size_t rvox = ((static_cast<size_t>(bb) * g.res_t_total + (tt + g.res_t_offset)) * g.out_h + hh) * g.out_w + ww;
-            const uint4* r4 = reinterpret_cast<const uint4*>(g.residual + rvox * g.out_c + n0);
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint4 rv = __ldg(r4 + u);
-              const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(hv[i]);
-                x[8 * u + 2 * i] += f.x;
-                x[8 * u + 2 * i + 1] += f.y;
-              }
-            }
-          }
-          const int nvalid = g.store_channels - n0;
-          if (g.out_f32) {
-            float* dst = reinterpret_cast<float*>(g.out) + vox * g.out_c + n0;
-            if (nvalid >= 16 && (g.out_c & 3) == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(dst)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) dst[i] = x[i];
-            }
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.out) + vox * g.out_c + n0;
-            if (nvalid >= 16 && (g.out_c & 7) == 0) {
-              uint4 u0, u1;
-              u0.x = pack_bf16x2(x[0], x[1]); u0.y = pack_bf16x2(x[2], x[3]); u0.z = pack_bf16x2(x[4], x[5]); u0.w = pack_bf16x2(x[6], x[7]);
-              u1.x = pack_bf16x2(x[8], x[9]); u1.y = pack_bf16x2(x[10], x[11]); u1.z = pack_bf16x2(x[12], x[13]); u1.w = pack_bf16x2(x[14], x[15]);
-              reinterpret_cast<uint4*>(dst)[0] = u0;
-              reinterpret_cast<uint4*>(dst)[1] = u1;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) dst[i] = __float2bfloat16(x[i]);
-            }
-          }
-        } else if (g.store_mode == 1) {
-          // 'b (c p1 p2) t h w -> b c t (h p1) (w p2)': conv channel n = 4c + 2 p1 + p2; 16 n = 4 output channels x 4 pixels
-          const int to = tt + g.out_t_offset;
-          if (to < 0 || to >= g.out_t_total) continue;
-          const int c0 = n0 >> 2;
-          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.out);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int p1 = p >> 1, p2 = p & 1;
-            const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + (2 * hh + p1)) * g.out_w + (2 * ww + p2);
-            uint2 u;
-            u.x = pack_bf16x2(x[0 + p], x[4 + p]);
-            u.y = pack_bf16x2(x[8 + p], x[12 + p]);
-            *reinterpret_cast<uint2*>(base + vox * g.out_c + c0) = u;
-          }
-        } else {
-          // 'b (c p) t h w -> b c (t p) h w': conv channel n = 2c + p; frame 2t + p (+offset; negative = dropped frame)
-          const int c0 = n0 >> 1;
-          __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(g.out);
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            const int to = 2 * tt + p + g.out_t_offset;
-            if (to < 0 || to >= g.out_t_total) continue;
-            const size_t vox = ((static_cast<size_t>(bb) * g.out_t_total + to) * g.out_h + hh) * g.out_w + ww;
-            uint4 u;
-            u.x = pack_bf16x2(x[0 + p], x[2 + p]);
-            u.y = pack_bf16x2(x[4 + p], x[6 + p]);
-            u.z = pack_bf16x2(x[8 + p], x[10 + p]);
-            u.w = pack_bf16x2(x[12 + p], x[14 + p]);
-            *reinterpret_cast<uint4*>(base + vox * g.out_c + c0) = u;
-          }
-        }
-      }
+      conv_epilogue_tile<BN>(g, taddr, bb, tt, hh, ww, valid, n_base);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) {
@@ -279,6 +288,200 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant: a CTA pair computes two spatially adjacent 128-voxel patches x BN channels with ONE 256-row MMA; each CTA
+// loads its own input box and half of the weight tile (protocol as gemm2_bf16_tc_kernel in pf_gemm.cu).
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct Conv2Cfg {
+  static constexpr int A_BYTES = CBM * CBK * 2;
+  static constexpr int B_BYTES = (BN / 2) * CBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv3d2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const ConvArgs g) {
+  using Cfg = Conv2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 256);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc2(&tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int cchunks = g.cin / CBK;
+  const int num_kb = g.taps * cchunks;
+  const int sp_tiles = g.tiles_h * g.tiles_w;
+  const int sp_pairs = (sp_tiles + 1) / 2;
+  const long long total_tiles = static_cast<long long>(g.b) * g.t * sp_pairs * g.n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  // decode: n tile fastest, then patch pair, frame, batch; this CTA owns patch 2*pair + rank (may fall off the end)
+  auto decode = [&](long long tile, int& nt, int& tt, int& bb, int& h0, int& w0) {
+    nt = static_cast<int>(tile % g.n_tiles);
+    long long r = tile / g.n_tiles;
+    const int sp = static_cast<int>(r % sp_pairs) * 2 + static_cast<int>(rank);
+    r /= sp_pairs;
+    tt = static_cast<int>(r % g.t);
+    bb = static_cast<int>(r / g.t);
+    if (sp < sp_tiles) {
+      h0 = (sp / g.tiles_w) * g.th;
+      w0 = (sp % g.tiles_w) * g.tw;
+    } else {
+      h0 = g.h + g.th;   // entirely outside: TMA zero-fills, the epilogue stores nothing
+      w0 = 0;
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int ph = g.kh >> 1, pw = g.kw >> 1;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      int nt, tt, bb, h0, w0;
+      decode(tile, nt, tt, bb, h0, w0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / cchunks;
+        const int cc = kb - tap * cchunks;
+        const int dt = tap / (g.kh * g.kw);
+        const int rem = tap - dt * g.kh * g.kw;
+        const int dh = rem / g.kw, dw = rem - dh * g.kw;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+        else mbar_arrive_remote(&full_bar[stage], 0);
+        tma_load_5d_2cta(sa, &tm_x, &full_bar[stage], cc * CBK, w0 + dw - pw, h0 + dh - ph, tt + dt, bb);
+        tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], kb * CBK, nt * BN + static_cast<int>(rank) * (BN / 2));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    constexpr uint32_t idesc = make_idesc_bf16(2 * CBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc_kmajor_sw128(sa);
+        const uint64_t db = make_smem_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < CBK / 16; ++kk) umma_ss_2cta(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+        umma_commit_2cta(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit_2cta(&tmem_full_bar[acc]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int rrow = q * 32 + lane;
+    const int lh = rrow / g.tw, lw = rrow - lh * g.tw;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      int nt, tt, bb, h0, w0;
+      decode(tile, nt, tt, bb, h0, w0);
+      const int hh = h0 + lh, ww = w0 + lw;
+      const bool valid = hh < g.h && ww < g.w;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      conv_epilogue_tile<BN>(g, taddr, bb, tt, hh, ww, valid, nt * BN);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_conv2(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
+  using Cfg = Conv2Cfg<BN>;
+  auto kern = conv3d2_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv2 smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const int sp_pairs = (g.tiles_h * g.tiles_w + 1) / 2;
+  const long long total = static_cast<long long>(g.b) * g.t * sp_pairs * g.n_tiles;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  long long clusters = sms / 2;
+  if (total < clusters) clusters = total;
+  kern<<<static_cast<int>(2 * clusters), CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_x, tm_w, g);
+  return check_launch("pf_causal_conv3d(2cta)");
 }
 
 template <int BN>
@@ -339,6 +542,12 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   g.residual = static_cast<const __nv_bfloat16*>(d->residual);
   g.res_t_total = d->res_t_total; g.res_t_offset = d->res_t_offset;
 
+  // 2-CTA tiles when there is enough work for 74 CTA pairs; PF_CONV_2CTA=0/1 overrides
+  const char* env_s = getenv("PF_CONV_2CTA");
+  const int env_2cta = env_s ? atoi(env_s) : -1;
+  bool two_cta = bn >= 128 && static_cast<long long>(d->b) * d->t * g.tiles_h * g.tiles_w * g.n_tiles >= 296;
+  if (env_2cta == 0) two_cta = false;
+  if (env_2cta == 1 && bn >= 128) two_cta = true;
   const int tin = d->t + d->kt - 1;
   CUtensorMap tm_x, tm_w;
   {
@@ -355,10 +564,14 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
     const uint64_t kdim = static_cast<uint64_t>(g.taps) * d->cin;
     const uint64_t dims[2] = {kdim, static_cast<uint64_t>(d->cout)};
     const uint64_t strides[1] = {kdim * 2};
-    const uint32_t box[2] = {CBK, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {CBK, static_cast<uint32_t>(two_cta ? bn / 2 : bn)};
     int rc = encode_tensor_map(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->wgt, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  }
+  if (two_cta) {
+    if (bn == 256) return launch_conv2<256>(tm_x, tm_w, g, stream);
+    return launch_conv2<128>(tm_x, tm_w, g, stream);
   }
   switch (bn) {
     case 256: return launch_conv<256>(tm_x, tm_w, g, stream);

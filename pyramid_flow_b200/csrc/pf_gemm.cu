@@ -23,6 +23,7 @@ struct GemmArgs {
   int batches, row_begin, row_count;
   int n, k;
   int m_tiles, n_tiles;
+  int n_begin;   // first output column of this launch (a GEMM may be issued as a 256-wide main part + a narrower tail)
   const float* bias;
   void* out;
   long long ldo;
@@ -266,7 +267,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint8_t* sb = sa + Cfg::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_3d(sa, &tm_a, &full_bar[stage], kb * BK, g.row_begin + mt * BM, b);
-        tma_load_2d(sb, &tm_b, &full_bar[stage], kb * BK, nt * BN);
+        tma_load_2d(sb, &tm_b, &full_bar[stage], kb * BK, g.n_begin + nt * BN);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -318,7 +319,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int mt = r / g.n_tiles;
       const int nt = r - mt * g.n_tiles;
       const int m = mt * BM + q * 32 + lane;
-      const int n_base = nt * BN;
+      const int n_base = g.n_begin + nt * BN;
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -429,7 +430,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
         else mbar_arrive_remote(&full_bar[stage], 0);
         tma_load_3d_2cta(sa, &tm_a, &full_bar[stage], kb * BK, g.row_begin + mt * 2 * BM + static_cast<int>(rank) * BM, b);
-        tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_b, &full_bar[stage], kb * BK, nt * BN + static_cast<int>(rank) * (BN / 2));
+        tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_b, &full_bar[stage], kb * BK, g.n_begin + nt * BN + static_cast<int>(rank) * (BN / 2));
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -479,7 +480,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       const int mt = r / g.n_tiles;
       const int nt = r - mt * g.n_tiles;
       const int m = mt * 2 * BM + static_cast<int>(rank) * BM + q * 32 + lane;
-      const int n_base = nt * BN;
+      const int n_base = g.n_begin + nt * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -584,34 +585,47 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   const int epi = d->epilogue;
   PF_REQUIRE(epi >= 0 && epi <= PF_EPI_QKV_GELU, "pf_gemm_bf16: unknown epilogue %d", epi);
 
-  int bn = 0;
+  // Column tiling: 256-wide tiles wherever they fit (and a 128-wide tail launch when n = 256 a + 128, e.g. 1920 / 5760),
+  // otherwise the widest of 192 / 128 / 64 that divides n.  The QKV epilogues work per 64-column head, so any multiple of 64
+  // is head-aligned.
+  int bn = 0, n_main = d->n, bn_tail = 0;
   const bool qkv = (epi == PF_EPI_QKV_ROPE || epi == PF_EPI_QKV_GELU);
   if (qkv) {
     PF_REQUIRE(d->head_dim == 64, "pf_gemm_bf16: QKV epilogue supports head_dim 64 only (got %d)", d->head_dim);
     const int inner = d->heads * d->head_dim;
     const int nq = 3 * inner;
     PF_REQUIRE(d->q_out && d->k_out && d->v_out && d->q_norm_w && d->k_norm_w, "pf_gemm_bf16: QKV epilogue needs q/k/v outputs and norm weights");
-    PF_REQUIRE(inner % 64 == 0, "pf_gemm_bf16: heads*head_dim must be a multiple of 64");
     PF_REQUIRE(d->out_row_begin + d->row_count <= d->seq_len, "pf_gemm_bf16: QKV rows exceed seq_len");
     if (epi == PF_EPI_QKV_ROPE) {
       PF_REQUIRE(d->n == nq, "pf_gemm_bf16: QKV_ROPE needs n == 3*heads*head_dim");
     } else {
       PF_REQUIRE(d->n_split == nq && d->n > nq && d->out != nullptr, "pf_gemm_bf16: QKV_GELU needs n_split == 3*heads*head_dim < n and out");
+      PF_REQUIRE(nq % 64 == 0, "pf_gemm_bf16: n_split must be a multiple of 64");
     }
-    bn = (inner % 192 == 0 && d->n % 192 == 0) ? 192 : ((inner % 128 == 0 && d->n % 128 == 0) ? 128 : 64);
-    PF_REQUIRE(d->n % bn == 0 && inner % bn == 0, "pf_gemm_bf16: n=%d / inner=%d not tileable", d->n, inner);
   } else {
     PF_REQUIRE(d->out != nullptr, "pf_gemm_bf16: null output");
-    if (d->n % 256 == 0) bn = 256;
-    else if (d->n % 192 == 0) bn = 192;
-    else if (d->n % 128 == 0) bn = 128;
-    else if (d->n % 64 == 0) bn = 64;
-    PF_REQUIRE(bn != 0, "pf_gemm_bf16: n=%d must be a multiple of 64", d->n);
     if (epi == PF_EPI_GATE_RESID) PF_REQUIRE(d->gate != nullptr, "pf_gemm_bf16: GATE_RESID needs gate");
     const int esz = (epi == PF_EPI_STORE_F32 || epi == PF_EPI_GATE_RESID) ? 4 : 2;
     PF_REQUIRE((d->ldo * esz) % 16 == 0 && (d->out_col_begin * esz) % 16 == 0 &&
                    (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
                "pf_gemm_bf16: output must be 16-byte aligned (ldo %lld col %d)", (long long)d->ldo, d->out_col_begin);
+  }
+  PF_REQUIRE(d->n % 64 == 0, "pf_gemm_bf16: n=%d must be a multiple of 64", d->n);
+  if (epi == PF_EPI_QKV_GELU) {
+    // tiles must not straddle the q|k|v / mlp boundary (different epilogue per tile): keep the uniform 192/128/64 tiling
+    bn = (d->n_split % 192 == 0 && d->n % 192 == 0) ? 192 : ((d->n_split % 128 == 0 && d->n % 128 == 0) ? 128 : 64);
+  } else if (d->n % 256 == 0) {
+    bn = 256;
+  } else if (d->n % 256 == 128 && d->n > 256) {
+    bn = 256;
+    n_main = d->n - 128;
+    bn_tail = 128;
+  } else if (d->n % 192 == 0) {
+    bn = 192;
+  } else if (d->n % 128 == 0) {
+    bn = 128;
+  } else {
+    bn = 64;
   }
 
   GemmArgs g{};
@@ -621,7 +635,6 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   g.n = d->n;
   g.k = d->k;
   g.m_tiles = (d->row_count + BM - 1) / BM;
-  g.n_tiles = d->n / bn;
   g.bias = d->bias;
   g.out = d->out;
   g.ldo = d->ldo;
@@ -642,15 +655,17 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   g.seq_len = d->seq_len;
   g.n_split = d->n_split;
 
-  // 2-CTA tiles (256 x BN) when the problem is big enough to feed 74 CTA pairs; PF_GEMM_2CTA=0/1 overrides
-  static const int env_2cta = [] {
-    const char* e = getenv("PF_GEMM_2CTA");
-    return e ? atoi(e) : -1;
-  }();
-  bool two_cta = bn >= 128 && d->row_count >= 1024;
-  if (env_2cta == 0) two_cta = false;
-  if (env_2cta == 1 && bn >= 128) two_cta = true;
-  CUtensorMap tm_a, tm_b;
+  // 2-CTA tiles (256 x BN, cta_group::2) pay off for 256-wide tiles and for short-K 192-wide ones (measured A/B on
+  // B200: +11 % at N=7680/K=1920, -1..3 % at N=1920/K>=7680); PF_GEMM_2CTA=0/1 overrides
+  const char* env_s = getenv("PF_GEMM_2CTA");
+  const int env_2cta = env_s ? atoi(env_s) : -1;
+  auto want_2cta = [&](int tile_n) {
+    bool t = d->row_count >= 1024 && (tile_n == 256 || (tile_n == 192 && d->k <= 2048));
+    if (env_2cta == 0) t = false;
+    if (env_2cta == 1 && tile_n >= 128) t = true;
+    return t;
+  };
+  CUtensorMap tm_a;
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->rows_per_batch),
                               static_cast<uint64_t>(d->batches)};
@@ -661,22 +676,30 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  {
+
+  auto launch_part = [&](int tile_n, int n_begin, int n_count) -> int {
+    const bool two_cta = want_2cta(tile_n);
+    CUtensorMap tm_b;
     const uint64_t dims[2] = {static_cast<uint64_t>(d->k), static_cast<uint64_t>(d->n)};
     const uint64_t strides[1] = {static_cast<uint64_t>(d->k) * 2};
-    const uint32_t box[2] = {BK, static_cast<uint32_t>(two_cta ? bn / 2 : bn)};
+    const uint32_t box[2] = {BK, static_cast<uint32_t>(two_cta ? tile_n / 2 : tile_n)};
     int rc = encode_tensor_map(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-  }
-
-  switch (epi) {
-    case PF_EPI_STORE_BF16: return dispatch_bn<PF_EPI_STORE_BF16>(bn, tm_a, tm_b, g, stream, two_cta);
-    case PF_EPI_GELU_BF16: return dispatch_bn<PF_EPI_GELU_BF16>(bn, tm_a, tm_b, g, stream, two_cta);
-    case PF_EPI_STORE_F32: return dispatch_bn<PF_EPI_STORE_F32>(bn, tm_a, tm_b, g, stream, two_cta);
-    case PF_EPI_GATE_RESID: return dispatch_bn<PF_EPI_GATE_RESID>(bn, tm_a, tm_b, g, stream, two_cta);
-    case PF_EPI_QKV_ROPE: return dispatch_bn<PF_EPI_QKV_ROPE>(bn, tm_a, tm_b, g, stream, two_cta);
-    case PF_EPI_QKV_GELU: return dispatch_bn<PF_EPI_QKV_GELU>(bn, tm_a, tm_b, g, stream, two_cta);
-  }
-  return -1;
+    GemmArgs gp = g;
+    gp.n_begin = n_begin;
+    gp.n_tiles = n_count / tile_n;
+    switch (epi) {
+      case PF_EPI_STORE_BF16: return dispatch_bn<PF_EPI_STORE_BF16>(tile_n, tm_a, tm_b, gp, stream, two_cta);
+      case PF_EPI_GELU_BF16: return dispatch_bn<PF_EPI_GELU_BF16>(tile_n, tm_a, tm_b, gp, stream, two_cta);
+      case PF_EPI_STORE_F32: return dispatch_bn<PF_EPI_STORE_F32>(tile_n, tm_a, tm_b, gp, stream, two_cta);
+      case PF_EPI_GATE_RESID: return dispatch_bn<PF_EPI_GATE_RESID>(tile_n, tm_a, tm_b, gp, stream, two_cta);
+      case PF_EPI_QKV_ROPE: return dispatch_bn<PF_EPI_QKV_ROPE>(tile_n, tm_a, tm_b, gp, stream, two_cta);
+      case PF_EPI_QKV_GELU: return dispatch_bn<PF_EPI_QKV_GELU>(tile_n, tm_a, tm_b, gp, stream, two_cta);
+    }
+    return -1;
+  };
+  int rc = launch_part(bn, 0, n_main);
+  if (rc == 0 && bn_tail) rc = launch_part(bn_tail, n_main, d->n - n_main);
+  return rc;
 }

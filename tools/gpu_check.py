@@ -272,14 +272,21 @@ def group_gemm_perf():
     from pyramid_flow_b200 import ops
     dev = "cuda"
     for (m, n, k) in [(30976, 1920, 1920), (30976, 5760, 1920), (30976, 7680, 1920), (30976, 1920, 7680),
-                      (30976, 13440, 1920), (30976, 1920, 9600)]:
+                      (30976, 1920, 9600), (30976, 2048, 8192), (30976, 1536, 6144), (7744, 1920, 9600)]:
         x = (torch.randn(m, k, device=dev) * 0.5).bfloat16()
         w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
         out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
-        ms = _time_cuda(lambda: ops.gemm(x, w, None, 0, rows_per_batch=m, out=out))
+        res = {}
+        for mode in ("0", "1", "auto"):
+            if mode == "auto":
+                os.environ.pop("PF_GEMM_2CTA", None)
+            else:
+                os.environ["PF_GEMM_2CTA"] = mode
+            res[mode] = _time_cuda(lambda: ops.gemm(x, w, None, 0, rows_per_batch=m, out=out))
         ms_ref = _time_cuda(lambda: torch.matmul(x, w.t(), out=out))
-        tf = 2.0 * m * n * k / ms / 1e9
-        print(f"[gemm_perf] m={m} n={n} k={k}: {ms:.3f} ms = {tf:.0f} TFLOP/s (cuBLAS {ms_ref:.3f} ms = {2.0*m*n*k/ms_ref/1e9:.0f})", flush=True)
+        fl = 2.0 * m * n * k / 1e9
+        print(f"[gemm_perf] m={m} n={n} k={k}: 1-CTA {res['0']:.3f} ms = {fl/res['0']:.0f} TF/s | 2-CTA {res['1']:.3f} ms = {fl/res['1']:.0f} | auto {res['auto']:.3f} ms = {fl/res['auto']:.0f} | cuBLAS {ms_ref:.3f} ms = {fl/ms_ref:.0f}", flush=True)
+    os.environ.pop("PF_GEMM_2CTA", None)
 
 
 def group_attn():
