@@ -388,7 +388,10 @@ class B200FluxTransformer(torch.nn.Module):
         scale = 1.0 / math.sqrt(64)
         seg, tim, sched = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b]
 
-        def attention():
+        def exchange_begin():
+            return SP.heads_to_sequence_qkv_begin(q[0], k[0], v[0], lay) if nsp > 1 else None
+
+        def attention(pending=None):
             ev = self.attn_events is not None
             if ev:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -400,7 +403,7 @@ class B200FluxTransformer(torch.nn.Module):
                     e1.record()
             else:
                 # Ulysses exchange: all (padded) heads of my token chunk -> my head group over the whole sequence
-                qf, kf, vf = SP.heads_to_sequence_qkv(q[0], k[0], v[0], lay)
+                qf, kf, vf = SP.heads_to_sequence_qkv_end(pending if pending is not None else exchange_begin())
                 of = ws["of"]
                 if ev:
                     e0.record()
@@ -442,9 +445,10 @@ class B200FluxTransformer(torch.nn.Module):
             # two launches sharing A: measured faster than the fused q|k|v|mlp GEMM (PF_EPI_QKV_GELU), whose 192-wide
             # tiles slow the MLP half down (1.81 ms fused vs 0.60 + 0.62 ms split at S=15488)
             qkv(w["w_qkv"], w["b_qkv"], w["nq"], w["nk"], 0, sl)
+            pending = exchange_begin()       # SP: the q/k/v all-to-alls run under the proj_mlp GEMM
             ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=0, row_count=sl,
                      out=cat, ldo=ldc, out_col_begin=wa)
-            attention()
+            attention(pending)
             ops.gemm(cat, w["w_out_p"] if pad else w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b,
                      rows_per_batch=sl, row_begin=0, row_count=sl, out=h, ldo=d, gate=mod[:, o + 2 * d:],
                      gate_batch_stride=nm)

@@ -79,9 +79,9 @@ def heads_to_sequence(x: torch.Tensor, lay: ParallelLayout) -> torch.Tensor:
     return recv.permute(1, 0, 2, 3).reshape(hg, lay.sp * s_l, hd)
 
 
-def heads_to_sequence_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lay: ParallelLayout):
-    """The three exchanges of one attention issued back to back (async) and waited together: one round of NCCL launch /
-    stream-sync latency instead of three."""
+def heads_to_sequence_qkv_begin(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lay: ParallelLayout):
+    """Start the three exchanges of one attention back to back (async on NCCL's stream); independent work — the single
+    block's proj_mlp GEMM — can be launched on the compute stream before `heads_to_sequence_qkv_end` waits."""
     hp, s_l, hd = q.shape
     hg = hp // lay.sp
     recvs, works = [], []
@@ -89,9 +89,18 @@ def heads_to_sequence_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lay
         r = torch.empty(lay.sp, hg, s_l, hd, dtype=x.dtype, device=x.device)
         works.append(dist.all_to_all_single(r, x.view(lay.sp, hg, s_l, hd), group=lay.sp_group, async_op=True))
         recvs.append(r)
+    return works, recvs, (hg, lay.sp * s_l, hd)
+
+
+def heads_to_sequence_qkv_end(handle):
+    works, recvs, shape = handle
     for w in works:
         w.wait()
-    return tuple(r.permute(1, 0, 2, 3).reshape(hg, lay.sp * s_l, hd) for r in recvs)
+    return tuple(r.permute(1, 0, 2, 3).reshape(shape) for r in recvs)
+
+
+def heads_to_sequence_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, lay: ParallelLayout):
+    return heads_to_sequence_qkv_end(heads_to_sequence_qkv_begin(q, k, v, lay))
 
 
 def sequence_to_heads(o: torch.Tensor, lay: ParallelLayout) -> torch.Tensor:
