@@ -339,6 +339,15 @@ def run_ours(args):
     step_e2e()
     step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    # per-kernel-family breakdown of ONE extra (untimed-for-the-metric) step, CUDA events around every launch
+    model.timer.enabled = True
+    model.attn_events = []
+    step_resident()
+    torch.cuda.synchronize()
+    breakdown = model.timer.totals_ms()
+    breakdown["attention"] = sum(a.elapsed_time(bq) for a, bq in model.attn_events)
+    model.timer.enabled = False
+    model.attn_events = None
 
     if rank != 0:
         if world > 1:
@@ -365,7 +374,8 @@ def run_ours(args):
                                    f"(heads 30 -> {model._hp}, one NCCL all-to-all each side of attention)"),
                    "layers": list(args.layers), "l2": "per-step working set (>1.5 GB of activations + 3.9 GB weights) exceeds the 126 MB L2; no explicit flush",
                    "step_tflop": {"gemm": fl["gemm"] / 1e12, "attention_masked": fl["attention"] / 1e12},
-                   "step_tflops_achieved": (fl["gemm"] + fl["attention"]) / (ms_step * 1e-3) / 1e12},
+                   "step_tflops_achieved": (fl["gemm"] + fl["attention"]) / (ms_step * 1e-3) / 1e12,
+                   "breakdown_ms_one_step": {k_: round(v_, 3) for k_, v_ in sorted(breakdown.items())}},
         "clocks": clocks,
         "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

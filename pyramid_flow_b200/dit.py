@@ -126,6 +126,48 @@ class _Cfg(dict):
     __getattr__ = dict.__getitem__
 
 
+class _KernelTimer:
+    """Optional CUDA-event timing of kernel families inside a step (bench.py breakdown); disabled => zero overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = []
+
+    def __call__(self, tag: str):
+        return _Span(self, tag) if self.enabled else _NULL_SPAN
+
+    def totals_ms(self):
+        out = {}
+        for tag, e0, e1 in self.events:
+            out[tag] = out.get(tag, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+class _Span:
+    def __init__(self, timer, tag):
+        self.t, self.tag = timer, tag
+
+    def __enter__(self):
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def __exit__(self, *a):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.t.events.append((self.tag, self.e0, e1))
+
+
+class _NullSpan:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL_SPAN = _NullSpan()
+
+
 class B200FluxTransformer(torch.nn.Module):
     """Holder of packed bf16 weights + the kernel-launch sequence of one DiT step."""
 
@@ -148,6 +190,7 @@ class B200FluxTransformer(torch.nn.Module):
         self.last_plan: Optional[SeqPlan] = None
         self._last_key = None
         self.attn_events = None   # bench.py: list collecting (start, end) CUDA events around every attention launch
+        self.timer = _KernelTimer()
 
     @classmethod
     def from_reference(cls, ref_module, device="cuda", **kw) -> "B200FluxTransformer":
@@ -375,15 +418,20 @@ class B200FluxTransformer(torch.nn.Module):
             ops.gemm(ws["tok"], self.w_x, self.b_x, PF_EPI_STORE_F32, batches=b, rows_per_batch=lv, row_begin=vb - t_len,
                      row_count=ve - vb, out=h, ldo=d, out_batch_rows=sl, out_row_begin=vb - c0)
 
+        T = self.timer
+
         def lnmod(off_shift, off_scale, r0, rc):
             if rc > 0:
-                ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=sl,
-                                row_begin=r0, row_count=rc)
+                with T("ln_modulate"):
+                    ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=sl,
+                                    row_begin=r0, row_count=rc)
 
         def qkv(wq, bq, nq, nk, r0, rc):
             if rc > 0:
-                ops.gemm(xn, wq, bq, PF_EPI_QKV_ROPE, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc, q_out=q,
-                         k_out=k, v_out=v, rope=rope, q_norm_w=nq, k_norm_w=nk, heads=hn, head_dim=64, seq_len=sl)
+                with T("gemm_qkv"):
+                    ops.gemm(xn, wq, bq, PF_EPI_QKV_ROPE, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc,
+                             q_out=q, k_out=k, v_out=v, rope=rope, q_norm_w=nq, k_norm_w=nk, heads=hn, head_dim=64,
+                             seq_len=sl)
 
         scale = 1.0 / math.sqrt(64)
         seg, tim, sched = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b]
@@ -431,13 +479,16 @@ class B200FluxTransformer(torch.nn.Module):
             for j, (r0, rc) in enumerate(ranges):
                 if rc == 0:
                     continue
-                ops.gemm(cat[:, :, :wa], wo[j], bo[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
-                         row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 2 * d:], gate_batch_stride=nm)   # gate_msa
+                with T("gemm_attn_out"):
+                    ops.gemm(cat[:, :, :wa], wo[j], bo[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
+                             row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 2 * d:], gate_batch_stride=nm)   # gate_msa
                 lnmod(offs[j] + 3 * d, offs[j] + 4 * d, r0, rc)                                   # (shift_mlp, scale_mlp)
-                ops.gemm(xn, wf1[j], bf1[j], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc,
-                         out=cat, ldo=ldc, out_col_begin=wa)
-                ops.gemm(cat[:, :, wa:], wf2[j], bf2[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
-                         row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 5 * d:], gate_batch_stride=nm)  # gate_mlp
+                with T("gemm_ff1_gelu"):
+                    ops.gemm(xn, wf1[j], bf1[j], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=r0,
+                             row_count=rc, out=cat, ldo=ldc, out_col_begin=wa)
+                with T("gemm_ff2"):
+                    ops.gemm(cat[:, :, wa:], wf2[j], bf2[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
+                             row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 5 * d:], gate_batch_stride=nm)  # gate_mlp
 
         for i, w in enumerate(self.sgl):
             o = self.mod_off[f"single_transformer_blocks.{i}.norm"]
@@ -446,12 +497,14 @@ class B200FluxTransformer(torch.nn.Module):
             # tiles slow the MLP half down (1.81 ms fused vs 0.60 + 0.62 ms split at S=15488)
             qkv(w["w_qkv"], w["b_qkv"], w["nq"], w["nk"], 0, sl)
             pending = exchange_begin()       # SP: the q/k/v all-to-alls run under the proj_mlp GEMM
-            ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=0, row_count=sl,
-                     out=cat, ldo=ldc, out_col_begin=wa)
+            with T("gemm_single_mlp_gelu"):
+                ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=0,
+                         row_count=sl, out=cat, ldo=ldc, out_col_begin=wa)
             attention(pending)
-            ops.gemm(cat, w["w_out_p"] if pad else w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b,
-                     rows_per_batch=sl, row_begin=0, row_count=sl, out=h, ldo=d, gate=mod[:, o + 2 * d:],
-                     gate_batch_stride=nm)
+            with T("gemm_single_out"):
+                ops.gemm(cat, w["w_out_p"] if pad else w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b,
+                         rows_per_batch=sl, row_begin=0, row_count=sl, out=h, ldo=d, gate=mod[:, o + 2 * d:],
+                         gate_batch_stride=nm)
 
         # ---- head: only the current clip's tokens are needed (F:380); AdaLN-continuous is (scale, shift) (N:119)
         n_last = plan.last_tokens
