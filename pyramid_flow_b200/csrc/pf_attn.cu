@@ -49,6 +49,18 @@ struct AttnArgs {
   int sched_stride;
 };
 
+// Debug timeline (variant bit 1): clock64 stamps of ONE CTA (batch 0, head 0, middle q tile) for the first
+// ATT_TRACE_ITERS kv tiles: [role 0 = softmax warp 0, 1 = softmax warp 4, 2 = MMA issuer][iteration][5 stamps].
+constexpr int ATT_TRACE_ITERS = 48;
+__device__ unsigned long long* g_attn_trace = nullptr;
+template <int TRACE>
+__device__ __forceinline__ void trace_stamp(bool on, int role, int j, int slot) {
+  if (TRACE) {
+    if (on && j < ATT_TRACE_ITERS && g_attn_trace != nullptr)
+      g_attn_trace[(role * ATT_TRACE_ITERS + j) * 5 + slot] = clock64();
+  }
+}
+
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -120,7 +132,7 @@ __device__ __forceinline__ void exp32(const uint32_t (&v)[32], uint32_t (&pk)[16
   }
 }
 
-template <int POLY>
+template <int POLY, int TRACE>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnArgs a) {
@@ -144,6 +156,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int bh = b * a.heads + h;
   const int* sched = a.sched + (static_cast<size_t>(b) * a.q_tiles + qt) * a.sched_stride;
   const int n_kv = sched[0];
+  const bool tr_cta = TRACE && b == 0 && h == 0 && qt == a.q_tiles / 2;
   constexpr int W_MMA = ATT_SOFTMAX_WARPS, W_TMA = ATT_SOFTMAX_WARPS + 1;
 
   if (warp == W_TMA && lane == 0) {
@@ -230,11 +243,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int j = 0; j < n_kv; ++j) {
         if (j + 1 < n_kv) {
           mbar_wait(&bar_s_free, j & 1);          // S(j) is in registers
+          trace_stamp<TRACE>(tr_cta, 2, j, 0);
           issue_qk();
+          trace_stamp<TRACE>(tr_cta, 2, j, 1);
         }
         mbar_wait(&bar_p_full, j & 1);
+        trace_stamp<TRACE>(tr_cta, 2, j, 2);
         mbar_wait(&v_full[vs], vph);
         tc_fence_after();
+        trace_stamp<TRACE>(tr_cta, 2, j, 3);
         // V tile [128 kv x 64 hd], 128-byte rows: MN-major, 8-row k groups 1024 B apart, 16 kv rows (2048 B) per MMA
         const uint32_t sv = smem_u32(smem_v + vs * ATT_TILE_BYTES);
 #pragma unroll
@@ -244,6 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         umma_commit(&v_empty[vs]);
         umma_commit(&bar_pv_done);
+        trace_stamp<TRACE>(tr_cta, 2, j, 4);
         if (++vs == ATT_VSTAGES) {
           vs = 0;
           vph ^= 1;
@@ -266,6 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float c = a.scale_log2;
     float m_run = -INFINITY;  // running reference max (raw score units); identical in both column halves
     float l4[4] = {0.f, 0.f, 0.f, 0.f};  // this half's partial row sum (4 chains)
+    const bool tr_me = tr_cta && lane == 0 && quarter == 0;
 
     for (int j = 0; j < n_kv; ++j) {
       const int entry = sched[1 + j];
@@ -290,12 +309,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       mbar_wait(&bar_s_full, j & 1);
       tc_fence_after();
+      trace_stamp<TRACE>(tr_me, half, j, 0);
 
       // ---- this thread's 64 scores stay in registers for both the max and the exp
       uint32_t va[32], vb[32];
       tmem_ld32(t_s, va);
       tmem_ld32(t_s + 32, vb);
       tmem_ld_wait();
+      trace_stamp<TRACE>(tr_me, half, j, 1);
       tc_fence_before();
       mbar_arrive(&bar_s_free);   // S(j) now lives in registers: the tensor pipe may overwrite it with S(j+1)
       if (masked) {
@@ -306,6 +327,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       xch[j & 1][half][row] = m_part;
       pair_bar_sync(quarter);
       const float m_tile = fmaxf(m_part, xch[j & 1][half ^ 1][row]);
+      trace_stamp<TRACE>(tr_me, half, j, 2);
 
       // ---- lazy rescale decision (per row, same in both halves), correction is warp-collective
       const float m_cand = fmaxf(m_run, m_tile);
@@ -323,6 +345,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&bar_pv_done, (j - 1) & 1);
         tc_fence_after();
       }
+      trace_stamp<TRACE>(tr_me, half, j, 3);
       if (j > 0 && __any_sync(0xffffffffu, need)) {
 #pragma unroll 1
         for (int cc = 0; cc < 32; cc += 16) {   // 16 columns at a time: the 64 scores stay live in registers
@@ -351,6 +374,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       tmem_st16(t_p + 16, pk);
       tmem_st_wait();
+      trace_stamp<TRACE>(tr_me, half, j, 4);
       tc_fence_before();
       mbar_arrive(&bar_p_full);
     }
@@ -480,9 +504,11 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+      e = cudaFuncSetAttribute(attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("pf_attn_fwd_masked: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return -2;
@@ -490,9 +516,22 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
     attr_set = true;
   }
   dim3 grid(q_tiles, d->heads, d->batch);
-  if (d->variant & 1)
-    attn_fwd_kernel<1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  if (d->variant & 2)
+    attn_fwd_kernel<0, 1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  else if (d->variant & 1)
+    attn_fwd_kernel<1, 0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   else
-    attn_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+    attn_fwd_kernel<0, 0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked");
+}
+
+// Debug: device buffer of 3 * 48 * 5 uint64 clock stamps filled by the variant-2 (trace) kernel; NULL disables.
+extern "C" int pf_debug_attn_trace(void* device_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(device_buf);
+  cudaError_t e = cudaMemcpyToSymbol(pf::g_attn_trace, &p, sizeof(p));
+  if (e != cudaSuccess) {
+    pf::set_error("pf_debug_attn_trace: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
 }

@@ -74,6 +74,7 @@ class B200CausalVAE(torch.nn.Module):
         super().__init__()
         self.cfg = config
         self.use_tiling = False
+        self._cp = None                     # (group, rank, world) when context-parallel decode is on
         self.decode_tile_overlap_factor = 0.25
         dev = torch.device(device)
         self._dev = dev
@@ -126,6 +127,33 @@ class B200CausalVAE(torch.nn.Module):
     def dtype(self):
         return torch.bfloat16
 
+    # ---- context parallel decode (temporal split + 2-frame halo exchange per causal conv) ------------------------------
+    def set_context_parallel(self, group=None) -> None:
+        """Split the latent frames over the ranks of `group` following the reference's VAE context-parallel layout
+        (video_vae/context_parallel_ops.py:14-38 split, :76-114 halo pass; the reference uses it in training only):
+        rank 0 takes the image frame plus its share, every 3x3x3 causal conv receives the last two input frames of the
+        previous rank (NCCL p2p over NVLink) instead of the zero / cached halo, and only rank 0 drops the first
+        up-sampled frame.  `group=None` = the default process group; world size 1 disables it."""
+        import torch.distributed as dist
+        self._cp = None
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 1:
+            self._cp = (group, rank, world)
+
+    @staticmethod
+    def cp_frame_split(n_frames: int, world: int):
+        """Latent-frame ranges per rank: rank 0 = image frame + share, others = share of the remaining n-1 frames (as even
+        as possible; the reference requires divisibility, X:24-33)."""
+        base, extra = divmod(n_frames - 1, world)
+        bounds, f = [], 0
+        for r in range(world):
+            n = base + (1 if r < extra else 0) + (1 if r == 0 else 0)
+            bounds.append((f, f + n))
+            f += n
+        return bounds
+
     def enable_tiling(self, use_tiling: bool = True):
         self.use_tiling = use_tiling
 
@@ -155,6 +183,20 @@ class B200CausalVAE(torch.nn.Module):
         """Fill the 2 leading frames of a 3x3x3 conv's input buffer from its cache (zeros for the first chunk) and
         remember the last 2 frames of the padded input for the next chunk (reference C:126-143)."""
         if cv.kt == 1:
+            return
+        if self._cp is not None:
+            import torch.distributed as dist
+            group, rank, world = self._cp
+            peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+            p2p = []
+            if rank + 1 < world:        # my last two (padded) input frames are the next rank's halo
+                p2p.append(dist.P2POp(dist.isend, buf[-2:], peer(rank + 1), group))
+            if rank > 0:
+                p2p.append(dist.P2POp(dist.irecv, buf[:2], peer(rank - 1), group))
+            else:
+                buf[:2].zero_()
+            for work in (dist.batch_isend_irecv(p2p) if p2p else []):
+                work.wait()
             return
         if first or cv.cache is None:
             buf[:2].zero_()
@@ -289,8 +331,32 @@ class B200CausalVAE(torch.nn.Module):
         self._conv(co, a, t, h, w, out=out, store_channels=cfg.out_channels, out_f32=True)
         return out
 
+    def _decode_sample_cp(self, z: torch.Tensor) -> torch.Tensor:
+        """Context-parallel decode of one sample: my frame range as ONE chunk with halos from the previous rank; the
+        decoded frames of all ranks are all-gathered (every rank returns the full clip)."""
+        import torch.distributed as dist
+        group, rank, world = self._cp
+        bounds = self.cp_frame_split(z.shape[2], world)
+        a, b = bounds[rank]
+        mine = self._decode_chunk(z[:, :, a:b].contiguous(), rank == 0)            # [T_r, H, W, 3] fp32
+        counts = [8 * (e - s) - (7 if r == 0 else 0) for r, (s, e) in enumerate(bounds)]
+        assert mine.shape[0] == counts[rank]
+        pad = torch.zeros(max(counts), *mine.shape[1:], device=mine.device, dtype=mine.dtype)
+        pad[: mine.shape[0]] = mine
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        return torch.cat([p_[:c] for p_, c in zip(parts, counts)], 0)
+
     def _decode_sample(self, z: torch.Tensor, window_size: int) -> torch.Tensor:
         """chunk_decode (V:346-374) for one sample: first chunk window+1 latent frames, then `window` each."""
+        if self._cp is not None:
+            if z.shape[2] - 1 >= 2 * self._cp[2]:        # every rank owns >= 2 frames: its halo source is its own data
+                return self._decode_sample_cp(z)
+            saved, self._cp = self._cp, None              # short clip: every rank decodes all of it (replicas)
+            try:
+                return self._decode_sample(z, window_size)
+            finally:
+                self._cp = saved
         self._reset_caches()
         n = z.shape[2]
         init = min(n, window_size + 1)

@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "attn_perf", "vae_perf"]
+GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "attn_perf", "attn_trace", "vae_perf"]
 
 
 def _rel_err(a, b):
@@ -354,6 +354,73 @@ def group_attn_perf():
     for variant in (0, 1):
         ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant), iters=5)
         print(f"[attn_perf] variant {variant} S={S} B={B} H={H}: {ms:.3f} ms, allowed pairs {pairs.tolist()}, {flops/ms/1e9:.0f} TFLOP/s (masked-pair flops)", flush=True)
+
+
+def group_gemm_epi_perf():
+    """Epilogue cost: the same K=1920 GEMM with STORE / GELU+bias / GATE_RESID / QKV_ROPE epilogues."""
+    import torch
+    from pyramid_flow_b200 import ops
+    dev = "cuda"
+    m, k = 30976, 1920
+    x = (torch.randn(m, k, device=dev) * 0.5).bfloat16()
+    for n, epi, name in [(7680, 0, "store"), (7680, 1, "gelu+bias"), (1920, 0, "store"), (1920, 3, "gate_resid")]:
+        w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
+        bias = torch.randn(n, device=dev) * 0.1
+        fl = 2.0 * m * n * k / 1e9
+        if epi == 3:
+            h = torch.zeros(2, m // 2, n, device=dev, dtype=torch.float32)
+            gate = torch.randn(2, n, device=dev) * 0.1
+            fn = lambda: ops.gemm(x, w, bias, 3, rows_per_batch=m // 2, out=h, gate=gate, gate_batch_stride=n, batches=2)
+        else:
+            out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+            fn = lambda: ops.gemm(x, w, bias if epi == 1 else None, epi, rows_per_batch=m, out=out)
+        try:
+            ms = _time_cuda(fn)
+            print(f"[gemm_epi_perf] m={m} n={n} k={k} {name}: {ms:.3f} ms = {fl/ms:.0f} TF/s", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"[gemm_epi_perf] {name}: EXC {e}", flush=True)
+
+
+def group_attn_trace():
+    """clock64 timeline of one CTA of the attention kernel at the bench shape (variant 2)."""
+    import torch
+    from pyramid_flow_b200 import ops, _lib
+    dev = "cuda"
+    B, H = 2, 30
+    lens = [128 + 240] + [240] * 27 + [960, 3840, 3840]
+    tim = torch.cat([torch.full((n,), float(i)) for i, n in enumerate(lens)]).int()[None].repeat(B, 1)
+    S = tim.shape[1]
+    seg = torch.ones(B, S, dtype=torch.int32)
+    q = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    k = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    v = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
+    sched, pairs = ops.attn_build_schedule(seg, tim)
+    sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
+    N = 48
+    buf = torch.zeros(3 * N * 5, dtype=torch.int64, device=dev)
+    _lib.check(_lib.load().pf_debug_attn_trace(buf.data_ptr()), "trace")
+    for _ in range(2):
+        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, 2)
+    torch.cuda.synchronize()
+    _lib.check(_lib.load().pf_debug_attn_trace(None), "trace")
+    t = buf.cpu().view(3, N, 5)
+    t0 = int(t[0, 0, 0])
+    print("[attn_trace] iteration: softmax half0 [S_full, ld_done, pair_done, pv_done(j-1), p_stored] | half1 [...] | "
+          "MMA [s_free, qk_issued, p_full, v_full, pv_issued]  (cycles since first S_full)")
+    for j in range(8, 28):
+        row = " | ".join(" ".join(f"{int(t[r, j, i]) - t0:7d}" for i in range(5)) for r in range(3))
+        print(f"[attn_trace] j={j:2d}: {row}")
+    per = (int(t[0, 40, 0]) - int(t[0, 8, 0])) / 32.0
+    d = t[:, 8:40].double()
+    print(f"[attn_trace] cycles per kv tile (this CTA): {per:.0f}")
+    print(f"[attn_trace] softmax half0 mean phase lengths: S_full->ld {float((d[0,:,1]-d[0,:,0]).mean()):.0f}, ld->pair "
+          f"{float((d[0,:,2]-d[0,:,1]).mean()):.0f}, pair->pv_done {float((d[0,:,3]-d[0,:,2]).mean()):.0f}, exp+store "
+          f"{float((d[0,:,4]-d[0,:,3]).mean()):.0f}, p_stored->next S_full {float((d[0,1:,0]-d[0,:-1,4]).mean()):.0f}")
+    print(f"[attn_trace] MMA: p_stored(half0)->p_full seen {float((d[2,:,2]-d[0,:,4]).mean()):.0f}, p_full->pv_issued "
+          f"{float((d[2,:,4]-d[2,:,2]).mean()):.0f}, pv_issued->pv_done seen by softmax(j+1) {float((d[0,1:,3]-d[2,:-1,4]).mean()):.0f}, "
+          f"ld_done(half0)->s_free seen {float((d[2,:,0]-d[0,:,1]).mean()):.0f}, qk issue {float((d[2,:,1]-d[2,:,0]).mean()):.0f}, "
+          f"qk_issued(j)->S_full(j+1) seen {float((d[0,1:,0]-d[2,:-1,1]).mean()):.0f}")
 
 
 def group_vae_perf():
