@@ -211,7 +211,7 @@ typedef struct pf_umma_probe {
 } pf_umma_probe;
 PF_API int pf_debug_umma(const pf_umma_probe* p, void* stream);
 
-/* Debug timeline of the attention kernel: `device_buf` = 3 * 48 * 5 uint64 (clock64 stamps of one CTA: two softmax warps
+/* Debug timeline of the attention kernel: `device_buf` = 3 * 48 * 8 uint64 (clock64 stamps of one CTA: two softmax warps
  * and the MMA issuer, first 48 kv tiles), filled by pf_attn_fwd_masked launches with variant bit 1 (value 2) set.
  * NULL disables.  Test/profiling aid only (tools/gpu_check.py attn_trace). */
 PF_API int pf_debug_attn_trace(void* device_buf);

@@ -9,9 +9,11 @@
 // One CTA = one (batch, head, 128-row q tile); 320 threads; two CTAs are co-resident per SM so that one CTA's softmax
 // (MUFU-bound at head_dim 64) overlaps the other CTA's tensor-core work:
 //   warps 0-7  softmax: thread == (q row == TMEM lane, 64-column half).  The thread's 64 scores are read from TMEM once
-//              and stay in registers for the FMNMX3 max pass and the ex2 pass; the two halves of a row exchange their
-//              partial max through shared memory (one named barrier per tile).  P is written back to TMEM as packed
-//              bf16; O is rescaled in TMEM only when the running max moved by > 2^8 (lazy rescale)
+//              and stay in registers for the FMNMX3 max pass and the ex2 pass.  The reference max is one tile stale: the
+//              two halves publish their partial max of tile j in shared memory and read the partner's for tile j-1
+//              (ordered by the P-ready mbarrier), so there is no per-tile pair barrier and the exps of tile j never
+//              wait for P.V(j-1).  P is written back to TMEM as packed bf16; O is rescaled in TMEM only when the
+//              reference moved by > 2^8 (lazy rescale)
 //   warp 8     MMA issuer (one lane): S = Q.K^T (SS: both operands in smem, K-major), O += P.V (TS: P from TMEM,
 //              V from smem MN-major — V is consumed in its natural [kv, hd] layout, no transpose)
 //   warp 9     TMA producer (one lane): Q once, then K tiles through a 3-stage and V tiles through a 2-stage mbarrier ring
@@ -52,12 +54,12 @@ struct AttnArgs {
 // Debug timeline (variant bit 1): clock64 stamps of ONE CTA (batch 0, head 0, middle q tile) for the first
 // ATT_TRACE_ITERS kv tiles: [role 0 = softmax warp 0, 1 = softmax warp 4, 2 = MMA issuer][iteration][5 stamps].
 constexpr int ATT_TRACE_ITERS = 48;
+constexpr int ATT_TRACE_SLOTS = 8;
 __device__ unsigned long long* g_attn_trace = nullptr;
 template <int TRACE>
-__device__ __forceinline__ void trace_stamp(bool on, int role, int j, int slot) {
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, int j, int slot) {
   if (TRACE) {
-    if (on && j < ATT_TRACE_ITERS && g_attn_trace != nullptr)
-      g_attn_trace[(role * ATT_TRACE_ITERS + j) * 5 + slot] = clock64();
+    if (tr != nullptr && j < ATT_TRACE_ITERS) tr[(role * ATT_TRACE_ITERS + j) * ATT_TRACE_SLOTS + slot] = clock64();
   }
 }
 
@@ -145,7 +147,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ __align__(8) uint64_t bar_q, bar_s_full, bar_s_free, bar_p_full, bar_pv_done;
   __shared__ __align__(8) uint64_t k_full[ATT_KSTAGES], k_empty[ATT_KSTAGES], v_full[ATT_VSTAGES], v_empty[ATT_VSTAGES];
   __shared__ uint32_t tmem_slot;
-  __shared__ float xch[2][2][ATT_BM];  // [tile parity][column half][row]: partial row max exchanged between paired warps
+  __shared__ float xch[2][2][ATT_BM];  // [tile parity][column half][row]: partial row max published to the paired warp
+  __shared__ float lxch[2][ATT_BM];    // [column half][row]: partial row sums (epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,7 +159,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int bh = b * a.heads + h;
   const int* sched = a.sched + (static_cast<size_t>(b) * a.q_tiles + qt) * a.sched_stride;
   const int n_kv = sched[0];
-  const bool tr_cta = TRACE && b == 0 && h == 0 && qt == a.q_tiles / 2;
+  unsigned long long* tr_cta = nullptr;   // trace buffer if this CTA is the traced one
+  if (TRACE) {
+    if (b == 0 && h == 0 && qt == a.q_tiles / 2) tr_cta = g_attn_trace;
+  }
   constexpr int W_MMA = ATT_SOFTMAX_WARPS, W_TMA = ATT_SOFTMAX_WARPS + 1;
 
   if (warp == W_TMA && lane == 0) {
@@ -190,7 +196,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == W_TMA) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== TMA producer =====
       mbar_arrive_expect_tx(&bar_q, ATT_TILE_BYTES);
       tma_load_3d(smem_q, &tm_q, &bar_q, 0, qt * ATT_BM, bh);
@@ -215,7 +221,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // A = Q (K-major), B = K (K-major)
       constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_HD, 0, 1);  // A = P (TMEM),    B = V (MN-major)
@@ -282,14 +288,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t t_o = tmem_base + lane_base + TM_O + half * 32;
     const uint32_t t_p = tmem_base + lane_base + TM_P + half * 32;
     const float c = a.scale_log2;
-    float m_run = -INFINITY;  // running reference max (raw score units); identical in both column halves
+    // Reference max of the row (raw score units), identical in both column halves.  It is STALE by one tile: tile j is
+    // exponentiated against the max over tiles < j (tile 0: exact, one paired exchange), and the max of tile j-1 -- each
+    // half publishes its partial in `xch`, ordered by bar_p_full(j-1) -- only raises the reference for tile j when it
+    // grew by more than 2^8 (lazy rescale).  bf16 P and the fp32 accumulators have fp32's exponent range, so a tile that
+    // overshoots the stale reference is exact as long as scores do not jump by > ~2^100 between neighbouring tiles
+    // (logits of RMS-normed q/k are bounded far below that).  This removes the per-tile pair barrier and the wait on
+    // P.V(j-1) from the softmax critical path: exps need only registers; P.V(j-1) is awaited just before P is stored.
+    float m_run = -INFINITY;        // -inf: no finite score seen yet, reference 0
+    float m_prev_part = -INFINITY;  // this half's partial max of the previous tile
     float l4[4] = {0.f, 0.f, 0.f, 0.f};  // this half's partial row sum (4 chains)
-    const bool tr_me = tr_cta && lane == 0 && quarter == 0;
+    unsigned long long* tr_me = (lane == 0 && quarter == 0) ? tr_cta : nullptr;
+    int entry = sched[1];
 
     for (int j = 0; j < n_kv; ++j) {
-      const int entry = sched[1 + j];
       const int kt = entry >> 1;
       const bool masked = (entry & 1) != 0;
+      if (j + 1 < n_kv) entry = __ldg(sched + 2 + j);   // next tile's entry: its latency hides under this iteration
       uint32_t allow0 = 0xffffffffu, allow1 = 0xffffffffu;
       if (masked) {
         const int* sg = a.seg + static_cast<size_t>(b) * a.seq;
@@ -324,66 +339,82 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mask32(vb, allow1);
       }
       const float m_part = fmaxf(max32(va), max32(vb));
-      xch[j & 1][half][row] = m_part;
-      pair_bar_sync(quarter);
-      const float m_tile = fmaxf(m_part, xch[j & 1][half ^ 1][row]);
+      if (TRACE) {   // keep the stamp behind the max (it would otherwise float above the FMNMX chain)
+        if (m_part == 12345.678f) trace_stamp<TRACE>(tr_me, half, j, 7);
+      }
+      trace_stamp<TRACE>(tr_me, half, j, 5);
+      float m_tile;   // exact max (both halves) of the newest tile that is known: tile 0 at j == 0, else tile j-1
+      if (j == 0) {
+        xch[0][half][row] = m_part;
+        pair_bar_sync(quarter);
+        m_tile = fmaxf(m_part, xch[0][half ^ 1][row]);
+      } else {
+        mbar_wait(&bar_p_full, (j - 1) & 1);   // every softmax thread finished tile j-1: partials published, slots reusable
+        m_tile = fmaxf(m_prev_part, xch[(j - 1) & 1][half ^ 1][row]);
+        xch[j & 1][half][row] = m_part;
+      }
+      m_prev_part = m_part;
       trace_stamp<TRACE>(tr_me, half, j, 2);
 
-      // ---- lazy rescale decision (per row, same in both halves), correction is warp-collective
+      // ---- lazy rescale decision (per row, same in both halves)
       const float m_cand = fmaxf(m_run, m_tile);
       float alpha = 1.f;
       bool need = false;
       if (m_cand > m_run) {
         if (m_run == -INFINITY || (m_cand - m_run) * c > 8.f) {
-          need = true;
-          alpha = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m_cand) * c);
+          const float ref_old = (m_run == -INFINITY) ? 0.f : m_run * c;
+          if (j > 0) {
+            need = true;
+            alpha = ex2f(fminf(fmaxf(ref_old - m_cand * c, -126.f), 126.f));
+          }
           m_run = m_cand;
-        }
-      }
-      // P(j-1) / O must have been consumed / produced by P.V(j-1) before P is overwritten or O is rescaled
-      if (j > 0) {
-        mbar_wait(&bar_pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      trace_stamp<TRACE>(tr_me, half, j, 3);
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-#pragma unroll 1
-        for (int cc = 0; cc < 32; cc += 16) {   // 16 columns at a time: the 64 scores stay live in registers
-          uint32_t o[16];
-          tmem_ld16(t_o + cc, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(t_o + cc, o);
         }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) l4[i] *= alpha;
       const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
 
-      // ---- p = exp2(s*c - m_ref) -> P (bf16x2) in TMEM
-      uint32_t pk[16];
+      // ---- p = exp2(s*c - m_ref), packed bf16x2, still in registers
+      uint32_t pk0[16], pk1[16];
       if (POLY && !masked) {
-        exp32<1>(va, pk, c, m_ref, l4);
-        tmem_st16(t_p, pk);
-        exp32<1>(vb, pk, c, m_ref, l4);
+        exp32<1>(va, pk0, c, m_ref, l4);
+        exp32<1>(vb, pk1, c, m_ref, l4);
       } else {
-        exp32<0>(va, pk, c, m_ref, l4);
-        tmem_st16(t_p, pk);
-        exp32<0>(vb, pk, c, m_ref, l4);
+        exp32<0>(va, pk0, c, m_ref, l4);
+        exp32<0>(vb, pk1, c, m_ref, l4);
       }
-      tmem_st16(t_p + 16, pk);
+      trace_stamp<TRACE>(tr_me, half, j, 3);
+
+      // ---- P(j-1) must have been consumed and O(j-1) produced by P.V(j-1) before P is overwritten / O is rescaled
+      if (j > 0) {
+        mbar_wait(&bar_pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+          for (int cc = 0; cc < 32; cc += 16) {
+            uint32_t o[16];
+            tmem_ld16(t_o + cc, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(t_o + cc, o);
+          }
+        }
+      }
+      tmem_st16(t_p, pk0);
+      tmem_st16(t_p + 16, pk1);
       tmem_st_wait();
       trace_stamp<TRACE>(tr_me, half, j, 4);
       tc_fence_before();
       mbar_arrive(&bar_p_full);
+      trace_stamp<TRACE>(tr_me, half, j, 6);
     }
 
     // ---- epilogue: combine the two halves' row sums, O / l -> bf16 -> out[b, qpos, h*64 + half*32 .. +32]
     const float l_part = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-    xch[n_kv & 1][half][row] = l_part;
+    lxch[half][row] = l_part;
     pair_bar_sync(quarter);
-    const float l_run = l_part + xch[n_kv & 1][half ^ 1][row];
+    const float l_run = l_part + lxch[half ^ 1][row];
     mbar_wait(&bar_pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
@@ -525,7 +556,7 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   return check_launch("pf_attn_fwd_masked");
 }
 
-// Debug: device buffer of 3 * 48 * 5 uint64 clock stamps filled by the variant-2 (trace) kernel; NULL disables.
+// Debug: device buffer of 3 * 48 * 8 uint64 clock stamps filled by the variant-2 (trace) kernel; NULL disables.
 extern "C" int pf_debug_attn_trace(void* device_buf) {
   unsigned long long* p = static_cast<unsigned long long*>(device_buf);
   cudaError_t e = cudaMemcpyToSymbol(pf::g_attn_trace, &p, sizeof(p));

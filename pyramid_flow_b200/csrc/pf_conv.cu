@@ -190,7 +190,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
   const int sp_tiles = g.tiles_h * g.tiles_w;
   const long long total_tiles = static_cast<long long>(g.b) * g.t * sp_tiles * g.n_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {   // elect.sync: the compiler keeps the role's code on the uniform datapath
     // ===== TMA producer =====
     int stage = 0;
     uint32_t phase = 0;
@@ -220,7 +220,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_bf16(CBM, BN, 0, 0);
     int stage = 0;
@@ -373,7 +373,7 @@ conv3d2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     }
   };
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
     const int ph = g.kh >> 1, pw = g.kw >> 1;
@@ -398,7 +398,7 @@ conv3d2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader && elect_one()) {
     constexpr uint32_t idesc = make_idesc_bf16(2 * CBM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;

@@ -252,7 +252,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const int tiles_per_batch = g.m_tiles * g.n_tiles;
   const int total_tiles = g.batches * tiles_per_batch;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {   // elect.sync: the compiler keeps the role's code on the uniform datapath
     // ===== TMA producer =====
     int stage = 0;
     uint32_t phase = 0;
@@ -274,7 +274,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && elect_one()) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
     int stage = 0;
@@ -415,7 +415,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && elect_one()) {   // elect.sync: the compiler keeps the role's code on the uniform datapath
     // ===== TMA producer (both CTAs) =====
     int stage = 0;
     uint32_t phase = 0;
@@ -437,7 +437,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader && elect_one()) {
     // ===== MMA issuer (leader CTA only) =====
     constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
     int stage = 0;

@@ -397,30 +397,33 @@ def group_attn_trace():
     out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
     sched, pairs = ops.attn_build_schedule(seg, tim)
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
-    N = 48
-    buf = torch.zeros(3 * N * 5, dtype=torch.int64, device=dev)
+    N, SL = 48, 8
+    buf = torch.zeros(3 * N * SL, dtype=torch.int64, device=dev)
     _lib.check(_lib.load().pf_debug_attn_trace(buf.data_ptr()), "trace")
     for _ in range(2):
         ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, 2)
     torch.cuda.synchronize()
     _lib.check(_lib.load().pf_debug_attn_trace(None), "trace")
-    t = buf.cpu().view(3, N, 5)
+    t = buf.cpu().view(3, N, SL)
     t0 = int(t[0, 0, 0])
-    print("[attn_trace] iteration: softmax half0 [S_full, ld_done, pair_done, pv_done(j-1), p_stored] | half1 [...] | "
-          "MMA [s_free, qk_issued, p_full, v_full, pv_issued]  (cycles since first S_full)")
-    for j in range(8, 28):
-        row = " | ".join(" ".join(f"{int(t[r, j, i]) - t0:7d}" for i in range(5)) for r in range(3))
-        print(f"[attn_trace] j={j:2d}: {row}")
+    print("[attn_trace] softmax slots: 0 S_full seen, 1 ld done, 5 max done, 2 reference known (p_full(j-1) + partner max), "
+          "3 exps done, 4 P stored (after pv_done(j-1)), 6 arrived p_full | MMA slots: 0 s_free seen, 1 QK(j+1) issued, "
+          "2 p_full seen, 3 v_full, 4 PV(j) issued")
+    order = [0, 1, 5, 2, 3, 4, 6]
+    for j in range(8, 16):
+        sm = " ".join(f"{int(t[0, j, i]) - t0:7d}" for i in order)
+        mm = " ".join(f"{int(t[2, j, i]) - t0:7d}" for i in range(5))
+        print(f"[attn_trace] j={j:2d}: softmax0 {sm} | mma {mm}")
     per = (int(t[0, 40, 0]) - int(t[0, 8, 0])) / 32.0
     d = t[:, 8:40].double()
+    ph = lambda r, x, y: float((d[r, :, y] - d[r, :, x]).mean())
     print(f"[attn_trace] cycles per kv tile (this CTA): {per:.0f}")
-    print(f"[attn_trace] softmax half0 mean phase lengths: S_full->ld {float((d[0,:,1]-d[0,:,0]).mean()):.0f}, ld->pair "
-          f"{float((d[0,:,2]-d[0,:,1]).mean()):.0f}, pair->pv_done {float((d[0,:,3]-d[0,:,2]).mean()):.0f}, exp+store "
-          f"{float((d[0,:,4]-d[0,:,3]).mean()):.0f}, p_stored->next S_full {float((d[0,1:,0]-d[0,:-1,4]).mean()):.0f}")
-    print(f"[attn_trace] MMA: p_stored(half0)->p_full seen {float((d[2,:,2]-d[0,:,4]).mean()):.0f}, p_full->pv_issued "
-          f"{float((d[2,:,4]-d[2,:,2]).mean()):.0f}, pv_issued->pv_done seen by softmax(j+1) {float((d[0,1:,3]-d[2,:-1,4]).mean()):.0f}, "
-          f"ld_done(half0)->s_free seen {float((d[2,:,0]-d[0,:,1]).mean()):.0f}, qk issue {float((d[2,:,1]-d[2,:,0]).mean()):.0f}, "
-          f"qk_issued(j)->S_full(j+1) seen {float((d[0,1:,0]-d[2,:-1,1]).mean()):.0f}")
+    print(f"[attn_trace] softmax half0 mean phases: S_full->ld {ph(0,0,1):.0f} | ld->max {ph(0,1,5):.0f} | max->ref_known "
+          f"{ph(0,5,2):.0f} | exps {ph(0,2,3):.0f} | pv_done wait + P store {ph(0,3,4):.0f} | fence+arrive {ph(0,4,6):.0f} | "
+          f"arrive->next S_full {float((d[0,1:,0]-d[0,:-1,6]).mean()):.0f}")
+    print(f"[attn_trace] MMA: arrive(half0)->p_full seen {float((d[2,:,2]-d[0,:,6]).mean()):.0f}, p_full->PV issued "
+          f"{ph(2,2,4):.0f}, ld_done(half0)->s_free seen {float((d[2,:,0]-d[0,:,1]).mean()):.0f}, "
+          f"QK issue {ph(2,0,1):.0f}, QK(j+1) issued->S_full(j+1) seen {float((d[0,1:,0]-d[2,:-1,1]).mean()):.0f}")
 
 
 def group_vae_perf():
