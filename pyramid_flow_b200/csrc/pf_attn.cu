@@ -322,7 +322,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         allow0 = bits0;
         allow1 = bits1;
       }
-      mbar_wait(&bar_s_full, j & 1);
+      // The three waits of an iteration (P-ready of tile j-1, S(j), P.V(j-1)) are probed early and consumed late: every
+      // mbarrier / shared-memory round trip queues behind the other CTA's MUFU stream in the MIO queue (~300 cycles),
+      // so they are overlapped with each other and with the exps instead of being paid one after the other.
+      bool pf_ok = true;
+      if (j > 0) pf_ok = mbar_test(&bar_p_full, (j - 1) & 1);
+      const bool s_ok = mbar_test(&bar_s_full, j & 1);
+      float m_partner = -INFINITY;
+      if (j > 0) {
+        if (!pf_ok) mbar_wait(&bar_p_full, (j - 1) & 1);   // every softmax thread finished tile j-1: partials published
+        m_partner = xch[(j - 1) & 1][half ^ 1][row];
+      }
+      if (!s_ok) mbar_wait(&bar_s_full, j & 1);
       tc_fence_after();
       trace_stamp<TRACE>(tr_me, half, j, 0);
 
@@ -349,9 +360,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         pair_bar_sync(quarter);
         m_tile = fmaxf(m_part, xch[0][half ^ 1][row]);
       } else {
-        mbar_wait(&bar_p_full, (j - 1) & 1);   // every softmax thread finished tile j-1: partials published, slots reusable
-        m_tile = fmaxf(m_prev_part, xch[(j - 1) & 1][half ^ 1][row]);
-        xch[j & 1][half][row] = m_part;
+        m_tile = fmaxf(m_prev_part, m_partner);
+        xch[j & 1][half][row] = m_part;   // slot (j & 1) was last read by the partner before its P-ready arrive of tile j-1
       }
       m_prev_part = m_part;
       trace_stamp<TRACE>(tr_me, half, j, 2);
@@ -375,6 +385,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
 
       // ---- p = exp2(s*c - m_ref), packed bf16x2, still in registers
+      bool pv_ok = true;
+      if (j > 0) pv_ok = mbar_test(&bar_pv_done, (j - 1) & 1);   // probe now, consume after the exps
       uint32_t pk0[16], pk1[16];
       if (POLY && !masked) {
         exp32<1>(va, pk0, c, m_ref, l4);
@@ -387,7 +399,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
       // ---- P(j-1) must have been consumed and O(j-1) produced by P.V(j-1) before P is overwritten / O is rescaled
       if (j > 0) {
-        mbar_wait(&bar_pv_done, (j - 1) & 1);
+        if (!pv_ok) mbar_wait(&bar_pv_done, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 1

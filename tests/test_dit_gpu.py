@@ -85,3 +85,32 @@ def test_miniflux_width_step_matches_oracle():
     assert err <= 1.5 * err_ref_bf16 + 2e-3, "CUDA path must be at least as close to fp32 truth as the reference's bf16 path"
     # sample 1 (full text) must not depend on sample 0's padding pattern; and the output must be non-degenerate
     assert ref.abs().mean().item() > 0.1
+
+
+def test_cuda_graph_replay_equals_host_launched_step(golden_dir):
+    """The captured-graph path (use_cuda_graph) replays the same kernels: outputs are bit-identical to the host-launched
+    step, for the capture call, for replays with new inputs, and after switching shapes and back."""
+    from oracle import flux_oracle as FO
+    from pyramid_flow_b200.dit import B200FluxTransformer, FluxConfigB200
+    g = torch.load(golden_dir / "flux_small.pt", weights_only=False)
+    cfg = FO.FluxConfig(**g["cfg"])
+    params = FO.synthetic_flux_params(cfg, seed=g["param_seed"])
+    dev = torch.device("cuda:0")
+    model = B200FluxTransformer(FluxConfigB200(**g["cfg"]), params, device=dev)
+    enc, mask, pooled = g["enc"].bfloat16().to(dev), g["mask"].to(dev), g["pooled"].to(dev)
+
+    def call(clips, t):
+        return model(sample=[[c.to(dev) for c in clips]], timestep_ratio=t.to(dev), encoder_hidden_states=enc,
+                     encoder_attention_mask=mask, pooled_projections=pooled)[0].float().cpu()
+
+    gen = torch.Generator().manual_seed(9)
+    variants = [([c.bfloat16() for c in g["clips"]], g["timestep"]),
+                ([torch.randn(c.shape, generator=gen).bfloat16() for c in g["clips"]], g["timestep"] * 0.25),
+                ([g["clips"][-1].bfloat16()], g["timestep"] * 0.5)]
+    eager = [call(c, t) for c, t in variants]
+    model.use_cuda_graph = True
+    for rnd in range(2):                       # round 0 captures (2 shapes), round 1 replays
+        for (c, t), ref in zip(variants, eager):
+            out = call(c, t)
+            assert torch.equal(out, ref), f"round {rnd}: graph replay differs from the host-launched step"
+    assert model.graph_replays == 6 and len(model._graphs) == 2
