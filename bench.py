@@ -300,7 +300,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = not args.no_graph
+    use_graph = world == 1 and not args.no_graph
     model.use_cuda_graph = use_graph
 
     def timed(fn, steps, events=False):

@@ -371,7 +371,11 @@ class B200FluxTransformer(torch.nn.Module):
         _lib.require_device()
         assert len(sample) == 1, "inference passes one stage per call (pipeline P:760-766)"
         clips = sample[0] if isinstance(sample[0], (list, tuple)) else [sample[0]]
-        if self.use_cuda_graph and not self.timer.enabled and self.attn_events is None:
+        lay = getattr(self, "layout", None)
+        # single-GPU layout only: capturing the NCCL all-to-alls of the CFG x SP layout hung on the 2-GPU box (round 1),
+        # so the parallel step stays host-launched
+        if (self.use_cuda_graph and not (lay is not None and lay.enabled) and not self.timer.enabled
+                and self.attn_events is None):
             return self._forward_graphed(list(clips), timestep_ratio, encoder_hidden_states, encoder_attention_mask,
                                          pooled_projections)
         return self._forward_eager(clips, timestep_ratio, encoder_hidden_states, encoder_attention_mask,
@@ -396,20 +400,14 @@ class B200FluxTransformer(torch.nn.Module):
             def run():
                 return self._forward_eager(static[:nclip], static[nclip], static[nclip + 1], mask, static[nclip + 2])[0]
 
-            lay = getattr(self, "layout", None)
-            par = lay is not None and lay.enabled
-            if par or not self._graph_warm:
-                # first capture of the process: let every kernel (and NCCL communicator) initialise outside capture;
-                # parallel layout: one host-launched step per new shape also allocates the per-rank workspace
+            self._workspace(clips[-1].shape[0], plan)          # allocate outside the capture (ordinary allocator pool)
+            if not self._graph_warm:        # first capture of the process: let every kernel initialise outside capture
                 run()
                 self._graph_warm = True
-            else:
-                self._workspace(clips[-1].shape[0], plan)      # allocate outside the capture (ordinary allocator pool)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures the collectives
-            with torch.cuda.graph(graph, capture_error_mode="thread_local" if par else "global"):
+            with torch.cuda.graph(graph):
                 out = run()
             ent = dict(graph=graph, static=static, out=out, launches=_lib.launch_count() - n0, plan=plan, mask=mask,
                        ws=dict(self._ws))   # the captured pointers must stay allocated as long as the graph lives

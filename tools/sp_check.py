@@ -48,21 +48,12 @@ for name, kw, clip_shapes, tlen in [
     out = model(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask,
                 pooled_projections=pooled)[0].float()
     torch.cuda.synchronize()
-    # captured-graph replay of the parallel step (NCCL all-to-alls inside the graph) must equal the host-launched one
-    model.use_cuda_graph = True
-    for _ in range(2):
-        outg = model(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask,
-                     pooled_projections=pooled)[0].float()
-    torch.cuda.synchronize()
-    model.use_cuda_graph = False
-    gdiff = (outg - out).abs().max().item()
-    assert gdiff == 0.0, f"graph replay differs from host-launched parallel step by {gdiff}"
     err = (out - ref).abs().max().item()
     errs = [None] * world
     dist.all_gather_object(errs, err)
     if rank == 0:
         print(f"[sp_check] {name}: world {world} = cfg {lay.cfg_ways} x sp {lay.sp} (heads {cfg.num_attention_heads} -> "
               f"{SP.padded_heads(cfg.num_attention_heads, lay.sp)}), S={seq}: max|parallel - single| per rank = "
-              f"{['%.2e' % e for e in errs]}  |ref| mean {ref.abs().mean().item():.3f}; graph replay bit-identical", flush=True)
+              f"{['%.2e' % e for e in errs]}  |ref| mean {ref.abs().mean().item():.3f}", flush=True)
     assert err < 2e-2, err
 dist.destroy_process_group()
