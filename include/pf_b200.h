@@ -100,6 +100,8 @@ typedef struct pf_attn_desc {
   const int32_t* tile_sched; /* device; layout documented at pf_attn_build_schedule */
   int32_t sched_stride;      /* int32 entries per (batch, q_tile) row */
   int32_t variant;           /* 0 = default; other values select experimental data paths (see pf_attn.cu) */
+  int32_t q_row_begin;       /* only q rows >= q_row_begin are computed (multiple of 128; 0 = all).  The last single block
+                              * needs the current clip's rows only (history outputs are discarded, reference F:380). */
 } pf_attn_desc;
 
 /* Host helper: from host copies of seg/time ids builds, for each (batch, 128-row q tile), the list of 128-wide kv

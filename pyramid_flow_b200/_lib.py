@@ -50,7 +50,7 @@ class AttnDesc(C.Structure):
         ("batch", C.c_int32), ("heads", C.c_int32), ("seq", C.c_int32), ("head_dim", C.c_int32),
         ("scale", C.c_float),
         ("seg", C.c_void_p), ("time", C.c_void_p), ("tile_sched", C.c_void_p),
-        ("sched_stride", C.c_int32), ("variant", C.c_int32),
+        ("sched_stride", C.c_int32), ("variant", C.c_int32), ("q_row_begin", C.c_int32),
     ]
 
 

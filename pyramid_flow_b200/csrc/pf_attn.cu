@@ -520,6 +520,8 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   PF_REQUIRE(d->batch > 0 && d->heads > 0 && d->seq > 0, "pf_attn_fwd_masked: bad shape");
   const int q_tiles = (d->seq + ATT_BM - 1) / ATT_BM;
   PF_REQUIRE(d->sched_stride >= 1 + q_tiles, "pf_attn_fwd_masked: schedule stride %d too small", d->sched_stride);
+  PF_REQUIRE(d->q_row_begin >= 0 && d->q_row_begin % ATT_BM == 0 && d->q_row_begin < d->seq,
+             "pf_attn_fwd_masked: q_row_begin %d must be a multiple of %d inside the sequence", d->q_row_begin, ATT_BM);
   PF_REQUIRE(d->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pf_attn_fwd_masked: out must be 16-byte aligned");
 
   CUtensorMap tm[3];
@@ -558,7 +560,8 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
     }
     attr_set = true;
   }
-  dim3 grid(q_tiles, d->heads, d->batch);
+  // q tile index = q_tiles - 1 - blockIdx.x: a shorter grid.x drops the leading (lowest) q tiles
+  dim3 grid(q_tiles - d->q_row_begin / ATT_BM, d->heads, d->batch);
   if (d->variant & 2)
     attn_fwd_kernel<0, 1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   else if (d->variant & 1)

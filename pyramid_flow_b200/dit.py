@@ -194,6 +194,7 @@ class B200FluxTransformer(torch.nn.Module):
         # CUDA graphs: the ~290 launches of a step are captured once per (plan, input shapes) and replayed, so the step
         # does not depend on how fast the host can walk the launch sequence (ctypes + descriptor encoding per launch).
         # Off by default: callers that reuse shapes for many steps (sampler, bench) turn it on.
+        self.trim_last_block = True     # last single block on the current clip's rows only (exact; see forward)
         self.use_cuda_graph = False
         self._graphs: "Dict[tuple, dict]" = {}
         self._graph_warm = False
@@ -499,14 +500,14 @@ class B200FluxTransformer(torch.nn.Module):
         def exchange_begin():
             return SP.heads_to_sequence_qkv_begin(q[0], k[0], v[0], lay) if nsp > 1 else None
 
-        def attention(pending=None):
+        def attention(pending=None, q_row_begin=0):
             ev = self.attn_events is not None
             if ev:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if nsp == 1:
                 if ev:
                     e0.record()
-                ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale)
+                ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale, q_row_begin=q_row_begin)
                 if ev:
                     e1.record()
             else:
@@ -550,24 +551,28 @@ class B200FluxTransformer(torch.nn.Module):
                     ops.gemm(cat[:, :, wa:], wf2[j], bf2[j], PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0,
                              row_count=rc, out=h, ldo=d, gate=mod[:, offs[j] + 5 * d:], gate_batch_stride=nm)  # gate_mlp
 
+        n_last = plan.last_tokens
         for i, w in enumerate(self.sgl):
             o = self.mod_off[f"single_transformer_blocks.{i}.norm"]
             lnmod(o, o + d, 0, sl)                                                                 # (shift, scale) N:232
+            # Last block: only the current clip's tokens are read afterwards (F:380), so its queries, MLP and projection
+            # run on the rows from the 128-aligned start of the current clip; K/V still cover every token.  Same kernels
+            # on fewer rows: the kept rows are bit-identical.  (Single-GPU layout; SP chunks stay uniform.)
+            r0 = ((s - n_last) // 128) * 128 if (self.trim_last_block and not par and i == len(self.sgl) - 1) else 0
             # two launches sharing A: measured faster than the fused q|k|v|mlp GEMM (PF_EPI_QKV_GELU), whose 192-wide
             # tiles slow the MLP half down (1.81 ms fused vs 0.60 + 0.62 ms split at S=15488)
             qkv(w["w_qkv"], w["b_qkv"], w["nq"], w["nk"], 0, sl)
             pending = exchange_begin()       # SP: the q/k/v all-to-alls run under the proj_mlp GEMM
             with T("gemm_single_mlp_gelu"):
-                ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=0,
-                         row_count=sl, out=cat, ldo=ldc, out_col_begin=wa)
-            attention(pending)
+                ops.gemm(xn, w["w_mlp"], w["b_mlp"], PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=r0,
+                         row_count=sl - r0, out=cat, ldo=ldc, out_col_begin=wa)
+            attention(pending, q_row_begin=r0)
             with T("gemm_single_out"):
                 ops.gemm(cat, w["w_out_p"] if pad else w["w_out"], w["b_out"], PF_EPI_GATE_RESID, batches=b,
-                         rows_per_batch=sl, row_begin=0, row_count=sl, out=h, ldo=d, gate=mod[:, o + 2 * d:],
+                         rows_per_batch=sl, row_begin=r0, row_count=sl - r0, out=h, ldo=d, gate=mod[:, o + 2 * d:],
                          gate_batch_stride=nm)
 
         # ---- head: only the current clip's tokens are needed (F:380); AdaLN-continuous is (scale, shift) (N:119)
-        n_last = plan.last_tokens
         o = self.mod_off["norm_out"]
         g0, g1 = max(s - n_last, c0), c1                 # my part of the last n_last tokens
         head = ws["head"]

@@ -139,8 +139,9 @@ def attn_build_schedule(seg: torch.Tensor, time: torch.Tensor):
 
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, seg: torch.Tensor,
-             time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0) -> None:
-    """q,k,v bf16 [B,H,S,64]; out bf16 [B,S,*] (row stride = out.stride(1)); seg/time/sched int32 on device."""
+             time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0, q_row_begin: int = 0) -> None:
+    """q,k,v bf16 [B,H,S,64]; out bf16 [B,S,*] (row stride = out.stride(1)); seg/time/sched int32 on device.
+    Only q rows >= q_row_begin (multiple of 128) are computed; other rows of `out` are left untouched."""
     assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     b, h, s, hd = q.shape
     d = AttnDesc()
@@ -151,6 +152,7 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
     d.seg, d.time, d.tile_sched = seg.data_ptr(), time.data_ptr(), sched.data_ptr()
     d.sched_stride = sched.shape[-1]
     d.variant = variant
+    d.q_row_begin = q_row_begin
     _lib.check(_lib.load().pf_attn_fwd_masked(C.byref(d), _lib.stream_ptr()), "pf_attn_fwd_masked")
 
 

@@ -114,3 +114,31 @@ def test_cuda_graph_replay_equals_host_launched_step(golden_dir):
             out = call(c, t)
             assert torch.equal(out, ref), f"round {rnd}: graph replay differs from the host-launched step"
     assert model.graph_replays == 6 and len(model._graphs) == 2
+
+
+def test_last_block_trim_is_exact():
+    """The last single block computed on the current clip's rows only (trim_last_block) gives bit-identical velocities."""
+    from oracle import flux_oracle as FO
+    from pyramid_flow_b200.dit import B200FluxTransformer, FluxConfigB200
+    kw = dict(num_layers=1, num_single_layers=2)
+    cfg = FO.FluxConfig(**kw)
+    dev = torch.device("cuda:0")
+    params = FO.synthetic_flux_params(cfg, seed=5)
+    g = torch.Generator().manual_seed(6)
+    clips = [torch.randn(2, 16, 2, 12, 20, generator=g).bfloat16().to(dev), torch.randn(2, 16, 1, 24, 40, generator=g).bfloat16().to(dev),
+             torch.randn(2, 16, 1, 48, 80, generator=g).bfloat16().to(dev)]
+    enc = (torch.randn(2, 128, 4096, generator=g) * 0.2).bfloat16().to(dev)
+    mask = torch.ones(2, 128, dtype=torch.long)
+    mask[1, 50:] = 0
+    mask = mask.to(dev)
+    pooled = torch.randn(2, 768, generator=g).to(dev)
+    t = torch.tensor([500.0, 500.0], device=dev)
+    model = B200FluxTransformer(FluxConfigB200(**kw), params, device=dev)
+    outs = []
+    for trim in (False, True):
+        model.trim_last_block = trim
+        outs.append(model(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask,
+                          pooled_projections=pooled)[0].float().cpu())
+    plan = model.last_plan
+    assert (plan.seq - plan.last_tokens) // 128 > 0, "shape too small to trim anything"
+    assert torch.equal(outs[0], outs[1])
