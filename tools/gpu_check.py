@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "attn_perf", "attn_trace", "vae_perf"]
+GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "gemm_qkv_perf", "attn_perf", "attn_trace", "vae_perf"]
 
 
 def _rel_err(a, b):
@@ -379,6 +379,27 @@ def group_gemm_epi_perf():
             print(f"[gemm_epi_perf] m={m} n={n} k={k} {name}: {ms:.3f} ms = {fl/ms:.0f} TF/s", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"[gemm_epi_perf] {name}: EXC {e}", flush=True)
+
+
+def group_gemm_qkv_perf():
+    """QKV GEMM with the RMSNorm + RoPE head-major epilogue vs the plain store at the same shape (N=5760, K=1920)."""
+    import torch
+    from pyramid_flow_b200 import ops
+    dev = "cuda"
+    B, S, H, D = 2, 15488, 30, 1920
+    m = B * S
+    x = (torch.randn(B, S, D, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(3 * D, D, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(3 * D, device=dev) * 0.1
+    q, k, v = (torch.empty(B, H, S, 64, device=dev, dtype=torch.bfloat16) for _ in range(3))
+    rope = torch.randn(S, 32, 2, device=dev)
+    nq, nk = torch.ones(64, device=dev), torch.ones(64, device=dev)
+    out = torch.empty(m, 3 * D, device=dev, dtype=torch.bfloat16)
+    fl = 2.0 * m * 3 * D * D / 1e9
+    ms0 = _time_cuda(lambda: ops.gemm(x, w, bias, 0, batches=B, rows_per_batch=S, out=out.view(B, S, 3 * D)))
+    ms1 = _time_cuda(lambda: ops.gemm(x, w, bias, 4, batches=B, rows_per_batch=S, q_out=q, k_out=k, v_out=v, rope=rope,
+                                      q_norm_w=nq, k_norm_w=nk, heads=H, head_dim=64, seq_len=S))
+    print(f"[gemm_qkv_perf] m={m} n={3*D} k={D}: store+bias {ms0:.3f} ms = {fl/ms0:.0f} TF/s | qkv_rope {ms1:.3f} ms = {fl/ms1:.0f} TF/s", flush=True)
 
 
 def group_attn_trace():
