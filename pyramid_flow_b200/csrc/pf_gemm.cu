@@ -88,8 +88,10 @@ __device__ __forceinline__ void add_bias32(float (&x)[32], const uint32_t (&v)[3
 
 // One head (64 columns = two 32-column TMEM chunks) of q / k / v for one token.
 // section 0 = q, 1 = k (RMSNorm over the head N:66-79, then RoPE B:34-39), 2 = v (plain store).
+// `cs` = this token's RoPE row (16 float4 = (cos, sin) of the 32 rotation pairs), loaded ONCE per output tile by the
+// caller: it depends on the position only, and fetching it inside every head call left its L2 latency exposed 4x per tile.
 __device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t taddr, int n0, int b, int pos,
-                                                  bool valid) {
+                                                  bool valid, const float4 (&cs_row)[16], bool have_rope) {
   uint32_t v0[32], v1[32];
   tmem_ld32(taddr, v0);
   tmem_ld32(taddr + 32, v1);
@@ -110,9 +112,15 @@ __device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t ta
   const int head = (n0 - section * inner) / g.head_dim;
   __nv_bfloat16* base = section == 0 ? g.q_out : (section == 1 ? g.k_out : g.v_out);
   if (section < 2) {
-    float ss = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four chains: a single 64-long FFMA chain is 256+ cycles of latency
 #pragma unroll
-    for (int i = 0; i < 64; ++i) ss += x[i] * x[i];
+    for (int i = 0; i < 64; i += 4) {
+      s0 = fmaf(x[i + 0], x[i + 0], s0);
+      s1 = fmaf(x[i + 1], x[i + 1], s1);
+      s2 = fmaf(x[i + 2], x[i + 2], s2);
+      s3 = fmaf(x[i + 3], x[i + 3], s3);
+    }
+    const float ss = (s0 + s1) + (s2 + s3);
     const float r = rsqrtf(ss * (1.0f / 64.0f) + g.norm_eps);
     const float4* w4 = reinterpret_cast<const float4*>(section == 0 ? g.q_norm_w : g.k_norm_w);
 #pragma unroll
@@ -123,11 +131,10 @@ __device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t ta
       x[4 * i + 2] *= r * w.z;
       x[4 * i + 3] *= r * w.w;
     }
-    if (g.rope != nullptr && valid) {
-      const float4* cs4 = reinterpret_cast<const float4*>(g.rope + static_cast<size_t>(pos) * 64);
+    if (have_rope) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float4 cs = __ldg(cs4 + i);  // (cos_{2i}, sin_{2i}, cos_{2i+1}, sin_{2i+1})
+        const float4 cs = cs_row[i];  // (cos_{2i}, sin_{2i}, cos_{2i+1}, sin_{2i+1})
         const float a0 = x[4 * i + 0], a1 = x[4 * i + 1], a2 = x[4 * i + 2], a3 = x[4 * i + 3];
         x[4 * i + 0] = cs.x * a0 - cs.y * a1;
         x[4 * i + 1] = cs.y * a0 + cs.x * a1;
@@ -158,9 +165,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
   if (EPI == PF_EPI_QKV_GELU) qkv_tile = n_base < g.n_split;
 
   if (qkv_tile) {
+    const int pos = g.out_row_begin + m;
+    const bool have_rope = g.rope != nullptr && valid;
+    float4 cs_row[16];
+    if (have_rope) {
+      const float4* cs4 = reinterpret_cast<const float4*>(g.rope + static_cast<size_t>(pos) * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs_row[i] = __ldg(cs4 + i);
+    }
 #pragma unroll 1
     for (int h = 0; h < BN / 64; ++h) {
-      qkv_head_epilogue(g, taddr + h * 64, n_base + h * 64, b, g.out_row_begin + m, valid);
+      qkv_head_epilogue(g, taddr + h * 64, n_base + h * 64, b, pos, valid, cs_row, have_rope);
     }
   } else {
 #pragma unroll 1
