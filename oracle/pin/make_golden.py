@@ -116,6 +116,7 @@ def make_sched():
 
 
 VAE_SMALL = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=(2, 2, 2, 2))
+VAE_ENC_SMALL = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=(1, 2, 1, 1))
 
 
 def make_vae():
@@ -145,6 +146,36 @@ def make_vae():
           "chunk2 diff", float((full - chunk2).abs().max()), "tiled diff", float((full - tiled).abs().max()))
     torch.save({"cfg": VAE_SMALL, "param_seed": 0, "z": z, "full": full, "chunk1_maxdiff": float((full - chunk1).abs().max()),
                 "chunk2_maxdiff": float((full - chunk2).abs().max()), "tiled32": tiled}, GOLD / "vae_small.pt")
+
+
+def make_vae_encoder():
+    """Tiny-width VAE encoder (stride-2 spatial / temporal causal convs, shortcut conv, mid attention) + quant_conv: the
+    moments the i2v path samples its image latent from (P:911), for a 1-frame image and for a 9-frame clip."""
+    from video_vae import CausalVideoVAE
+    from oracle import vae_oracle as VO
+    cfg = VO.VaeEncoderConfig(**VAE_ENC_SMALL)
+    params = VO.synthetic_vae_params(cfg, seed=1)
+    vae = CausalVideoVAE(encoder_out_channels=16, decoder_in_channels=16, encoder_block_out_channels=cfg.block_out_channels,
+                         encoder_layers_per_block=cfg.layers_per_block, decoder_block_out_channels=(32, 32, 32, 32),
+                         decoder_layers_per_block=(1, 1, 1, 1)).eval()
+    sd = vae.state_dict()
+    enc_keys = {k for k in sd if k.startswith("encoder.") or k.startswith("quant_conv.")}
+    assert enc_keys == set(params.keys()), (enc_keys ^ set(params.keys()))
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    sd.update(params)
+    vae.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    image = torch.randn(1, 3, 1, 64, 96, generator=g)
+    clip = torch.randn(1, 3, 9, 32, 48, generator=g)
+    with torch.no_grad():
+        m_image = vae.encode(image).latent_dist.parameters
+        m_clip = vae.encode(clip).latent_dist.parameters
+        d = vae.encode(image).latent_dist
+    print("vae encoder:", m_image.shape, float(m_image.abs().mean()), m_clip.shape, float(m_clip.abs().mean()))
+    torch.save({"cfg": VAE_ENC_SMALL, "param_seed": 1, "image": image, "clip": clip, "moments_image": m_image,
+                "moments_clip": m_clip, "mean_image": d.mean, "logvar_image": d.logvar, "std_image": d.std},
+               GOLD / "vae_encoder_small.pt")
 
 
 def make_sampler():

@@ -37,12 +37,13 @@ class VaeDecoderConfig:
     norm_num_groups: int = 32
 
 
-def causal_conv3d(p: Params, pre: str, x: torch.Tensor) -> torch.Tensor:
-    """CausalConv3d.forward, non-chunked (C:116-125,145): zero pad (k-1) frames in front, k//2 each side spatially."""
+def causal_conv3d(p: Params, pre: str, x: torch.Tensor, stride=(1, 1, 1)) -> torch.Tensor:
+    """CausalConv3d.forward, non-chunked (C:116-125,145): zero pad (k-1) frames in front, k//2 each side spatially;
+    `stride` = (t, h, w) of the down-samplers (C:66-67, R:322, R:486)."""
     w, b = p[pre + ".conv.weight"], p.get(pre + ".conv.bias")
     kt, kh, kw = w.shape[2:]
     x = F.pad(x, (kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0))
-    return F.conv3d(x, w, b)
+    return F.conv3d(x, w, b, stride=stride)
 
 
 def causal_group_norm(p: Params, pre: str, x: torch.Tensor, groups: int) -> torch.Tensor:
@@ -158,6 +159,84 @@ def tiled_decode(p: Params, cfg: VaeDecoderConfig, z: torch.Tensor, tile_sample_
     return torch.cat(out_rows, dim=3)
 
 
+# ---- encoder (i2v image latent: pipeline P:911) ------------------------------------------------------------------------
+@dataclass
+class VaeEncoderConfig:
+    """Encoder-side constructor arguments of CausalVideoVAE (V:76-93)."""
+    in_channels: int = 3
+    latent_channels: int = 16
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: Tuple[int, ...] = (2, 2, 2, 2)
+    spatial_down_sample: Tuple[bool, ...] = (True, True, True, False)
+    temporal_down_sample: Tuple[bool, ...] = (True, True, True, False)
+    norm_num_groups: int = 32
+
+
+def encoder_forward(p: Params, cfg: VaeEncoderConfig, x: torch.Tensor) -> torch.Tensor:
+    """CausalVaeEncoder.forward (D:149-198), whole clip at once (is_init_image=True): conv_in, down blocks (resnets, then the
+    stride-(1,2,2) and stride-(2,1,1) causal convs K:528-540), mid block, GroupNorm+SiLU, conv_out (2*latent channels)."""
+    g = cfg.norm_num_groups
+    h = causal_conv3d(p, "encoder.conv_in", x)
+    for i in range(len(cfg.block_out_channels)):
+        for j in range(cfg.layers_per_block[i]):
+            h = resnet_block(p, f"encoder.down_blocks.{i}.resnets.{j}", h, g)
+        if cfg.spatial_down_sample[i]:
+            h = causal_conv3d(p, f"encoder.down_blocks.{i}.downsamplers.0.conv", h, stride=(1, 2, 2))
+        if cfg.temporal_down_sample[i]:
+            h = causal_conv3d(p, f"encoder.down_blocks.{i}.temporal_downsamplers.0.conv", h, stride=(2, 1, 1))
+    h = resnet_block(p, "encoder.mid_block.resnets.0", h, g)
+    h = mid_attention(p, "encoder.mid_block.attentions.0", h, g)
+    h = resnet_block(p, "encoder.mid_block.resnets.1", h, g)
+    h = F.silu(causal_group_norm(p, "encoder.conv_norm_out", h, g))
+    return causal_conv3d(p, "encoder.conv_out", h)
+
+
+def encode_moments(p: Params, cfg: VaeEncoderConfig, x: torch.Tensor) -> torch.Tensor:
+    """CausalVideoVAE.encode, un-tiled, un-chunked (V:300-303): encoder then quant_conv (1x1x1); returns the moments
+    [B, 2*latent, T', h, w]: mean = first half, logvar = second half clamped to [-30, 20] (D:372-373)."""
+    return causal_conv3d(p, "quant_conv", encoder_forward(p, cfg, x))
+
+
+def vae_encoder_param_shapes(cfg: VaeEncoderConfig) -> Dict[str, tuple]:
+    s: Dict[str, tuple] = {}
+
+    def conv(name, co, ci, k):
+        s[name + ".conv.weight"] = (co, ci, k, k, k)
+        s[name + ".conv.bias"] = (co,)
+
+    def norm(name, c):
+        s[name + ".weight"] = (c,)
+        s[name + ".bias"] = (c,)
+
+    def res(name, ci, co):
+        norm(name + ".norm1", ci); conv(name + ".conv1", co, ci, 3)
+        norm(name + ".norm2", co); conv(name + ".conv2", co, co, 3)
+        if ci != co:
+            conv(name + ".conv_shortcut", co, ci, 1)
+
+    conv("encoder.conv_in", cfg.block_out_channels[0], cfg.in_channels, 3)
+    prev = cfg.block_out_channels[0]
+    for i, co in enumerate(cfg.block_out_channels):
+        for j in range(cfg.layers_per_block[i]):
+            res(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if cfg.spatial_down_sample[i]:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", co, co, 3)
+        if cfg.temporal_down_sample[i]:
+            conv(f"encoder.down_blocks.{i}.temporal_downsamplers.0.conv", co, co, 3)
+        prev = co
+    top = cfg.block_out_channels[-1]
+    res("encoder.mid_block.resnets.0", top, top)
+    norm("encoder.mid_block.attentions.0.group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        s[f"encoder.mid_block.attentions.0.{n}.weight"] = (top, top)
+        s[f"encoder.mid_block.attentions.0.{n}.bias"] = (top,)
+    res("encoder.mid_block.resnets.1", top, top)
+    norm("encoder.conv_norm_out", top)
+    conv("encoder.conv_out", 2 * cfg.latent_channels, top, 3)
+    conv("quant_conv", 2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+    return s
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def vae_decoder_param_shapes(cfg: VaeDecoderConfig) -> Dict[str, tuple]:
     s: Dict[str, tuple] = {}
@@ -200,12 +279,14 @@ def vae_decoder_param_shapes(cfg: VaeDecoderConfig) -> Dict[str, tuple]:
     return s
 
 
-def synthetic_vae_params(cfg: VaeDecoderConfig, seed: int = 0, device: str = "cpu", bf16_representable: bool = True) -> Params:
+def synthetic_vae_params(cfg, seed: int = 0, device: str = "cpu", bf16_representable: bool = True) -> Params:
     """Seeded parameters: conv/linear weights N(0, 1/fan_in) (x0.5 on each residual branch's last conv so activations stay
-    O(1) through ~30 residual blocks), biases N(0, 0.02^2), GroupNorm weight 1+N(0,0.1^2), bias N(0,0.05^2)."""
+    O(1) through ~30 residual blocks), biases N(0, 0.02^2), GroupNorm weight 1+N(0,0.1^2), bias N(0,0.05^2).
+    `cfg`: VaeDecoderConfig (decoder + post_quant_conv keys) or VaeEncoderConfig (encoder + quant_conv keys)."""
     g = torch.Generator().manual_seed(seed)
     out: Params = {}
-    for name, shp in vae_decoder_param_shapes(cfg).items():
+    shapes = vae_encoder_param_shapes(cfg) if isinstance(cfg, VaeEncoderConfig) else vae_decoder_param_shapes(cfg)
+    for name, shp in shapes.items():
         if len(shp) >= 2:
             fan_in = 1
             for d in shp[1:]:

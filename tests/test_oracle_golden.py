@@ -74,6 +74,25 @@ def test_vae_decode_oracle_matches_reference(golden_dir):
     assert g["full"].abs().mean().item() > 0.05
 
 
+def test_vae_encode_oracle_matches_reference(golden_dir):
+    """Encoder + quant_conv (stride-2 spatial / temporal causal convs) against the unmodified reference's moments."""
+    from oracle import vae_oracle as VO
+    g = _load(golden_dir, "vae_encoder_small.pt")
+    cfg = VO.VaeEncoderConfig(**g["cfg"])
+    p = VO.synthetic_vae_params(cfg, seed=g["param_seed"])
+    with torch.no_grad():
+        m_image = VO.encode_moments(p, cfg, g["image"])
+        m_clip = VO.encode_moments(p, cfg, g["clip"])
+    assert m_image.shape == g["moments_image"].shape == (1, 32, 1, 8, 12)
+    assert m_clip.shape == g["moments_clip"].shape == (1, 32, 2, 4, 6)
+    assert (m_image - g["moments_image"]).abs().max().item() < 5e-5
+    assert (m_clip - g["moments_clip"]).abs().max().item() < 5e-5
+    mean, logvar = m_image.chunk(2, dim=1)
+    assert (mean - g["mean_image"]).abs().max().item() < 5e-5
+    assert (logvar.clamp(-30.0, 20.0) - g["logvar_image"]).abs().max().item() < 5e-5
+    assert g["moments_image"].abs().mean().item() > 0.05
+
+
 def test_mmdit_small_forward_matches_reference(golden_dir):
     from oracle import mmdit_oracle as MO
     g = _load(golden_dir, "mmdit_small.pt")
