@@ -161,7 +161,7 @@ PF_API int pf_cfg_euler_step(const float* v2, float guidance, float dsigma, cons
  */
 typedef struct pf_conv3d_desc {
   const void* x;
-  int32_t b, t, h, w, cin; /* t = OUTPUT frames */
+  int32_t b, t, h, w, cin; /* OUTPUT frames / height / width (= input dims at unit stride) */
   const void* wgt;
   const float* bias; /* fp32 [cout] or NULL */
   int32_t cout, kt, kh, kw;
@@ -172,6 +172,9 @@ typedef struct pf_conv3d_desc {
   int32_t store_channels; /* first store_channels conv outputs are stored (the rest is filter padding) */
   const void* residual;   /* bf16 [B, res_t_total, H, W, out_c] read at frame t + res_t_offset, plain mode only */
   int32_t res_t_total, res_t_offset;
+  int32_t stride_t, stride_h, stride_w; /* 0/1 = unit stride; 2 = the encoder's down-samplers (C:66-67: CausalDownsample2x
+                                         * stride (1,2,2) R:322, CausalTemporalDownsample2x stride (2,1,1) R:486).  b,t,h,w
+                                         * stay OUTPUT dims; x is [B, (t-1)*stride_t + kt, h*stride_h, w*stride_w, cin]. */
 } pf_conv3d_desc;
 PF_API int pf_causal_conv3d(const pf_conv3d_desc* desc, void* stream);
 

@@ -65,6 +65,7 @@ class ConvDesc(C.Structure):
         ("out_t_total", C.c_int32), ("out_t_offset", C.c_int32), ("out_c", C.c_int32),
         ("store_channels", C.c_int32),
         ("residual", C.c_void_p), ("res_t_total", C.c_int32), ("res_t_offset", C.c_int32),
+        ("stride_t", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32),
     ]
 
 

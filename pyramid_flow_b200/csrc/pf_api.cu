@@ -49,7 +49,7 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,
                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                      CUtensorMapSwizzle swizzle) {
+                      CUtensorMapSwizzle swizzle, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   PF_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver / no GPU): libpf_b200 has no CPU fallback");
   cuuint64_t gdims[5];
@@ -59,7 +59,7 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
   for (uint32_t i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = fn(map, dtype, rank, const_cast<void*>(base), gdims, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -29,7 +29,8 @@ int  check_launch(const char* what);   // cudaGetLastError() -> status
 // Driver entry point (no link-time libcuda dependency: the .so must load on a box without a GPU).
 int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,
                       const uint64_t* dims, const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
-                      CUtensorMapSwizzle swizzle);
+                      CUtensorMapSwizzle swizzle,
+                      const uint32_t* elem_strides = nullptr /* traversal stride per dim (strided convs); NULL = 1 */);
 
 int num_sms();
 

@@ -23,6 +23,7 @@ struct ConvArgs {
   int b, t, h, w, cin;
   int cout;            // padded N actually computed (multiple of BN)
   int taps, kt, kh, kw;
+  int st, sh, sw;      // conv stride (t, h, w): 1, or 2 for the encoder's down-samplers; (b, t, h, w) are OUTPUT dims
   int th, tw, tiles_h, tiles_w;
   int n_tiles;
   const float* bias;
@@ -212,7 +213,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-        tma_load_5d(sa, &tm_x, &full_bar[stage], cc * CBK, w0 + dw - pw, h0 + dh - ph, tt + dt, bb);
+        tma_load_5d(sa, &tm_x, &full_bar[stage], cc * CBK, w0 * g.sw + dw - pw, h0 * g.sh + dh - ph, tt * g.st + dt, bb);
         tma_load_2d(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], kb * CBK, nt * BN);
         if (++stage == STAGES) {
           stage = 0;
@@ -390,7 +391,7 @@ conv3d2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
         else mbar_arrive_remote(&full_bar[stage], 0);
-        tma_load_5d_2cta(sa, &tm_x, &full_bar[stage], cc * CBK, w0 + dw - pw, h0 + dh - ph, tt + dt, bb);
+        tma_load_5d_2cta(sa, &tm_x, &full_bar[stage], cc * CBK, w0 * g.sw + dw - pw, h0 * g.sh + dh - ph, tt * g.st + dt, bb);
         tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], kb * CBK, nt * BN + static_cast<int>(rank) * (BN / 2));
         if (++stage == STAGES) {
           stage = 0;
@@ -520,10 +521,14 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   if (d->store_mode == 1) PF_REQUIRE(d->store_channels == d->cout && d->out_c * 4 == d->cout && !d->out_f32 && !d->residual, "pf_causal_conv3d: spatial depth-to-space needs out_c = cout/4, bf16, no residual");
   if (d->store_mode == 2) PF_REQUIRE(d->store_channels == d->cout && d->out_c * 2 == d->cout && !d->out_f32 && !d->residual, "pf_causal_conv3d: temporal depth-to-space needs out_c = cout/2, bf16, no residual");
   if (d->store_mode == 0) PF_REQUIRE(d->out_c >= d->store_channels, "pf_causal_conv3d: out_c < store_channels");
+  const int st = d->stride_t > 1 ? d->stride_t : 1, sh = d->stride_h > 1 ? d->stride_h : 1, sw = d->stride_w > 1 ? d->stride_w : 1;
+  PF_REQUIRE(st <= 2 && sh <= 2 && sw <= 2 && sh == sw, "pf_causal_conv3d: strides must be 1 or 2 with stride_h == stride_w");
+  if (st > 1 || sh > 1) PF_REQUIRE(d->store_mode == 0 && d->kt == 3 && d->kh == 3, "pf_causal_conv3d: strided convs are plain-store 3x3x3 (CausalDownsample2x R:322, CausalTemporalDownsample2x R:486)");
 
   ConvArgs g{};
   g.b = d->b; g.t = d->t; g.h = d->h; g.w = d->w; g.cin = d->cin; g.cout = d->cout;
   g.kt = d->kt; g.kh = d->kh; g.kw = d->kw; g.taps = d->kt * d->kh * d->kw;
+  g.st = st; g.sh = sh; g.sw = sw;
   int tw = 128;
   while (tw > 8 && tw / 2 >= d->w) tw >>= 1;   // smallest power of two >= w, clamped to [8, 128]
   g.tw = tw; g.th = 128 / tw;
@@ -548,16 +553,20 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   bool two_cta = bn >= 128 && static_cast<long long>(d->b) * d->t * g.tiles_h * g.tiles_w * g.n_tiles >= 296;
   if (env_2cta == 0) two_cta = false;
   if (env_2cta == 1 && bn >= 128) two_cta = true;
-  const int tin = d->t + d->kt - 1;
+  // input geometry: (t-1)*st + kt frames (the kt-1 causal frames physically first), h*sh x w*sw voxels (symmetric pad 1 is
+  // the TMA's out-of-bounds zero fill).  A strided conv loads every sh-th / sw-th voxel of a (th*sh) x (tw*sw) box.
+  const int tin = (d->t - 1) * st + d->kt;
+  const int hin = d->h * sh, win = d->w * sw;
   CUtensorMap tm_x, tm_w;
   {
-    const uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(d->w), static_cast<uint64_t>(d->h),
+    const uint64_t dims[5] = {static_cast<uint64_t>(d->cin), static_cast<uint64_t>(win), static_cast<uint64_t>(hin),
                               static_cast<uint64_t>(tin), static_cast<uint64_t>(d->b)};
     const uint64_t s0 = static_cast<uint64_t>(d->cin) * 2;
-    const uint64_t strides[4] = {s0, s0 * d->w, s0 * d->w * d->h, s0 * d->w * d->h * tin};
-    const uint32_t box[5] = {CBK, static_cast<uint32_t>(g.tw), static_cast<uint32_t>(g.th), 1, 1};
+    const uint64_t strides[4] = {s0, s0 * win, s0 * win * hin, s0 * win * hin * tin};
+    const uint32_t box[5] = {CBK, static_cast<uint32_t>(g.tw * sw), static_cast<uint32_t>(g.th * sh), 1, 1};
+    const uint32_t estr[5] = {1, static_cast<uint32_t>(sw), static_cast<uint32_t>(sh), 1, 1};
     int rc = encode_tensor_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->x, dims, strides, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B);
+                               CU_TENSOR_MAP_SWIZZLE_128B, estr);
     if (rc) return rc;
   }
   {

@@ -1,11 +1,13 @@
-"""B200CausalVAE — drop-in for the DECODE half of the reference `CausalVideoVAE` (video_vae/modeling_causal_vae.py).
+"""B200CausalVAE — drop-in for the reference `CausalVideoVAE` (video_vae/modeling_causal_vae.py) as the sampler uses it.
 
-Call surface used by the pipeline (pyramid_dit_for_video_gen_pipeline.py:1221-1243):
+Call surface used by the pipeline (pyramid_dit_for_video_gen_pipeline.py:1221-1243, :911):
 
     self.vae.decode(latents, temporal_chunk=True, window_size=w, tile_sample_min_size=s).sample    # [B, 3, T', H', W']
+    self.vae.encode(image[:, :, None]).latent_dist.sample()                                        # i2v image latent
 
 plus `.device`, `.dtype`, `.to()`, `.enable_tiling()`.  Weights come from a state-dict in the reference key layout
-(`decoder.*`, `post_quant_conv.*`).
+(`decoder.*`, `post_quant_conv.*`, and — when present — `encoder.*`, `quant_conv.*`).  The encoder reuses the
+decoder's kernels; its down-samplers are the same implicit-GEMM conv with a strided TMA box (`stride_*` in pf_conv3d_desc).
 
 Execution model (all math in libpf_b200 kernels, channels-last bf16 activations `[T, H, W, C]`, batch handled one sample
 at a time as the pipeline does):
@@ -40,11 +42,42 @@ class VaeConfigB200:
     temporal_up_sample: Tuple[bool, ...] = (True, True, True, False)
     norm_num_groups: int = 32
     downsample_scale: int = 8
+    # encoder side (V:76-93); used only when the state-dict carries `encoder.*`
+    enc_in_channels: int = 3
+    enc_block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    enc_layers_per_block: Tuple[int, ...] = (2, 2, 2, 2)
+    enc_spatial_down_sample: Tuple[bool, ...] = (True, True, True, False)
+    enc_temporal_down_sample: Tuple[bool, ...] = (True, True, True, False)
 
 
 class DecoderOutput:
     def __init__(self, sample):
         self.sample = sample
+
+
+class DiagonalGaussian:
+    """DiagonalGaussianDistribution (D:369-391) over moments [B, 2C, T, h, w]: mean | logvar (clamped to [-30, 20])."""
+
+    def __init__(self, parameters: torch.Tensor):
+        self.parameters = parameters
+        self.mean, logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        # randn_tensor semantics (P:676-695): a CPU generator draws on the CPU, then the noise moves to the device
+        gdev = generator.device if generator is not None else self.mean.device
+        noise = torch.randn(self.mean.shape, generator=generator, device=gdev, dtype=self.mean.dtype).to(self.mean.device)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class EncoderOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
 
 
 def _pad64(n: int) -> int:
@@ -67,6 +100,8 @@ class _Conv:
             b[:co] = sd[name + ".conv.bias"].float()
         self.bias = b.to(device)
         self.cache: Optional[torch.Tensor] = None   # last (kt-1) frames of the previous chunk's padded input
+        # conv stride (t, h, w): the encoder's CausalDownsample2x (R:322) / CausalTemporalDownsample2x (R:486)
+        self.stride = (2, 1, 1) if ".temporal_downsamplers." in name else (1, 2, 2) if ".downsamplers." in name else (1, 1, 1)
 
 
 class B200CausalVAE(torch.nn.Module):
@@ -81,31 +116,37 @@ class B200CausalVAE(torch.nn.Module):
         sd = state_dict
         self.convs: Dict[str, _Conv] = {}
         self.norms: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        sides = ("decoder.", "post_quant_conv.", "encoder.", "quant_conv.")
         for k in sd:
-            if k.endswith(".conv.weight") and (k.startswith("decoder.") or k.startswith("post_quant_conv.")):
+            if k.endswith(".conv.weight") and k.startswith(sides):
                 name = k[: -len(".conv.weight")]
                 self.convs[name] = _Conv(sd, name, dev)
         for k in sd:
-            if k.startswith("decoder.") and k.endswith(".weight") and sd[k].ndim == 1:
+            if k.startswith(("decoder.", "encoder.")) and k.endswith(".weight") and sd[k].ndim == 1:
                 name = k[: -len(".weight")]
                 self.norms[name] = (sd[k].float().to(dev).contiguous(), sd[name + ".bias"].float().to(dev).contiguous())
+        self.has_decoder = "decoder.conv_in" in self.convs
+        self.has_encoder = "encoder.conv_in" in self.convs
         # mid-block attention (diffusers Attention): q/k/out as 1x1x1 convs, v as a transposed GEMM
-        a = "decoder.mid_block.attentions.0"
-        c = sd[a + ".to_q.weight"].shape[0]
-        self.attn_c = c
+        self.attn: Dict[str, dict] = {}
+        for side in ("decoder", "encoder"):
+            a = side + ".mid_block.attentions.0"
+            if (a + ".to_q.weight") not in sd:
+                continue
+            c = sd[a + ".to_q.weight"].shape[0]
 
-        def lin_as_conv(prefix, bias_override=None):
-            fake = {"x.conv.weight": sd[prefix + ".weight"].float().reshape(c, c, 1, 1, 1),
-                    "x.conv.bias": sd[prefix + ".bias"].float() if bias_override is None else bias_override}
-            return _Conv(fake, "x", dev)
+            def lin_as_conv(prefix, bias_override=None, c=c):
+                fake = {"x.conv.weight": sd[prefix + ".weight"].float().reshape(c, c, 1, 1, 1),
+                        "x.conv.bias": sd[prefix + ".bias"].float() if bias_override is None else bias_override}
+                return _Conv(fake, "x", dev)
 
-        self.attn_q = lin_as_conv(a + ".to_q")
-        self.attn_k = lin_as_conv(a + ".to_k")
-        wo, bo = sd[a + ".to_out.0.weight"].float(), sd[a + ".to_out.0.bias"].float()
-        bv = sd[a + ".to_v.bias"].float()
-        # softmax rows sum to 1 => P(V + 1 b_v^T) = PV + b_v^T: fold W_o b_v into the output bias
-        self.attn_o = lin_as_conv(a + ".to_out.0", bias_override=bo + wo @ bv)
-        self.attn_wv = sd[a + ".to_v.weight"].float().to(device=dev, dtype=torch.bfloat16).contiguous()
+            wo, bo = sd[a + ".to_out.0.weight"].float(), sd[a + ".to_out.0.bias"].float()
+            bv = sd[a + ".to_v.bias"].float()
+            self.attn[side] = dict(
+                q=lin_as_conv(a + ".to_q"), k=lin_as_conv(a + ".to_k"),
+                # softmax rows sum to 1 => P(V + 1 b_v^T) = PV + b_v^T: fold W_o b_v into the output bias
+                o=lin_as_conv(a + ".to_out.0", bias_override=bo + wo @ bv),
+                wv=sd[a + ".to_v.weight"].float().to(device=dev, dtype=torch.bfloat16).contiguous())
         self.register_buffer("_anchor", torch.zeros(1, device=dev, dtype=torch.bfloat16))
 
     @classmethod
@@ -116,7 +157,12 @@ class B200CausalVAE(torch.nn.Module):
                             layers_per_block=tuple(rc.decoder_layers_per_block),
                             spatial_up_sample=tuple(rc.decoder_spatial_up_sample),
                             temporal_up_sample=tuple(rc.decoder_temporal_up_sample),
-                            norm_num_groups=rc.decoder_norm_num_groups, downsample_scale=rc.downsample_scale)
+                            norm_num_groups=rc.decoder_norm_num_groups, downsample_scale=rc.downsample_scale,
+                            enc_in_channels=rc.encoder_in_channels,
+                            enc_block_out_channels=tuple(rc.encoder_block_out_channels),
+                            enc_layers_per_block=tuple(rc.encoder_layers_per_block),
+                            enc_spatial_down_sample=tuple(rc.encoder_spatial_down_sample),
+                            enc_temporal_down_sample=tuple(rc.encoder_temporal_down_sample))
         return cls(cfg, ref_vae.state_dict(), device=device)
 
     @property
@@ -164,9 +210,12 @@ class B200CausalVAE(torch.nn.Module):
     def _conv(self, cv: _Conv, x: torch.Tensor, t: int, h: int, w: int, *, out: torch.Tensor, out_t_offset: int = 0,
               store_mode: int = 0, residual: Optional[torch.Tensor] = None, res_t_offset: int = 0,
               store_channels: Optional[int] = None, out_f32: bool = False) -> None:
-        """x: [t + kt - 1, h, w, cin_p] (halo frames first); out: [out_t_total, H', W', out_c]."""
-        assert x.is_contiguous() and out.is_contiguous() and x.shape[-1] == cv.cin_p and x.shape[0] == t + cv.kt - 1
+        """t, h, w = OUTPUT dims.  x: [(t-1)*st + kt, h*sh, w*sw, cin_p] (halo frames first); out: [out_t_total, H', W', out_c]."""
+        st, sh, sw = cv.stride
+        assert x.is_contiguous() and out.is_contiguous() and x.shape[-1] == cv.cin_p
+        assert tuple(x.shape[:3]) == ((t - 1) * st + cv.kt, h * sh, w * sw), (tuple(x.shape), t, h, w, cv.stride)
         d = ConvDesc()
+        d.stride_t, d.stride_h, d.stride_w = st, sh, sw
         d.x = x.data_ptr()
         d.b, d.t, d.h, d.w, d.cin = 1, t, h, w, cv.cin_p
         d.wgt, d.bias = cv.w.data_ptr(), cv.bias.data_ptr()
@@ -246,19 +295,20 @@ class B200CausalVAE(torch.nn.Module):
         self._conv(c2, bbuf, t, h, w, out=out, out_t_offset=off, residual=sc, res_t_offset=0)
         return out
 
-    def _mid_attention(self, x: torch.Tensor) -> torch.Tensor:
+    def _mid_attention(self, x: torch.Tensor, side: str = "decoder") -> torch.Tensor:
         """Per-frame single-head attention over the h*w tokens (K:454-460 + diffusers Attention). x [T, H, W, C]."""
+        at = self.attn[side]
         t, h, w, c = x.shape
         dev = x.device
         n = h * w
         npad = _pad64(n)
         slack = 128
         xn = torch.zeros(t * n + slack, c, device=dev, dtype=torch.bfloat16)
-        self._gn("decoder.mid_block.attentions.0.group_norm", x, xn[: t * n].view(t, h, w, c), 0, False)
+        self._gn(side + ".mid_block.attentions.0.group_norm", x, xn[: t * n].view(t, h, w, c), 0, False)
         q = torch.empty(t, h, w, c, device=dev, dtype=torch.bfloat16)
         k = torch.zeros(t * n + slack, c, device=dev, dtype=torch.bfloat16)
-        self._conv(self.attn_q, xn[: t * n].view(t, h, w, c), t, h, w, out=q)
-        self._conv(self.attn_k, xn[: t * n].view(t, h, w, c), t, h, w, out=k[: t * n].view(t, h, w, c))
+        self._conv(at["q"], xn[: t * n].view(t, h, w, c), t, h, w, out=q)
+        self._conv(at["k"], xn[: t * n].view(t, h, w, c), t, h, w, out=k[: t * n].view(t, h, w, c))
         o = torch.empty(t, h, w, c, device=dev, dtype=torch.bfloat16)
         vt = torch.empty(c, npad, device=dev, dtype=torch.bfloat16)
         s = torch.empty(n, npad, device=dev, dtype=torch.bfloat16)
@@ -266,13 +316,13 @@ class B200CausalVAE(torch.nn.Module):
         for f in range(t):
             xf = xn[f * n: f * n + npad]          # rows beyond n are the next frame / zero slack: finite, masked below
             kf = k[f * n: f * n + npad]
-            ops.gemm(self.attn_wv, xf, None, PF_EPI_STORE_BF16, rows_per_batch=c, out=vt)       # V^T [C, npad]
+            ops.gemm(at["wv"], xf, None, PF_EPI_STORE_BF16, rows_per_batch=c, out=vt)           # V^T [C, npad]
             ops.gemm(qf[f], kf, None, PF_EPI_STORE_BF16, rows_per_batch=n, out=s)               # S = Q K^T
             _lib.check(_lib.load().pf_softmax_rows(s.data_ptr(), n, n, npad, float(c) ** -0.5, _lib.stream_ptr()),
                        "pf_softmax_rows")
             ops.gemm(s, vt, None, PF_EPI_STORE_BF16, rows_per_batch=n, out=of[f])               # O = P V
         out = torch.empty(t, h, w, c, device=dev, dtype=torch.bfloat16)
-        self._conv(self.attn_o, o, t, h, w, out=out, residual=x, res_t_offset=0)
+        self._conv(at["o"], o, t, h, w, out=out, residual=x, res_t_offset=0)
         return out
 
     def _reset_caches(self):
@@ -295,7 +345,7 @@ class B200CausalVAE(torch.nn.Module):
         x = torch.empty(t, h, w, cin.cout_p, device=dev, dtype=torch.bfloat16)
         self._conv(cin, a, t, h, w, out=x)                                       # conv_in, D:310
         x = self._resnet("decoder.mid_block.resnets.0", x, first)
-        x = self._mid_attention(x)
+        x = self._mid_attention(x, "decoder")
         x = self._resnet("decoder.mid_block.resnets.1", x, first)
         n_blocks = len(cfg.block_out_channels)
         for i in range(n_blocks):
@@ -330,6 +380,82 @@ class B200CausalVAE(torch.nn.Module):
         out = torch.empty(t, h, w, cfg.out_channels, device=dev, dtype=torch.float32)
         self._conv(co, a, t, h, w, out=out, store_channels=cfg.out_channels, out_f32=True)
         return out
+
+    # ---- encoder (i2v image latent, P:911) ----------------------------------------------------------------------------
+    def _encode_sample(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [1, C, T, H, W] (T = 1 + 8k, H and W multiples of 8) -> moments fp32 [T', h, w, 2*latent], whole clip as one
+        chunk (CausalVaeEncoder.forward D:149-198 with is_init_image=True, then quant_conv V:301)."""
+        cfg, dev = self.cfg, self.device
+        _, cx, t, h, w = x.shape
+        n_blocks = len(cfg.enc_block_out_channels)
+        n_sp, n_tp = sum(cfg.enc_spatial_down_sample), sum(cfg.enc_temporal_down_sample)
+        assert h % (1 << n_sp) == 0 and w % (1 << n_sp) == 0, "height / width must be divisible by the spatial down-sampling"
+        assert (t - 1) % (1 << n_tp) == 0, "frames must be 1 + k * temporal down-sampling (V:315)"
+        cin = self.convs["encoder.conv_in"]
+        a = torch.empty(t + 2, h, w, cin.cin_p, device=dev, dtype=torch.bfloat16)
+        xx = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        _lib.check(_lib.load().pf_pack_latent(xx.contiguous().data_ptr(), int(xx.dtype == torch.float32), 1, cx, t, h, w,
+                                              a.data_ptr(), cin.cin_p, t + 2, 2, None, None, _lib.stream_ptr()), "pf_pack_latent")
+        self._halo(cin, a, True)
+        y = torch.empty(t, h, w, cin.cout_p, device=dev, dtype=torch.bfloat16)
+        self._conv(cin, a, t, h, w, out=y)                                        # conv_in, D:152
+        del a
+        for i in range(n_blocks):
+            sp, tp = cfg.enc_spatial_down_sample[i], cfg.enc_temporal_down_sample[i]
+            xb = None
+            for j in range(cfg.enc_layers_per_block[i]):
+                last = j == cfg.enc_layers_per_block[i] - 1
+                y = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", y, True, halo_out=last and (sp or tp))
+                if last and (sp or tp):
+                    xb = y                                  # [t+2, h, w, c]: data in frames [2:]
+            if sp:                                          # CausalDownsample2x: 3x3x3, stride (1,2,2), K:532-534
+                cv = self.convs[f"encoder.down_blocks.{i}.downsamplers.0.conv"]
+                self._halo(cv, xb, True)
+                off = 2 if tp else 0
+                h, w = h // 2, w // 2
+                y = torch.empty(t + off, h, w, cv.cout_p, device=dev, dtype=torch.bfloat16)
+                self._conv(cv, xb, t, h, w, out=y, out_t_offset=off)
+                xb = y
+                y = y[off:]
+            if tp:                                          # CausalTemporalDownsample2x: 3x3x3, stride (2,1,1), K:536-538
+                cv = self.convs[f"encoder.down_blocks.{i}.temporal_downsamplers.0.conv"]
+                self._halo(cv, xb, True)
+                t_out = (t - 1) // 2 + 1                    # padded length t+2, kernel 3, stride 2
+                y = torch.empty(t_out, h, w, cv.cout_p, device=dev, dtype=torch.bfloat16)
+                self._conv(cv, xb[: 2 * (t_out - 1) + 3], t_out, h, w, out=y)
+                t = t_out
+        y = self._resnet("encoder.mid_block.resnets.0", y, True)
+        y = self._mid_attention(y, "encoder")
+        y = self._resnet("encoder.mid_block.resnets.1", y, True)
+        co, qc = self.convs["encoder.conv_out"], self.convs["quant_conv"]
+        a = torch.empty(t + 2, h, w, y.shape[-1], device=dev, dtype=torch.bfloat16)
+        self._gn("encoder.conv_norm_out", y, a, 2, True)
+        self._halo(co, a, True)
+        m = torch.zeros(t, h, w, qc.cin_p, device=dev, dtype=torch.bfloat16)      # padded channels must read as zero
+        self._conv(co, a, t, h, w, out=m, store_channels=co.cout)                 # conv_out -> 2*latent channels
+        out = torch.empty(t, h, w, qc.cout, device=dev, dtype=torch.float32)
+        self._conv(qc, m, t, h, w, out=out, store_channels=qc.cout, out_f32=True)  # quant_conv (1x1x1), V:301
+        self._reset_caches()
+        return out
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = True, is_init_image: bool = True, temporal_chunk: bool = False,
+               window_size: int = 16, tile_sample_min_size: int = 256):
+        """CausalVideoVAE.encode (V:274-308), un-tiled and un-chunked (the pipeline encodes ONE image, P:911; chunking is
+        exact in the reference, so a clip is encoded whole): returns `.latent_dist` with mean / logvar / std / sample()."""
+        _lib.require_device()
+        assert self.has_encoder, "this B200CausalVAE was built from a state-dict without encoder.* weights"
+        assert is_init_image, "clips start with the image frame"
+        x = x.to(self.device)
+        saved_cp, self._cp = self._cp, None
+        try:
+            moments = torch.stack([self._encode_sample(x[i:i + 1]) for i in range(x.shape[0])], 0)   # [B, T', h, w, 2C]
+        finally:
+            self._cp = saved_cp
+        dist = DiagonalGaussian(moments.permute(0, 4, 1, 2, 3).to(self.dtype))
+        if not return_dict:
+            return (dist,)
+        return EncoderOutput(dist)
 
     def _decode_sample_cp(self, z: torch.Tensor) -> torch.Tensor:
         """Context-parallel decode of one sample: my frame range as ONE chunk with halos from the previous rank; the

@@ -118,3 +118,64 @@ def test_default_width_vae_matches_oracle():
     assert err < TOL_MAX_ABS and mse < TOL_MSE
     assert err <= 1.5 * e2 + 1e-2 and mse <= 2.0 * m2 + 1e-5, "must be comparable to the reference's own bf16 error"
     assert ref.abs().mean().item() > 0.05
+
+
+def test_conv3d_strided_kernel():
+    """The encoder's down-samplers: 3x3x3 causal conv with stride (1,2,2) / (2,1,1) (strided TMA box) vs F.conv3d."""
+    from pyramid_flow_b200.vae import B200CausalVAE, _Conv
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    holder = B200CausalVAE.__new__(B200CausalVAE)
+    cases = [((1, 2, 2), 64, 128, 3, 6, 10), ((1, 2, 2), 128, 128, 2, 17, 33), ((1, 2, 2), 64, 128, 2, 96, 160),
+             ((2, 1, 1), 64, 64, 3, 9, 20), ((2, 1, 1), 128, 256, 1, 12, 150), ((2, 1, 1), 64, 128, 5, 48, 80)]
+    for (stride, ci, co, t_out, h_out, w_out) in cases:
+        st, sh, sw = stride
+        wt = (torch.randn(co, ci, 3, 3, 3) * (ci * 27) ** -0.5).bfloat16().float()
+        bias = torch.randn(co) * 0.1
+        cv = _Conv({"c.conv.weight": wt, "c.conv.bias": bias}, "c", dev)
+        cv.stride = stride
+        t_in = (t_out - 1) * st + 1                       # real frames; 2 causal zero frames go in front
+        x = torch.randn(t_in, h_out * sh, w_out * sw, ci, device=dev).bfloat16()
+        xin = torch.zeros(t_in + 2, h_out * sh, w_out * sw, ci, device=dev, dtype=torch.bfloat16)
+        xin[2:] = x
+        xr = F.pad(x.permute(3, 0, 1, 2)[None].float(), (1, 1, 1, 1, 2, 0))
+        ref = F.conv3d(xr, wt.to(dev), bias.to(dev), stride=stride)[0].permute(1, 2, 3, 0)
+        assert tuple(ref.shape) == (t_out, h_out, w_out, co), (ref.shape, stride)
+        out = torch.zeros(t_out, h_out, w_out, co, device=dev, dtype=torch.bfloat16)
+        B200CausalVAE._conv(holder, cv, xin, t_out, h_out, w_out, out=out)
+        torch.cuda.synchronize()
+        err = (out.float() - ref).abs().max().item()
+        assert err < 3e-2, (stride, ci, co, t_out, h_out, w_out, err)
+
+
+def test_vae_encoder_matches_reference_golden(golden_dir):
+    """encode() (encoder + quant_conv moments, P:911's image latent) vs the unmodified reference's moments and the oracle."""
+    from oracle import vae_oracle as VO
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    g = torch.load(golden_dir / "vae_encoder_small.pt", weights_only=False)
+    ecfg = VO.VaeEncoderConfig(**g["cfg"])
+    params = VO.synthetic_vae_params(ecfg, seed=g["param_seed"])
+    dev = torch.device("cuda:0")
+    vae = B200CausalVAE(VaeConfigB200(enc_block_out_channels=ecfg.block_out_channels,
+                                      enc_layers_per_block=ecfg.layers_per_block), params, device=dev)
+    assert vae.has_encoder and not vae.has_decoder
+    pd = {k: v.to(dev) for k, v in params.items()}
+    for name in ("image", "clip"):
+        x = g[name].bfloat16()                             # the pipeline feeds the image in the VAE dtype (bf16), P:911
+        dist = vae.encode(x.to(dev)).latent_dist
+        torch.cuda.synchronize()
+        ours = dist.parameters.float().cpu()
+        with torch.no_grad():
+            ref = VO.encode_moments(params, ecfg, x.float())
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ref_bf16 = VO.encode_moments(pd, ecfg, x.to(dev)).float().cpu()
+        err = (ours - ref).abs().max().item()
+        err_gold = (ours - g["moments_" + name]).abs().max().item()    # reference ran on the un-rounded fp32 input
+        err_pol = (ref_bf16 - ref).abs().max().item()
+        print(f"vae encode {name}: max_abs vs oracle {err:.3e}, vs reference golden {err_gold:.3e}, reference bf16 policy {err_pol:.3e}, |ref| mean {ref.abs().mean():.3f}")
+        assert ours.shape == ref.shape
+        assert err < 5e-2 and err_gold < 6e-2 and err <= max(1.5 * err_pol, 1e-2)
+        assert torch.equal(dist.mean.float().cpu(), ours[:, :16]) and dist.std.shape == dist.mean.shape
+    gen = torch.Generator().manual_seed(0)
+    z = dist.sample(gen)
+    assert z.shape == dist.mean.shape and z.device.type == "cuda" and z.dtype == torch.bfloat16
