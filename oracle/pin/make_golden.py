@@ -235,6 +235,76 @@ def make_sampler():
                                                                 video_guidance_scale=5.0)}, GOLD / "sampler_small.pt")
 
 
+def make_sampler_i2v():
+    """The UNMODIFIED reference generate_i2v() loop (P:791-1003) on CPU fp32: tiny reference DiT, fake text encoder, a fake
+    VAE whose encode() returns a fixed image latent, injected block noise."""
+    from PIL import Image
+    from pyramid_dit import PyramidDiTForVideoGeneration
+    from pyramid_dit.flux_modules import PyramidFluxTransformer
+    from diffusion_schedulers import PyramidFlowMatchEulerDiscreteScheduler
+    cfg = FO.FluxConfig(**SMALL_CFG)
+    params = FO.synthetic_flux_params(cfg, seed=0)
+    dit = PyramidFluxTransformer(**SMALL_CFG).eval()
+    dit.load_state_dict(params, strict=True)
+    g = torch.Generator().manual_seed(17)
+    enc = torch.randn(2, 24, SMALL_CFG["joint_attention_dim"], generator=g) * 0.5      # [negative ; positive]
+    mask = torch.ones(2, 24, dtype=torch.long)
+    mask[0, 13:] = 0
+    pooled = torch.randn(2, SMALL_CFG["pooled_projection_dim"], generator=g)
+    image_latent_raw = torch.randn(1, 16, 1, 16, 16, generator=g)     # what vae.encode(...).latent_dist.sample() returns
+
+    class FakeText:
+        def __init__(self):
+            self.calls = 0
+
+        def __call__(self, prompt, device):
+            i = 1 if self.calls == 0 else 0
+            self.calls += 1
+            return enc[i:i + 1], mask[i:i + 1], pooled[i:i + 1]
+
+    class FakeDist:
+        def sample(self):
+            return image_latent_raw
+
+    class FakeVae:
+        device, dtype = torch.device("cpu"), torch.float32
+        seen = []
+
+        def encode(self, x):
+            FakeVae.seen.append(x)
+            return type("O", (), {"latent_dist": FakeDist()})()
+
+    pipe = object.__new__(PyramidDiTForVideoGeneration)
+    pipe.dit = dit
+    pipe.text_encoder = FakeText()
+    pipe.vae = FakeVae()
+    pipe.scheduler = PyramidFlowMatchEulerDiscreteScheduler(shift=1.0, stages=3, stage_range=[0, 1 / 3, 2 / 3, 1], gamma=1 / 3)
+    pipe.stages = [1, 2, 4]
+    pipe.frame_per_unit = 1
+    pipe.model_name = "pyramid_flux"
+    pipe.sequential_offload_enabled = False
+    pipe.downsample = 8
+    pipe.vae_shift_factor, pipe.vae_scale_factor = -0.04, 1 / 1.8726
+    ng = torch.Generator().manual_seed(12)
+    noises = []
+
+    def fake_block_noise(bs, ch, temp, height, width):
+        n = torch.randn(bs, ch, temp, height, width, generator=ng)
+        noises.append(n)
+        return n
+
+    pipe.sample_block_noise = fake_block_noise
+    img = Image.fromarray((torch.rand(128, 128, 3, generator=g) * 255).byte().numpy())
+    gen = torch.Generator().manual_seed(5)
+    args = dict(temp=4, num_inference_steps=[2, 1, 2], guidance_scale=7.0, video_guidance_scale=4.0)
+    with torch.no_grad():
+        lat = pipe.generate_i2v(prompt="x", input_image=img, generator=gen, output_type="latent", save_memory=True, **args)
+    print("sampler_i2v:", lat.shape, float(lat.abs().mean()), "block-noise draws", len(noises), "image tensor", FakeVae.seen[0].shape)
+    torch.save({"cfg": SMALL_CFG, "param_seed": 0, "enc": enc, "mask": mask, "pooled": pooled, "noises": noises,
+                "latent_seed": 5, "latents": lat, "image_tensor": FakeVae.seen[0], "image_latent_raw": image_latent_raw,
+                "args": dict(height=128, width=128, **args)}, GOLD / "sampler_i2v_small.pt")
+
+
 MMDIT_SMALL = dict(num_layers=3, num_attention_heads=4, attention_head_dim=64, in_channels=16, patch_size=2,
                    joint_attention_dim=128, pooled_projection_dim=64, pos_embed_max_size=24, sample_size=32)
 

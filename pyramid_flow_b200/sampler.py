@@ -1,6 +1,6 @@
 """Host-side mirror of the reference sampler loop, so the hot path can be driven end-to-end without the reference tree.
 
-Mirrors `PyramidDiTForVideoGeneration.generate` / `generate_one_unit` / `get_pyramid_latent` / `sample_block_noise` /
+Mirrors `PyramidDiTForVideoGeneration.generate` / `generate_i2v` (P:791-1003) / `generate_one_unit` / `get_pyramid_latent` / `sample_block_noise` /
 `decode_latent` (pyramid_dit/pyramid_dit_for_video_gen_pipeline.py:1006-1219, 706-788, 555-570, 697-703, 1221-1243) from
 the point where text embeddings exist (text encoders are out of scope: SURVEY.md §2 row 14).  In a reference checkout the
 pipeline itself stays the call surface; this mirror is what tests and bench.py drive on the GPU box, and
@@ -116,6 +116,67 @@ class B200PyramidSampler:
             inter.append(latents)
         return inter
 
+    def _past_conditions(self, generated: List[torch.Tensor], unit: int, do_cfg: bool = True) -> List[List[torch.Tensor]]:
+        """Compressed history per stage (P:1159-1182 == P:923-952): the last clean unit at the stage's own resolution, older
+        units at successively coarser stages, everything older than that at the coarsest; oldest first."""
+        n_stage = len(self.stages)
+        clean = self.get_pyramid_latent(torch.cat(generated, dim=2), n_stage - 1)
+        fpu = self.frame_per_unit
+        dup = (lambda x: torch.cat([x] * 2)) if do_cfg else (lambda x: x)
+        past = []
+        for i_s in range(n_stage):
+            stage_input = [dup(clean[i_s][:, :, -fpu:])]
+            cur_stage, ptx = i_s, 1
+            while ptx < unit:
+                cur_stage = max(cur_stage - 1, 0)
+                if cur_stage == 0:
+                    break
+                ptx += 1
+                stage_input.append(dup(clean[cur_stage][:, :, -(ptx * fpu): -((ptx - 1) * fpu)]))
+            if cur_stage == 0 and ptx < unit:
+                stage_input.append(dup(clean[0][:, :, :-(ptx * fpu)]))
+            past.append(list(reversed(stage_input)))
+        return past
+
+    @torch.no_grad()
+    def generate_i2v(self, input_image_tensor: Optional[torch.Tensor], prompt_embeds, prompt_attention_mask,
+                     pooled_prompt_embeds, height: int, width: int, temp: int = 1, num_inference_steps=(10, 10, 10),
+                     guidance_scale: float = 7.0, video_guidance_scale: float = 4.0,
+                     generator: Optional[torch.Generator] = None, output_type: str = "latent", save_memory: bool = True,
+                     image_latent: Optional[torch.Tensor] = None):
+        """P:791-1003 after text encoding and the PIL -> tensor transform: `input_image_tensor` is `[1, 3, 1, H, W]` in
+        [-1, 1] (ToTensor + Normalize(0.5, 0.5), P:907-910).  The image latent is `vae.encode(...).latent_dist.sample()`
+        shifted/scaled with the IMAGE factors (P:911); `image_latent` injects it instead (tests without a VAE).  The first
+        unit is the image itself; every later unit runs with `is_first_frame=False` and ONE step list (P:954-968)."""
+        device, dtype = prompt_embeds.device, prompt_embeds.dtype
+        n_stage = len(self.stages)
+        num_inference_steps = [num_inference_steps] * n_stage if isinstance(num_inference_steps, int) else list(num_inference_steps)
+        c_lat = (self.dit.config.in_channels // 4) if self.model_name == "pyramid_flux" else self.dit.config.in_channels
+        shape = (1, c_lat, int(temp), int(height) // self.downsample, int(width) // self.downsample)
+        latents = torch.randn(shape, generator=generator, dtype=dtype).to(device)      # prepare_latents, P:881-890
+        temp, h, w = latents.shape[-3:]
+        for _ in range(n_stage - 1):                                                 # P:894-899
+            h //= 2
+            w //= 2
+            latents = _resize_frames(latents, (h, w), "bilinear") * 2
+        num_units = temp // self.frame_per_unit                                      # P:903 (the image is unit 0)
+        if image_latent is None:
+            x = input_image_tensor.to(device=self.vae.device, dtype=self.vae.dtype)
+            image_latent = self.vae.encode(x).latent_dist.sample()
+        image_latent = ((image_latent - self.vae_shift_factor) * self.vae_scale_factor).to(device=device, dtype=dtype)
+        generated = [image_latent]
+        fpu = self.frame_per_unit
+        for unit in range(1, num_units):
+            past = self._past_conditions(generated, unit)
+            inter = self.generate_one_unit(latents[:, :, (unit - 1) * fpu: unit * fpu], past, prompt_embeds,
+                                           prompt_attention_mask, pooled_prompt_embeds, num_inference_steps, h, w, fpu,
+                                           device, dtype, False, guidance_scale, video_guidance_scale)
+            generated.append(inter[-1])
+        out = torch.cat(generated, dim=2)
+        if output_type == "latent":
+            return out
+        return self.decode_latent(out, save_memory=save_memory)
+
     @torch.no_grad()
     def generate(self, prompt_embeds, prompt_attention_mask, pooled_prompt_embeds, height: int, width: int, temp: int = 1,
                  num_inference_steps=(20, 20, 20), video_num_inference_steps=(10, 10, 10), guidance_scale: float = 7.0,
@@ -145,24 +206,8 @@ class B200PyramidSampler:
                                                pooled_prompt_embeds, num_inference_steps, h, w, 1, device, dtype, True,
                                                guidance_scale, video_guidance_scale)
             else:
-                past = []
-                clean = self.get_pyramid_latent(torch.cat(generated, dim=2), n_stage - 1)
                 fpu = self.frame_per_unit
-                for i_s in range(n_stage):                         # P:1159-1182: compressed history per stage
-                    last = clean[i_s][:, :, -fpu:]
-                    stage_input = [torch.cat([last] * 2)]
-                    cur_stage, ptx = i_s, 1
-                    while ptx < unit:
-                        cur_stage = max(cur_stage - 1, 0)
-                        if cur_stage == 0:
-                            break
-                        ptx += 1
-                        cond = clean[cur_stage][:, :, -(ptx * fpu): -((ptx - 1) * fpu)]
-                        stage_input.append(torch.cat([cond] * 2))
-                    if cur_stage == 0 and ptx < unit:
-                        cond = clean[0][:, :, :-(ptx * fpu)]
-                        stage_input.append(torch.cat([cond] * 2))
-                    past.append(list(reversed(stage_input)))
+                past = self._past_conditions(generated, unit)
                 sl = slice(1 + (unit - 1) * fpu, 1 + unit * fpu)
                 inter = self.generate_one_unit(latents[:, :, sl], past, prompt_embeds, prompt_attention_mask,
                                                pooled_prompt_embeds, video_num_inference_steps, h, w, fpu, device, dtype,

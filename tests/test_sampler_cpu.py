@@ -48,3 +48,23 @@ def test_block_noise_covariance():
     cov = (blocks.T @ blocks) / blocks.shape[0]
     target = torch.eye(4) * (1 + 1 / 3) - torch.ones(4, 4) / 3
     assert (cov - target).abs().max().item() < 0.03
+
+
+def test_i2v_loop_matches_reference_generate_i2v(golden_dir):
+    """generate_i2v mirror (P:791-1003) against the unmodified reference loop with a fake VAE encode (fixed image latent)."""
+    g = torch.load(golden_dir / "sampler_i2v_small.pt", weights_only=False)
+    cfg = FO.FluxConfig(**g["cfg"])
+    dit = OracleDit(cfg, FO.synthetic_flux_params(cfg, seed=g["param_seed"]))
+    noises = list(g["noises"])
+    sampler = B200PyramidSampler(dit, B200FlowMatchScheduler(), block_noise_fn=lambda *a: noises.pop(0))
+    gen = torch.Generator().manual_seed(g["latent_seed"])
+    with torch.no_grad():
+        lat = sampler.generate_i2v(g["image_tensor"], g["enc"], g["mask"], g["pooled"], generator=gen, output_type="latent",
+                                   image_latent=g["image_latent_raw"], **g["args"])
+    assert lat.shape == g["latents"].shape and not noises
+    err = (lat - g["latents"]).abs().max().item()
+    assert err < 5e-4, err
+    # unit 0 is the normalised image latent itself (P:911)
+    ref0 = (g["image_latent_raw"] - sampler.vae_shift_factor) * sampler.vae_scale_factor
+    assert torch.allclose(lat[:, :, :1], ref0, atol=1e-6)
+    assert sampler.dit_calls == 3 * 5            # 3 generated units x (2 + 1 + 2) steps

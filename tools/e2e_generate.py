@@ -47,6 +47,7 @@ def counting(*a, **k):
 
 
 dit.forward = counting
+dit.use_cuda_graph = True      # every (unit, stage) shape is captured once and replayed for its 10-20 steps
 sampler = B200PyramidSampler(dit, B200FlowMatchScheduler(), vae=vae)
 torch.cuda.synchronize()
 t0 = time.time()
