@@ -198,6 +198,8 @@ class B200FluxTransformer(torch.nn.Module):
         self.use_cuda_graph = False
         self._graphs: "Dict[tuple, dict]" = {}
         self._graph_warm = False
+        self._graph_pool = None
+        self._graph_stream = None
         self.graph_replays = 0          # bookkeeping for bench.py: replays and kernel launches replayed
         self.graph_launches_replayed = 0
 
@@ -405,11 +407,23 @@ class B200FluxTransformer(torch.nn.Module):
             if not self._graph_warm:        # first capture of the process: let every kernel initialise outside capture
                 run()
                 self._graph_warm = True
-            torch.cuda.synchronize()
+            # Manual capture on a side stream (what torch.cuda.graph() does, minus its gc.collect() + empty_cache(), which
+            # cost ~50 ms per capture and made the per-(unit, stage) captures of the sampler a net loss at 384p); all
+            # graphs share one memory pool, so the buffers of an evicted graph are reused by the next capture.
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+                self._graph_stream = torch.cuda.Stream()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
-                out = run()
+            side = self._graph_stream
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph.capture_begin(pool=self._graph_pool)
+                try:
+                    out = run()
+                finally:
+                    graph.capture_end()
+            torch.cuda.current_stream().wait_stream(side)
             ent = dict(graph=graph, static=static, out=out, launches=_lib.launch_count() - n0, plan=plan, mask=mask,
                        ws=dict(self._ws))   # the captured pointers must stay allocated as long as the graph lives
             self._graphs[key] = ent
