@@ -22,6 +22,7 @@ ap.add_argument("--height", type=int, default=768)
 ap.add_argument("--width", type=int, default=1280)
 ap.add_argument("--temp", type=int, default=31)
 ap.add_argument("--no-decode", action="store_true")
+ap.add_argument("--graph", action="store_true", help="capture every (unit, stage) step shape into a CUDA graph (pays ~30 ms per shape; useful on slow hosts)")
 ap.add_argument("--window", type=int, default=4, help="latent frames per VAE chunk (exact; memory knob)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -47,7 +48,7 @@ def counting(*a, **k):
 
 
 dit.forward = counting
-dit.use_cuda_graph = True      # every (unit, stage) shape is captured once and replayed for its 10-20 steps
+dit.use_cuda_graph = args.graph   # each (unit, stage) shape lives for 10-20 steps only: capture pays off on slow hosts
 sampler = B200PyramidSampler(dit, B200FlowMatchScheduler(), vae=vae)
 torch.cuda.synchronize()
 t0 = time.time()
