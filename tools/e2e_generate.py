@@ -1,5 +1,7 @@
-"""End-to-end generate() + decode on one B200 with synthetic text embeddings and random-init weights:
+"""End-to-end generate() + decode on one or N B200s with synthetic text embeddings and random-init weights:
 python tools/e2e_generate.py [--height 768 --width 1280 --temp 31]   (BASELINE configs[2]; --temp 16 --height 384 --width 640 = configs[1])
+torchrun --nproc-per-node N tools/e2e_generate.py ...   : every rank runs the same sampler loop (same seeds); the DiT step is
+sharded CFG x sequence-parallel (sp.py) and the VAE decode is context-parallel (temporal split + halo exchange).
 Reports wall-clock frames/s (excluding text encoding, as SURVEY.md §8d defines) and aggregate DiT token-passes/s."""
 import argparse
 import json
@@ -25,7 +27,14 @@ ap.add_argument("--no-decode", action="store_true")
 ap.add_argument("--graph", action="store_true", help="capture every (unit, stage) step shape into a CUDA graph (pays ~30 ms per shape; useful on slow hosts)")
 ap.add_argument("--window", type=int, default=4, help="latent frames per VAE chunk (exact; memory knob)")
 args = ap.parse_args()
-dev = torch.device("cuda:0")
+import os
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+torch.manual_seed(1234)          # block noise comes from the global CPU RNG: identical on every rank
 cfg, sd = random_flux_state_dict(dict(num_layers=8, num_single_layers=16), dev, seed=0)
 dit = B200FluxTransformer(cfg, sd, device=dev)
 del sd
@@ -47,6 +56,11 @@ def counting(*a, **k):
     return out
 
 
+if world > 1:
+    from pyramid_flow_b200 import sp as SP
+    dit.set_parallel_layout(SP.make_layout())
+    if vae is not None:
+        vae.set_context_parallel(None)
 dit.forward = counting
 dit.use_cuda_graph = args.graph   # each (unit, stage) shape lives for 10-20 steps only: capture pays off on slow hosts
 sampler = B200PyramidSampler(dit, B200FlowMatchScheduler(), vae=vae)
@@ -58,7 +72,7 @@ lat = sampler.generate(enc, mask, pooled, height=args.height, width=args.width, 
 torch.cuda.synchronize()
 t1 = time.time()
 frames = 1 + 8 * (args.temp - 1)
-res = {"config": f"miniFLUX {args.height}x{args.width}, temp={args.temp} ({frames} frames), steps 20/10, guidance 7/5, 1xB200 bf16",
+res = {"config": f"miniFLUX {args.height}x{args.width}, temp={args.temp} ({frames} frames), steps 20/10, guidance 7/5, {world}xB200 bf16",
        "dit_calls": sampler.dit_calls, "dit_seconds": t1 - t0, "dit_token_passes": tokens[0],
        "dit_token_passes_per_s": tokens[0] / (t1 - t0), "latent_finite": bool(torch.isfinite(lat.float()).all())}
 if vae is not None:
@@ -76,4 +90,9 @@ if vae is not None:
     t3 = time.time()
     res.update(decode_seconds=t3 - t2, video_shape=list(u8.shape), frames_per_s_end_to_end=frames / ((t1 - t0) + (t3 - t2)),
                decode_frames_per_s=frames / (t3 - t2), peak_mem_gib=torch.cuda.max_memory_allocated() / 2 ** 30)
-print(json.dumps(res))
+if world > 1:
+    dist.barrier()
+if rank == 0:
+    print(json.dumps(res))
+if world > 1:
+    dist.destroy_process_group()
