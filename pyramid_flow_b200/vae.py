@@ -110,6 +110,8 @@ class B200CausalVAE(torch.nn.Module):
         self.cfg = config
         self.use_tiling = False
         self._cp = None                     # (group, rank, world) when context-parallel decode is on
+        self._cp_ctx = None
+        self.cp_frames_per_round = 4        # latent frames per rank per round (memory knob: ~6 GiB per frame at 768p)
         self.decode_tile_overlap_factor = 0.25
         dev = torch.device(device)
         self._dev = dev
@@ -189,16 +191,23 @@ class B200CausalVAE(torch.nn.Module):
             self._cp = (group, rank, world)
 
     @staticmethod
-    def cp_frame_split(n_frames: int, world: int):
-        """Latent-frame ranges per rank: rank 0 = image frame + share, others = share of the remaining n-1 frames (as even
-        as possible; the reference requires divisibility, X:24-33)."""
-        base, extra = divmod(n_frames - 1, world)
-        bounds, f = [], 0
-        for r in range(world):
-            n = base + (1 if r < extra else 0) + (1 if r == 0 else 0)
-            bounds.append((f, f + n))
-            f += n
-        return bounds
+    def cp_frame_split(n_frames: int, world: int, frames_per_round: int = 4):
+        """Context-parallel schedule: a list of rounds, each a list of per-rank latent-frame ranges [a, b).  Round 0 gives rank 0
+        the image frame plus `frames_per_round` frames and every other rank `frames_per_round` (the reference's split,
+        X:24-33, applied to the first world*c frames); later rounds continue in time order, so a rank never holds more than
+        c (+1) latent frames of activations at once — one round covering the whole clip is the reference's layout, but at
+        768p it needs ~6 GiB per latent frame (15 frames per rank = 147 GiB measured).  Only the last round may be partial."""
+        rounds, f, k = [], 0, 0
+        while f < n_frames:
+            ranges = []
+            for r in range(world):
+                ln = frames_per_round + (1 if (k == 0 and r == 0) else 0)
+                a, b = min(f, n_frames), min(f + ln, n_frames)
+                ranges.append((a, b))
+                f = b
+            rounds.append(ranges)
+            k += 1
+        return rounds
 
     def enable_tiling(self, use_tiling: bool = True):
         self.use_tiling = use_tiling
@@ -234,18 +243,31 @@ class B200CausalVAE(torch.nn.Module):
         if cv.kt == 1:
             return
         if self._cp is not None:
+            # ring of rounds: my halo = the last two (padded) input frames of the rank before me in this round; rank 0 takes
+            # the zero pad in round 0 and afterwards what the LAST rank sent it during the previous round (kept in cv.cache)
             import torch.distributed as dist
             group, rank, world = self._cp
+            ctx = self._cp_ctx
             peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
-            p2p = []
-            if rank + 1 < world:        # my last two (padded) input frames are the next rank's halo
+            p2p, nxt = [], None
+            if ctx["send_next"]:
                 p2p.append(dist.P2POp(dist.isend, buf[-2:], peer(rank + 1), group))
+            if ctx["ring_send"]:
+                p2p.append(dist.P2POp(dist.isend, buf[-2:], peer(0), group))
             if rank > 0:
                 p2p.append(dist.P2POp(dist.irecv, buf[:2], peer(rank - 1), group))
             else:
-                buf[:2].zero_()
+                if ctx["round"] == 0:
+                    buf[:2].zero_()
+                else:
+                    buf[:2].copy_(cv.cache)
+                if ctx["ring_recv"]:
+                    nxt = torch.empty_like(buf[:2])
+                    p2p.append(dist.P2POp(dist.irecv, nxt, peer(world - 1), group))
             for work in (dist.batch_isend_irecv(p2p) if p2p else []):
                 work.wait()
+            if nxt is not None:
+                cv.cache = nxt
             return
         if first or cv.cache is None:
             buf[:2].zero_()
@@ -458,25 +480,42 @@ class B200CausalVAE(torch.nn.Module):
         return EncoderOutput(dist)
 
     def _decode_sample_cp(self, z: torch.Tensor) -> torch.Tensor:
-        """Context-parallel decode of one sample: my frame range as ONE chunk with halos from the previous rank; the
-        decoded frames of all ranks are all-gathered (every rank returns the full clip)."""
+        """Context-parallel decode of one sample (schedule: cp_frame_split): per round every rank decodes its frame range as
+        ONE chunk with the halo of every causal conv passed along the ring; the decoded frames of each round are
+        all-gathered in time order (every rank returns the full clip)."""
         import torch.distributed as dist
         group, rank, world = self._cp
-        bounds = self.cp_frame_split(z.shape[2], world)
-        a, b = bounds[rank]
-        mine = self._decode_chunk(z[:, :, a:b].contiguous(), rank == 0)            # [T_r, H, W, 3] fp32
-        counts = [8 * (e - s) - (7 if r == 0 else 0) for r, (s, e) in enumerate(bounds)]
-        assert mine.shape[0] == counts[rank]
-        pad = torch.zeros(max(counts), *mine.shape[1:], device=mine.device, dtype=mine.dtype)
-        pad[: mine.shape[0]] = mine
-        parts = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(parts, pad, group=group)
-        return torch.cat([p_[:c] for p_, c in zip(parts, counts)], 0)
+        n = z.shape[2]
+        c = max(2, min(self.cp_frames_per_round, -(-(n - 1) // world)))     # short clips: spread the frames over all ranks
+        rounds = self.cp_frame_split(n, world, c)
+        self._reset_caches()
+        outs = []
+        up = 2 ** sum(bool(x) for x in self.cfg.spatial_up_sample)
+        tail_shape = (z.shape[3] * up, z.shape[4] * up, self.cfg.out_channels)
+        for k, ranges in enumerate(rounds):
+            a, b = ranges[rank]
+            more = k + 1 < len(rounds)
+            self._cp_ctx = dict(round=k,
+                                send_next=rank + 1 < world and ranges[rank + 1][1] > ranges[rank + 1][0] and b > a,
+                                ring_send=more and rank == world - 1, ring_recv=more and rank == 0)
+            mine = self._decode_chunk(z[:, :, a:b].contiguous(), k == 0 and rank == 0) if b > a else None
+            counts = [8 * (e - s0) - (7 if (k == 0 and r == 0) else 0) if e > s0 else 0 for r, (s0, e) in enumerate(ranges)]
+            if mine is not None:
+                assert mine.shape[0] == counts[rank] and tuple(mine.shape[1:]) == tail_shape, (mine.shape, counts, rank)
+            pad = torch.zeros(max(counts), *tail_shape, device=self.device, dtype=torch.float32)
+            if mine is not None:
+                pad[: mine.shape[0]] = mine
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad, group=group)
+            outs.extend(p_[:c] for p_, c in zip(parts, counts) if c > 0)
+        self._cp_ctx = None
+        self._reset_caches()
+        return torch.cat(outs, 0)
 
     def _decode_sample(self, z: torch.Tensor, window_size: int) -> torch.Tensor:
         """chunk_decode (V:346-374) for one sample: first chunk window+1 latent frames, then `window` each."""
         if self._cp is not None:
-            if z.shape[2] - 1 >= 2 * self._cp[2]:        # every rank owns >= 2 frames: its halo source is its own data
+            if z.shape[2] - 1 >= 2 * self._cp[2] and self.cp_frames_per_round >= 2:   # full shares own their halo source
                 return self._decode_sample_cp(z)
             saved, self._cp = self._cp, None              # short clip: every rank decodes all of it (replicas)
             try:

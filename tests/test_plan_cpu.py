@@ -71,3 +71,25 @@ def test_plan_schedule_covers_exactly_the_allowed_pairs():
                 if not flag:
                     assert bool(dense[bi, q0:q1, k0:k1].all())
         assert not bool((dense[bi] & ~covered).any())
+
+
+def test_vae_context_parallel_schedule():
+    """cp_frame_split: rounds cover the clip in time order; round 0 / rank 0 holds the image frame; only the last round is
+    partial; every share that has a successor owns >= 2 frames (its halo source is its own data)."""
+    from pyramid_flow_b200.vae import B200CausalVAE as V
+    for n in (5, 9, 12, 17, 31, 64):
+        for world in (2, 4, 8):
+            for c in (2, 4):
+                rounds = V.cp_frame_split(n, world, c)
+                flat = [x for r in rounds for x in r]
+                assert flat[0][0] == 0 and flat[-1][1] == n
+                assert all(flat[i][1] == flat[i + 1][0] for i in range(len(flat) - 1))
+                assert rounds[0][0] == (0, min(n, c + 1))
+                for k, ranges in enumerate(rounds):
+                    assert len(ranges) == world
+                    for r, (a, b) in enumerate(ranges):
+                        full = c + (1 if (k == 0 and r == 0) else 0)
+                        assert b - a <= full
+                        has_successor = (r + 1 < world and ranges[r + 1][1] > ranges[r + 1][0]) or (r == world - 1 and k + 1 < len(rounds))
+                        if has_successor:
+                            assert b - a == full >= 2

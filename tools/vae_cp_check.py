@@ -33,7 +33,7 @@ def timed(fn):
     return out, t.item()
 
 
-cases = [(1 + 2 * world, 24, 40, 2), (int(os.environ.get("PF_CP_T", "17")), 96, 160, 2)]
+cases = [(1 + 2 * world, 24, 40, 2), (2 + 5 * world, 24, 40, 2), (int(os.environ.get("PF_CP_T", "31")), 96, 160, 2)]
 for (T, h, w, win) in cases:
     g = torch.Generator().manual_seed(5)
     z = torch.randn(1, 16, T, h, w, generator=g).bfloat16().to(dev)
@@ -50,7 +50,7 @@ for (T, h, w, win) in cases:
         fr = ref.shape[2]
         print(f"[vae_cp_check] latent {T}x{h}x{w} -> {tuple(ref.shape)}: 1 GPU (chunked, window {win}) {ms1:.1f} ms = "
               f"{fr / ms1 * 1e3:.1f} frames/s | {world} GPUs context-parallel {msn:.1f} ms = {fr / msn * 1e3:.1f} frames/s "
-              f"(x{ms1 / msn:.2f}); split {vae.cp_frame_split(T, world)}; bit-identical per rank {[f[0] for f in flags]} "
+              f"(x{ms1 / msn:.2f}); {len(vae.cp_frame_split(T, world, vae.cp_frames_per_round))} round(s) of {vae.cp_frames_per_round} latent frames per rank, peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; bit-identical per rank {[f[0] for f in flags]} "
               f"max|diff| {max(f[1] for f in flags):.2e}", flush=True)
     assert err < 1e-3, err
 dist.destroy_process_group()
