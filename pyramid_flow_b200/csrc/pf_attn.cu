@@ -9,10 +9,9 @@
 // One CTA = one (batch, head, 128-row q tile); 320 threads; two CTAs are co-resident per SM so that one CTA's softmax
 // (MUFU-bound at head_dim 64) overlaps the other CTA's tensor-core work:
 //   warps 0-7  softmax: thread == (q row == TMEM lane, 64-column half).  The thread's 64 scores are read from TMEM once
-//              and stay in registers for the FMNMX3 max pass and the ex2 pass.  The reference max is two tiles stale: the
-//              two halves publish their partial max of tile j in shared memory and read the partner's for tile j-1 at
-//              the end of iteration j (ordered by the P-ready mbarrier) for use in iteration j+1, so there is no
-//              per-tile pair barrier, no shared-memory round trip on the critical path, and the exps of tile j never
+//              and stay in registers for the FMNMX3 max pass and the ex2 pass.  The reference max is one tile stale: the
+//              two halves publish their partial max of tile j in shared memory and read the partner's for tile j-1
+//              (ordered by the P-ready mbarrier), so there is no per-tile pair barrier and the exps of tile j never
 //              wait for P.V(j-1).  P is written back to TMEM as packed bf16; O is rescaled in TMEM only when the
 //              reference moved by > 2^8 (lazy rescale)
 //   warp 8     MMA issuer (one lane): S = Q.K^T (SS: both operands in smem, K-major), O += P.V (TS: P from TMEM,
@@ -289,22 +288,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t t_o = tmem_base + lane_base + TM_O + half * 32;
     const uint32_t t_p = tmem_base + lane_base + TM_P + half * 32;
     const float c = a.scale_log2;
-    // Reference max of the row (raw score units), identical in both column halves.  It is STALE: tile j is exponentiated
-    // against the max over tiles <= j-2 (tiles 0 and 1: against tile 0's exact max, one paired exchange).  Each half
-    // publishes its partial max of tile j in `xch` before its P-ready arrive; the partner's value for tile j-1 is read at
-    // the END of iteration j (ordered by bar_p_full(j-1), probed at the top of the iteration) and consumed at the top of
-    // iteration j+1, so neither the barrier nor the shared-memory round trip is on the critical path.  The reference only
-    // moves when it grew by more than 2^8 (lazy rescale).  bf16 P and the fp32 accumulators have fp32's exponent range, so
-    // a tile that overshoots the stale reference is exact as long as scores do not jump by > ~2^100 within two tiles
-    // (logits of RMS-normed q/k are bounded far below that).  Exps need only registers; P.V(j-1) is awaited just before P
-    // is stored, and S(j+1) is probed under that store.
-    float m_run = -INFINITY;          // -inf: no finite score seen yet, reference 0
-    float m_mine_prev = -INFINITY;    // this half's partial max of tile j-1 (at the top of iteration j)
-    float m_mine_old = -INFINITY;     // this half's / the partner's partial max of the newest tile known on both sides
-    float m_partner_old = -INFINITY;
+    // Reference max of the row (raw score units), identical in both column halves.  It is STALE by one tile: tile j is
+    // exponentiated against the max over tiles < j (tile 0: exact, one paired exchange), and the max of tile j-1 -- each
+    // half publishes its partial in `xch`, ordered by bar_p_full(j-1) -- only raises the reference for tile j when it
+    // grew by more than 2^8 (lazy rescale).  bf16 P and the fp32 accumulators have fp32's exponent range, so a tile that
+    // overshoots the stale reference is exact as long as scores do not jump by > ~2^100 between neighbouring tiles
+    // (logits of RMS-normed q/k are bounded far below that).  This removes the per-tile pair barrier and the wait on
+    // P.V(j-1) from the softmax critical path: exps need only registers; P.V(j-1) is awaited just before P is stored.
+    float m_run = -INFINITY;        // -inf: no finite score seen yet, reference 0
+    float m_prev_part = -INFINITY;  // this half's partial max of the previous tile
     float l4[4] = {0.f, 0.f, 0.f, 0.f};  // this half's partial row sum (4 chains)
     unsigned long long* tr_me = (lane == 0 && quarter == 0) ? tr_cta : nullptr;
-    bool s_ok = mbar_test(&bar_s_full, 0);
     int entry = sched[1];
 
     for (int j = 0; j < n_kv; ++j) {
@@ -328,11 +322,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         allow0 = bits0;
         allow1 = bits1;
       }
-      // The waits of an iteration (S(j), P-ready of tile j-1, P.V(j-1)) are probed early and consumed late: every
+      // The three waits of an iteration (P-ready of tile j-1, S(j), P.V(j-1)) are probed early and consumed late: every
       // mbarrier / shared-memory round trip queues behind the other CTA's MUFU stream in the MIO queue (~300 cycles),
       // so they are overlapped with each other and with the exps instead of being paid one after the other.
       bool pf_ok = true;
       if (j > 0) pf_ok = mbar_test(&bar_p_full, (j - 1) & 1);
+      const bool s_ok = mbar_test(&bar_s_full, j & 1);
+      float m_partner = -INFINITY;
+      if (j > 0) {
+        if (!pf_ok) mbar_wait(&bar_p_full, (j - 1) & 1);   // every softmax thread finished tile j-1: partials published
+        m_partner = xch[(j - 1) & 1][half ^ 1][row];
+      }
       if (!s_ok) mbar_wait(&bar_s_full, j & 1);
       tc_fence_after();
       trace_stamp<TRACE>(tr_me, half, j, 0);
@@ -354,16 +354,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (m_part == 12345.678f) trace_stamp<TRACE>(tr_me, half, j, 7);
       }
       trace_stamp<TRACE>(tr_me, half, j, 5);
-      float m_tile;   // exact max (both halves) of the newest tile known on both sides: tile 0 at j <= 1, else tile j-2
-      float m_partner0 = -INFINITY;
+      float m_tile;   // exact max (both halves) of the newest tile that is known: tile 0 at j == 0, else tile j-1
       if (j == 0) {
         xch[0][half][row] = m_part;
         pair_bar_sync(quarter);
-        m_partner0 = xch[0][half ^ 1][row];
-        m_tile = fmaxf(m_part, m_partner0);
+        m_tile = fmaxf(m_part, xch[0][half ^ 1][row]);
       } else {
-        m_tile = fmaxf(m_mine_old, m_partner_old);
+        m_tile = fmaxf(m_prev_part, m_partner);
+        xch[j & 1][half][row] = m_part;   // slot (j & 1) was last read by the partner before its P-ready arrive of tile j-1
       }
+      m_prev_part = m_part;
       trace_stamp<TRACE>(tr_me, half, j, 2);
 
       // ---- lazy rescale decision (per row, same in both halves)
@@ -397,18 +397,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       trace_stamp<TRACE>(tr_me, half, j, 3);
 
-      // ---- publish my partial max of tile j, fetch the partner's of tile j-1 (consumed at the top of iteration j+1)
-      if (j == 0) {
-        m_mine_old = m_part;
-        m_partner_old = m_partner0;
-      } else {
-        if (!pf_ok) mbar_wait(&bar_p_full, (j - 1) & 1);   // every softmax thread finished tile j-1: partials published,
-        m_partner_old = xch[(j - 1) & 1][half ^ 1][row];   // and my slot (j & 1) has been read by the partner
-        m_mine_old = m_mine_prev;
-        xch[j & 1][half][row] = m_part;
-      }
-      m_mine_prev = m_part;
-
       // ---- P(j-1) must have been consumed and O(j-1) produced by P.V(j-1) before P is overwritten / O is rescaled
       if (j > 0) {
         if (!pv_ok) mbar_wait(&bar_pv_done, (j - 1) & 1);
@@ -425,7 +413,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
-      s_ok = (j + 1 < n_kv) ? mbar_test(&bar_s_full, (j + 1) & 1) : true;   // S(j+1): probed under the P store
       tmem_st16(t_p, pk0);
       tmem_st16(t_p + 16, pk1);
       tmem_st_wait();
