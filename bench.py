@@ -405,8 +405,8 @@ def run_ours(args):
                      "share_of_step": (attn_avg * n_attn / ms_eager) if ms_eager else None,
                      "algorithmic_flops_per_launch": attn_flops_launch,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
-                     # shape (profiles/r01_attn_v1_6_ncu.txt: 357.3 MB + 104.2 MB) = the algorithmic Q+K+V+O bytes
-                     "traffic": 461.5e6 if lay is None else None, "traffic_unit": "B/launch",
+                     # shape (profiles/r01_attn_v2_ncu.txt: 357.3 MB + 103.9 MB) = the algorithmic Q+K+V+O bytes
+                     "traffic": 461.2e6 if lay is None else None, "traffic_unit": "B/launch",
                      "algorithmic_bytes_per_launch": 4.0 * b * plan.seq * cfg.inner_dim * 2},
     }
     if args.no_cpu:

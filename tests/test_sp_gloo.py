@@ -70,3 +70,66 @@ def test_layout_arithmetic():
         assert b[0][0] == 0 and b[-1][1] == 15488 and all(b[i][1] == b[i + 1][0] for i in range(sp - 1))
     lay = SP.make_layout(8, 5, create_groups=False)
     assert (lay.cfg_ways, lay.sp, lay.cfg_rank, lay.sp_rank) == (2, 4, 1, 1)
+
+
+# ---- VAE context-parallel ring (vae.py): the host-side schedule + halo plumbing with a stand-in for the kernels -------------
+class _FakeConv:
+    kt = 3
+    cache = None
+
+
+def _fake_vae():
+    """B200CausalVAE with the CUDA chunk decoder replaced by a causal 3-tap FIR over time (uses the real `_halo`) followed
+    by the x8 temporal up-sampling with the first-frame rule, so only the schedule / halo / gather logic is exercised."""
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    vae = B200CausalVAE.__new__(B200CausalVAE)
+    torch.nn.Module.__init__(vae)
+    vae.cfg = VaeConfigB200(spatial_up_sample=(False, False, False, False))
+    vae.register_buffer("_anchor", torch.zeros(1))
+    vae._cp, vae._cp_ctx, vae.cp_frames_per_round = None, None, 4
+    vae.convs = {"fir": _FakeConv()}
+
+    def decode_chunk(z, first):
+        x = z[0].permute(1, 2, 3, 0).contiguous().float()[..., :3]          # [T, h, w, 3]
+        buf = torch.zeros(x.shape[0] + 2, *x.shape[1:])
+        buf[2:] = x
+        vae._halo(vae.convs["fir"], buf, first)
+        y = buf[:-2] + 2.0 * buf[1:-1] + 3.0 * buf[2:]                         # causal: frame t sees t-2, t-1, t
+        y = y.repeat_interleave(8, dim=0)
+        return y[7:] if first else y
+
+    vae._decode_chunk = decode_chunk
+    return vae
+
+
+def _cp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for n_frames, c in [(5, 4), (12, 4), (31, 4), (23, 2), (9, 3)]:
+            g = torch.Generator().manual_seed(n_frames)
+            z = torch.randn(1, 16, n_frames, 3, 4, generator=g)
+            vae = _fake_vae()
+            ref = vae._decode_sample(z, 2)                                  # single process, chunked with the feature cache
+            assert ref.shape[0] == 8 * (n_frames - 1) + 1
+            vae.cp_frames_per_round = c
+            vae.set_context_parallel(None)
+            out = vae._decode_sample(z, 2)
+            assert vae._cp is not None and torch.equal(out, ref), (n_frames, c, (out - ref).abs().max())
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_vae_context_parallel_ring_world2_and_3():
+    for world in (2, 3):
+        ctx = mp.get_context("spawn")
+        ret = ctx.Manager().dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_cp_worker, args=(r, world, port, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=120)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert sorted(ret.keys()) == list(range(world))
