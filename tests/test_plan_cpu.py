@@ -1,4 +1,5 @@
 """Host-side logic of the drop-in (no GPU): sequence plan vs the oracle's restatement of merge_input, C-ABI exports."""
+import ctypes as C
 import re
 from pathlib import Path
 
@@ -93,3 +94,42 @@ def test_vae_context_parallel_schedule():
                         has_successor = (r + 1 < world and ranges[r + 1][1] > ranges[r + 1][0]) or (r == world - 1 and k + 1 < len(rounds))
                         if has_successor:
                             assert b - a == full >= 2
+
+
+def test_c_abi_rejects_bad_arguments_with_a_message():
+    """Error behaviour of the C-ABI (int status + pf_last_error): argument validation is host-side and happens
+    before any CUDA call, so it is checkable without a GPU.  Pointers are dummies — they are never dereferenced here."""
+    from pyramid_flow_b200._lib import AttnDesc, ConvDesc, GemmDesc
+    lib = _lib.load()
+    dummy = 0x1000
+
+    def err():
+        return lib.pf_last_error().decode()
+
+    a = AttnDesc()
+    a.q = a.k = a.v = a.out = a.seg = a.time = a.tile_sched = dummy
+    a.batch, a.heads, a.seq, a.head_dim, a.ldo, a.sched_stride = 1, 2, 256, 32, 128, 3
+    assert lib.pf_attn_fwd_masked(C.byref(a), None) < 0 and "head_dim" in err()
+    a.head_dim, a.sched_stride = 64, 1
+    assert lib.pf_attn_fwd_masked(C.byref(a), None) < 0 and "stride" in err()
+    a.sched_stride, a.q_row_begin = 3, 100
+    assert lib.pf_attn_fwd_masked(C.byref(a), None) < 0 and "q_row_begin" in err()
+    assert lib.pf_attn_fwd_masked(None, None) < 0 and "null" in err()
+
+    c = ConvDesc()
+    c.x = c.wgt = c.out = dummy
+    c.b, c.t, c.h, c.w, c.cin, c.cout, c.kt, c.kh, c.kw = 1, 1, 8, 8, 10, 64, 3, 3, 3
+    c.store_channels, c.out_c = 64, 64
+    assert lib.pf_causal_conv3d(C.byref(c), None) < 0 and "cin" in err()
+    c.cin, c.kt = 64, 2
+    assert lib.pf_causal_conv3d(C.byref(c), None) < 0 and "kernel" in err()
+    c.kt, c.stride_h, c.stride_w = 3, 2, 1
+    assert lib.pf_causal_conv3d(C.byref(c), None) < 0 and "stride" in err()
+    c.stride_w, c.store_mode, c.out_c = 2, 1, 16
+    assert lib.pf_causal_conv3d(C.byref(c), None) < 0      # strided convs are plain-store only
+
+    g = GemmDesc()
+    g.a = g.w = g.out = dummy
+    g.batches, g.rows_per_batch, g.row_count, g.n, g.k, g.lda, g.ldo = 1, 128, 128, 64, 64, 64, 64
+    g.epilogue = 17
+    assert lib.pf_gemm_bf16(C.byref(g), None) < 0 and "epilogue" in err()
