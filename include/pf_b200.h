@@ -213,6 +213,9 @@ typedef struct pf_umma_probe {
   uint32_t b_k_step_bytes; /* descriptor start-address advance per UMMA_K=16 inside a 64-wide k block */
   uint32_t b_kblock_bytes; /* descriptor start-address advance per 4 UMMA_K steps (one 64-wide k block) */
   int32_t a_from_tmem;     /* 1: A is converted to packed bf16 pairs in TMEM (lane = row, 32-bit column = 2 k) */
+  int32_t a_rows;          /* rows of a staged in shared memory (0 = 128); the MMA reads rows [a_row_offset, +128) */
+  int32_t a_row_offset;    /* start-address advance of the A descriptor in 128-byte rows (inside the swizzle atom) */
+  int32_t a_base_offset;   /* value of the descriptor's base-offset field, bits [49,52) */
 } pf_umma_probe;
 PF_API int pf_debug_umma(const pf_umma_probe* p, void* stream);
 

@@ -75,7 +75,7 @@ class UmmaProbe(C.Structure):
         ("n", C.c_int32), ("k", C.c_int32),
         ("b_rows", C.c_int32), ("b_cols", C.c_int32), ("b_box_rows", C.c_int32), ("b_mn_major", C.c_int32),
         ("b_lbo", C.c_uint32), ("b_sbo", C.c_uint32), ("b_k_step_bytes", C.c_uint32), ("b_kblock_bytes", C.c_uint32),
-        ("a_from_tmem", C.c_int32),
+        ("a_from_tmem", C.c_int32), ("a_rows", C.c_int32), ("a_row_offset", C.c_int32), ("a_base_offset", C.c_int32),
     ]
 
 

@@ -23,6 +23,7 @@ struct ConvArgs {
   int b, t, h, w, cin;
   int cout;            // padded N actually computed (multiple of BN)
   int taps, kt, kh, kw;
+  int kw_baseoff;      // kw-reuse kernel: set the A descriptor's base-offset field to the row offset (debug switch)
   int st, sh, sw;      // conv stride (t, h, w): 1, or 2 for the encoder's down-samplers; (b, t, h, w) are OUTPUT dims
   int th, tw, tiles_h, tiles_w;
   int n_tiles;
@@ -486,6 +487,210 @@ static int launch_conv2(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const 
 }
 
 template <int BN>
+struct Conv2wCfg {
+  // kw-tap reuse: ONE haloed input row of 128 + 2 voxels (x 64 channels) per (kt, kh, channel chunk) feeds the three kw
+  // taps -- the A descriptor of tap kw starts kw rows (kw * 128 B) into the tile -- so the input patch crosses L2 -> smem
+  // 9x instead of 27x (ncu on the 128->128 full-resolution conv: tensor pipe 46 %, operand traffic bound).
+  static constexpr int A_ROWS = CBM + 2;
+  static constexpr int A_TX = A_ROWS * CBK * 2;                   // bytes the TMA delivers
+  static constexpr int A_BYTES = (A_TX + 1023) / 1024 * 1024;     // padded: the weight tiles stay 1024-aligned
+  static constexpr int B_BYTES = (BN / 2) * CBK * 2;              // one tap, this CTA's half of the filters
+  static constexpr int STAGE_BYTES = A_BYTES + 3 * B_BYTES;
+  static constexpr int STAGES = (226 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv3d2w_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const ConvArgs g) {
+  using Cfg = Conv2wCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 256);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    tmem_alloc2(&tmem_base_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int cchunks = g.cin / CBK;
+  const int num_grp = g.kt * g.kh * cchunks;   // (dt, dh, channel chunk) groups, three kw taps each
+  const int sp_tiles = g.tiles_h * g.tiles_w;
+  const int sp_pairs = (sp_tiles + 1) / 2;
+  const long long total_tiles = static_cast<long long>(g.b) * g.t * sp_pairs * g.n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  // decode: n tile fastest, then patch pair, frame, batch; this CTA owns patch 2*pair + rank (may fall off the end)
+  auto decode = [&](long long tile, int& nt, int& tt, int& bb, int& h0, int& w0) {
+    nt = static_cast<int>(tile % g.n_tiles);
+    long long r = tile / g.n_tiles;
+    const int sp = static_cast<int>(r % sp_pairs) * 2 + static_cast<int>(rank);
+    r /= sp_pairs;
+    tt = static_cast<int>(r % g.t);
+    bb = static_cast<int>(r / g.t);
+    if (sp < sp_tiles) {
+      h0 = (sp / g.tiles_w) * g.th;
+      w0 = (sp % g.tiles_w) * g.tw;
+    } else {
+      h0 = g.h + g.th;   // entirely outside: TMA zero-fills, the epilogue stores nothing
+      w0 = 0;
+    }
+  };
+
+  if (warp == 0 && elect_one()) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const int ph = g.kh >> 1, pw = g.kw >> 1;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      int nt, tt, bb, h0, w0;
+      decode(tile, nt, tt, bb, h0, w0);
+      for (int grp = 0; grp < num_grp; ++grp) {
+        const int dtdh = grp / cchunks;
+        const int cc = grp - dtdh * cchunks;
+        const int dt = dtdh / g.kh, dh = dtdh - dt * g.kh;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (Cfg::A_TX + 3 * Cfg::B_BYTES));
+        else mbar_arrive_remote(&full_bar[stage], 0);
+        tma_load_5d_2cta(sa, &tm_x, &full_bar[stage], cc * CBK, w0 - pw, h0 + dh - ph, tt + dt, bb);   // 130 voxels
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int kb = (dtdh * 3 + kw) * cchunks + cc;        // K block of tap (dt, dh, kw), channel chunk cc
+          tma_load_2d_2cta(sa + Cfg::A_BYTES + kw * Cfg::B_BYTES, &tm_w, &full_bar[stage], kb * CBK,
+                           nt * BN + static_cast<int>(rank) * (BN / 2));
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && leader && elect_one()) {
+    constexpr uint32_t idesc = make_idesc_bf16(2 * CBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int grp = 0; grp < num_grp; ++grp) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          // rows [kw, kw + 128) of the haloed tile: start address advanced by kw 128-byte rows inside the 1024-byte swizzle
+          // atom, descriptor base-offset field [49,52) = (start >> 7) & 7 = kw (pinned by tools/gpu_check.py probe_rowoff)
+          const uint64_t da = make_smem_desc_kmajor_sw128(sa + kw * 128) | (static_cast<uint64_t>(g.kw_baseoff ? kw : 0) << 49);
+          const uint64_t db = make_smem_desc_kmajor_sw128(sa + Cfg::A_BYTES + kw * Cfg::B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < CBK / 16; ++kk)
+            umma_ss_2cta(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (grp | kw | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit_2cta(&empty_bar[stage]);
+        if (grp == num_grp - 1) umma_commit_2cta(&tmem_full_bar[acc]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int rrow = q * 32 + lane;
+    const int lh = rrow / g.tw, lw = rrow - lh * g.tw;
+    for (long long tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      int nt, tt, bb, h0, w0;
+      decode(tile, nt, tt, bb, h0, w0);
+      const int hh = h0 + lh, ww = w0 + lw;
+      const bool valid = hh < g.h && ww < g.w;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      conv_epilogue_tile<BN>(g, taddr, bb, tt, hh, ww, valid, nt * BN);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty_bar[acc]);
+      else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_conv2w(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
+  using Cfg = Conv2wCfg<BN>;
+  auto kern = conv3d2w_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv2 smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const int sp_pairs = (g.tiles_h * g.tiles_w + 1) / 2;
+  const long long total = static_cast<long long>(g.b) * g.t * sp_pairs * g.n_tiles;
+  int sms = num_sms();
+  if (sms <= 0) sms = 148;
+  long long clusters = sms / 2;
+  if (total < clusters) clusters = total;
+  kern<<<static_cast<int>(2 * clusters), CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_x, tm_w, g);
+  return check_launch("pf_causal_conv3d(2cta, kw reuse)");
+}
+
+template <int BN>
 static int launch_conv(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   auto kern = conv3d_tc_kernel<BN>;
@@ -555,6 +760,13 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   if (env_2cta == 1 && bn >= 128) two_cta = true;
   // input geometry: (t-1)*st + kt frames (the kt-1 causal frames physically first), h*sh x w*sw voxels (symmetric pad 1 is
   // the TMA's out-of-bounds zero fill).  A strided conv loads every sh-th / sw-th voxel of a (th*sh) x (tw*sw) box.
+  // kw-tap reuse (conv3d2w): full 128-voxel rows, 3x3x3, unit stride.  Off unless PF_CONV_KWREUSE=1 (round-1: written and
+  // compiled, descriptor row-offset semantics still to be pinned on hardware).
+  const char* env_kw = getenv("PF_CONV_KWREUSE");
+  const bool kwr = two_cta && env_kw && atoi(env_kw) == 1 && g.th == 1 && g.tw == 128 && d->kt == 3 && d->kh == 3 &&
+                   st == 1 && sh == 1;
+  const char* env_bo = getenv("PF_CONV_KW_BASEOFF");
+  g.kw_baseoff = env_bo ? atoi(env_bo) : 1;
   const int tin = (d->t - 1) * st + d->kt;
   const int hin = d->h * sh, win = d->w * sw;
   CUtensorMap tm_x, tm_w;
@@ -563,7 +775,7 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
                               static_cast<uint64_t>(tin), static_cast<uint64_t>(d->b)};
     const uint64_t s0 = static_cast<uint64_t>(d->cin) * 2;
     const uint64_t strides[4] = {s0, s0 * win, s0 * win * hin, s0 * win * hin * tin};
-    const uint32_t box[5] = {CBK, static_cast<uint32_t>(g.tw * sw), static_cast<uint32_t>(g.th * sh), 1, 1};
+    const uint32_t box[5] = {CBK, static_cast<uint32_t>(kwr ? g.tw + 2 : g.tw * sw), static_cast<uint32_t>(g.th * sh), 1, 1};
     const uint32_t estr[5] = {1, static_cast<uint32_t>(sw), static_cast<uint32_t>(sh), 1, 1};
     int rc = encode_tensor_map(&tm_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d->x, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B, estr);
@@ -577,6 +789,10 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
     int rc = encode_tensor_map(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->wgt, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  }
+  if (kwr) {
+    if (bn == 256) return launch_conv2w<256>(tm_x, tm_w, g, stream);
+    return launch_conv2w<128>(tm_x, tm_w, g, stream);
   }
   if (two_cta) {
     if (bn == 256) return launch_conv2<256>(tm_x, tm_w, g, stream);

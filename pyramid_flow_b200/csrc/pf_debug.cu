@@ -16,6 +16,7 @@ struct ProbeArgs {
   int b_mn_major;
   uint32_t b_lbo, b_sbo, b_k_step_bytes, b_kblock_bytes;
   int a_from_tmem;
+  int a_rows, a_row_offset, a_base_offset;   // A tile of a_rows (>= 128) rows in smem, MMA reads rows [off, off+128)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -29,7 +30,8 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int a_bytes = 128 * p.k * 2;  // [k/64] boxes of 128 x 64
+  const int a_box_bytes = (p.a_rows * 128 + 1023) & ~1023;   // one 64-wide k block: a_rows x 128 B, padded to the swizzle atom
+  const int a_bytes = a_box_bytes * (p.k / 64);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + a_bytes;
   const int box_bytes = p.b_box_rows * 128;
@@ -52,10 +54,10 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
   if (tid == 0) {
     uint32_t bytes = p.b_row_blocks * p.b_col_blocks * box_bytes;
-    if (!p.a_from_tmem) bytes += a_bytes;
+    if (!p.a_from_tmem) bytes += p.a_rows * 128 * (p.k / 64);
     mbar_arrive_expect_tx(&load_bar, bytes);
     if (!p.a_from_tmem) {
-      for (int kb = 0; kb < p.k / 64; ++kb) tma_load_2d(smem_a + kb * 16384, &tm_a, &load_bar, kb * 64, 0);
+      for (int kb = 0; kb < p.k / 64; ++kb) tma_load_2d(smem_a + kb * a_box_bytes, &tm_a, &load_bar, kb * 64, 0);
     }
     int idx = 0;
     for (int cb = 0; cb < p.b_col_blocks; ++cb)
@@ -89,7 +91,10 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (p.a_from_tmem) {
         umma_ts(tmem_d, tmem_a + j * 8, db, idesc, j != 0);
       } else {
-        const uint64_t da = make_smem_desc_kmajor_sw128(sa + (j / 4) * 16384 + (j % 4) * 32);
+        // row offset: the start address moves by whole 128-byte rows inside the 1024-byte swizzle atom; the descriptor's
+        // base-offset field [49,52) carries (start >> 7) & 7 (hypothesis under test when a_row_offset != 0)
+        const uint64_t da = make_smem_desc_kmajor_sw128(sa + (j / 4) * a_box_bytes + p.a_row_offset * 128 + (j % 4) * 32) |
+                            (static_cast<uint64_t>(p.a_base_offset & 7) << 49);
         umma_ss(tmem_d, da, db, idesc, j != 0);
       }
     }
@@ -135,14 +140,20 @@ extern "C" int pf_debug_umma(const pf_umma_probe* p, void* stream_) {
   a.b_k_step_bytes = p->b_k_step_bytes;
   a.b_kblock_bytes = p->b_kblock_bytes;
   a.a_from_tmem = p->a_from_tmem;
-  const int smem = 128 * p->k * 2 + p->b_rows * p->b_cols * 2 + 2048;
+  a.a_rows = p->a_rows > 0 ? p->a_rows : 128;
+  a.a_row_offset = p->a_row_offset;
+  a.a_base_offset = p->a_base_offset;
+  PF_REQUIRE(a.a_rows >= 128 && a.a_rows <= 256 && a.a_row_offset >= 0 && a.a_row_offset + 128 <= a.a_rows,
+             "pf_debug_umma: bad a_rows / a_row_offset");
+  PF_REQUIRE(!(a.a_from_tmem && a.a_rows != 128), "pf_debug_umma: row offsets need A in shared memory");
+  const int smem = ((a.a_rows * 128 + 1023) & ~1023) * (p->k / 64) + p->b_rows * p->b_cols * 2 + 2048;
   PF_REQUIRE(smem <= 220 * 1024, "pf_debug_umma: operands do not fit in shared memory");
 
   CUtensorMap tm_a, tm_b;
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(p->k), 128};
+    const uint64_t dims[2] = {static_cast<uint64_t>(p->k), static_cast<uint64_t>(a.a_rows)};
     const uint64_t strides[1] = {static_cast<uint64_t>(p->k) * 2};
-    const uint32_t box[2] = {64, 128};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(a.a_rows)};
     int rc = encode_tensor_map(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->a, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;

@@ -157,7 +157,8 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
 
 
 def debug_umma(a: torch.Tensor, b: torch.Tensor, n: int, k: int, *, b_box_rows: int, b_mn_major: int, b_lbo: int,
-               b_sbo: int, b_k_step_bytes: int, b_kblock_bytes: int, a_from_tmem: int) -> torch.Tensor:
+               b_sbo: int, b_k_step_bytes: int, b_kblock_bytes: int, a_from_tmem: int, a_row_offset: int = 0,
+               a_base_offset: int = 0) -> torch.Tensor:
     d = torch.zeros(128, n, dtype=torch.float32, device=a.device)
     p = UmmaProbe()
     p.a, p.b, p.d = a.data_ptr(), b.data_ptr(), d.data_ptr()
@@ -165,6 +166,7 @@ def debug_umma(a: torch.Tensor, b: torch.Tensor, n: int, k: int, *, b_box_rows: 
     p.b_rows, p.b_cols = b.shape
     p.b_box_rows, p.b_mn_major = b_box_rows, b_mn_major
     p.b_lbo, p.b_sbo, p.b_k_step_bytes, p.b_kblock_bytes = b_lbo, b_sbo, b_k_step_bytes, b_kblock_bytes
+    p.a_rows, p.a_row_offset, p.a_base_offset = a.shape[0], a_row_offset, a_base_offset
     p.a_from_tmem = a_from_tmem
     _lib.check(_lib.load().pf_debug_umma(C.byref(p), _lib.stream_ptr()), "pf_debug_umma")
     return d

@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-GROUPS = ["probe", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "gemm_qkv_perf", "attn_perf", "attn_trace", "vae_perf"]
+GROUPS = ["probe", "probe_rowoff", "conv_kwreuse", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "gemm_qkv_perf", "attn_perf", "attn_trace", "vae_perf"]
 
 
 def _rel_err(a, b):
@@ -59,6 +59,64 @@ def group_probe():
             ref = a.float() @ b.float()
             run(f"mnmajor n={n} k={k}", a, b, ref, n=n, k=k, b_box_rows=k, b_mn_major=1, b_lbo=k * 128, b_sbo=1024,
                 b_k_step_bytes=2048, b_kblock_bytes=8192, a_from_tmem=0)
+
+
+def group_probe_rowoff():
+    """A descriptor advanced by whole rows inside the 128B-swizzle atom (the conv's kw-tap reuse of one haloed patch):
+    which value of the base-offset field makes D = A[off:off+128] . B^T ?"""
+    import torch
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    n = 128
+    for k in (64, 128):
+        a = torch.randn(136, k, device=dev).bfloat16()
+        bt = torch.randn(n, k, device=dev).bfloat16()
+        for off in (0, 1, 2, 5, 8):
+            ref = a[off:off + 128].float() @ bt.float().t()
+            for bo in sorted({0, off & 7}):
+                try:
+                    d = ops.debug_umma(a, bt, n=n, k=k, b_box_rows=n, b_mn_major=0, b_lbo=16, b_sbo=1024, b_k_step_bytes=32,
+                                       b_kblock_bytes=n * 128, a_from_tmem=0, a_row_offset=off, a_base_offset=bo)
+                    torch.cuda.synchronize()
+                    err = _rel_err(d, ref)
+                    print(f"[probe_rowoff] k={k} row offset {off}, base_offset field {bo}: rel_err={err:.3e} {'OK' if err < 2e-2 else 'MISMATCH'}", flush=True)
+                except Exception as e:  # noqa: BLE001
+                    print(f"[probe_rowoff] k={k} off={off} bo={bo}: EXC {e}", flush=True)
+
+
+def group_conv_kwreuse():
+    """kw-tap reuse conv kernel (PF_CONV_KWREUSE=1) vs the default 2-CTA kernel and F.conv3d: correctness + time."""
+    import torch
+    import torch.nn.functional as F
+    from pyramid_flow_b200.vae import B200CausalVAE, _Conv
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    holder = B200CausalVAE.__new__(B200CausalVAE)
+    for (ci, co, t, h, w, check) in [(64, 128, 2, 96, 160, True), (128, 256, 2, 40, 300, True), (128, 128, 2, 768, 1280, False),
+                                     (256, 256, 2, 384, 640, False)]:
+        wt = (torch.randn(co, ci, 3, 3, 3) * (ci * 27) ** -0.5).bfloat16().float()
+        bias = torch.randn(co) * 0.1
+        cv = _Conv({"c.conv.weight": wt, "c.conv.bias": bias}, "c", dev)
+        x = torch.randn(t, h, w, ci, device=dev).bfloat16()
+        xin = torch.zeros(t + 2, h, w, ci, device=dev, dtype=torch.bfloat16)
+        xin[2:] = x
+        ref = None
+        if check:
+            xr = F.pad(x.permute(3, 0, 1, 2)[None].float(), (1, 1, 1, 1, 2, 0))
+            ref = F.conv3d(xr, wt.to(dev), bias.to(dev))[0].permute(1, 2, 3, 0)
+        fl = 2.0 * 27 * ci * co * t * h * w / 1e9
+        for (kwr, bo) in [("0", "1"), ("1", "1"), ("1", "0")]:
+            os.environ["PF_CONV_KWREUSE"], os.environ["PF_CONV_KW_BASEOFF"] = kwr, bo
+            out = torch.zeros(t, h, w, co, device=dev, dtype=torch.bfloat16)
+            try:
+                ms = _time_cuda(lambda: B200CausalVAE._conv(holder, cv, xin, t, h, w, out=out), iters=5, warm=2)
+                err = (out.float() - ref).abs().max().item() if ref is not None else float("nan")
+                print(f"[conv_kwreuse] {ci}->{co} on {t}x{h}x{w}: kwreuse={kwr} base_offset={bo}: {ms:.3f} ms = {fl/ms:.0f} TF/s, max_abs_err {err:.3e}", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"[conv_kwreuse] {ci}->{co} kwreuse={kwr} bo={bo}: EXC {e}", flush=True)
+    os.environ.pop("PF_CONV_KWREUSE", None)
+    os.environ.pop("PF_CONV_KW_BASEOFF", None)
 
 
 def group_probe_ts():
