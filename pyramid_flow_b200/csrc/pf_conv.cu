@@ -615,7 +615,8 @@ conv3d2w_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           // rows [kw, kw + 128) of the haloed tile: start address advanced by kw 128-byte rows inside the 1024-byte swizzle
-          // atom, descriptor base-offset field [49,52) = (start >> 7) & 7 = kw (pinned by tools/gpu_check.py probe_rowoff)
+          // atom.  The swizzle is applied on absolute smem address bits, so the advanced descriptor reads exactly what
+          // the TMA wrote; the base-offset field [49,52) must stay 0 (pinned on hardware: tools/gpu_check.py probe_rowoff)
           const uint64_t da = make_smem_desc_kmajor_sw128(sa + kw * 128) | (static_cast<uint64_t>(g.kw_baseoff ? kw : 0) << 49);
           const uint64_t db = make_smem_desc_kmajor_sw128(sa + Cfg::A_BYTES + kw * Cfg::B_BYTES);
 #pragma unroll
@@ -760,13 +761,13 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   if (env_2cta == 1 && bn >= 128) two_cta = true;
   // input geometry: (t-1)*st + kt frames (the kt-1 causal frames physically first), h*sh x w*sw voxels (symmetric pad 1 is
   // the TMA's out-of-bounds zero fill).  A strided conv loads every sh-th / sw-th voxel of a (th*sh) x (tw*sw) box.
-  // kw-tap reuse (conv3d2w): full 128-voxel rows, 3x3x3, unit stride.  Off unless PF_CONV_KWREUSE=1 (round-1: written and
-  // compiled, descriptor row-offset semantics still to be pinned on hardware).
+  // kw-tap reuse (conv3d2w): full 128-voxel rows, 3x3x3, unit stride; PF_CONV_KWREUSE=0 falls back to one box per tap.
+  // Measured on B200: 128->128 on 2x768x1280 1.65 -> 1.01 ms (1057 -> 1724 TFLOP/s), 256->256 on 2x384x640 1765 -> 1888.
   const char* env_kw = getenv("PF_CONV_KWREUSE");
-  const bool kwr = two_cta && env_kw && atoi(env_kw) == 1 && g.th == 1 && g.tw == 128 && d->kt == 3 && d->kh == 3 &&
+  const bool kwr = two_cta && !(env_kw && atoi(env_kw) == 0) && g.th == 1 && g.tw == 128 && d->kt == 3 && d->kh == 3 &&
                    st == 1 && sh == 1;
-  const char* env_bo = getenv("PF_CONV_KW_BASEOFF");
-  g.kw_baseoff = env_bo ? atoi(env_bo) : 1;
+  const char* env_bo = getenv("PF_CONV_KW_BASEOFF");   // debug: the probe showed the base-offset field must stay 0
+  g.kw_baseoff = env_bo ? atoi(env_bo) : 0;
   const int tin = (d->t - 1) * st + d->kt;
   const int hin = d->h * sh, win = d->w * sw;
   CUtensorMap tm_x, tm_w;

@@ -1,6 +1,3 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-python bench.py 2>&1 | tail -1 > gpurun_out/bench_r1_final.json
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_r1_final.json').read()); print(d['ms_per_step'], d['value'], d['clocks'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['gpu_launches'], d['e2e']['ms_per_step'], d['cpu_baseline'])"
-python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 > gpurun_out/bench_r1_ref.json; head -c 600 gpurun_out/bench_r1_ref.json
+python tools/gpu_check.py vae_perf 2>&1 | grep "^\["
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv3d2w -s 1 -c 1 -f -o gpurun_out/r01_conv_kw python tools/prof_one.py conv 2 > gpurun_out/ncu_conv_kw.log 2>&1; tail -2 gpurun_out/ncu_conv_kw.log
