@@ -206,16 +206,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
       const int bb = static_cast<int>(r / g.t);
       const int h0 = (sp / g.tiles_w) * g.th, w0 = (sp % g.tiles_w) * g.tw;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / cchunks;
-        const int cc = kb - tap * cchunks;
-        const int dt = tap / (g.kh * g.kw);
-        const int rem = tap - dt * g.kh * g.kw;
-        const int dh = rem / g.kw, dw = rem - dh * g.kw;
+        // K order (dt, dh, channel chunk, dw): the same accumulation order as the kw-reuse kernel, so which kernel a call
+        // is dispatched to (it depends on the number of tiles, i.e. on the temporal chunking) never changes the bits
+        const int grp = kb / g.kw;
+        const int dw = kb - grp * g.kw;
+        const int dtdh = grp / cchunks;
+        const int cc = grp - dtdh * cchunks;
+        const int dt = dtdh / g.kh, dh = dtdh - dt * g.kh;
+        const int wk = (dtdh * g.kw + dw) * cchunks + cc;     // K block of tap (dt, dh, dw), chunk cc in the weight matrix
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         tma_load_5d(sa, &tm_x, &full_bar[stage], cc * CBK, w0 * g.sw + dw - pw, h0 * g.sh + dh - ph, tt * g.st + dt, bb);
-        tma_load_2d(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], kb * CBK, nt * BN);
+        tma_load_2d(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], wk * CBK, nt * BN);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -383,17 +386,20 @@ conv3d2_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       int nt, tt, bb, h0, w0;
       decode(tile, nt, tt, bb, h0, w0);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int tap = kb / cchunks;
-        const int cc = kb - tap * cchunks;
-        const int dt = tap / (g.kh * g.kw);
-        const int rem = tap - dt * g.kh * g.kw;
-        const int dh = rem / g.kw, dw = rem - dh * g.kw;
+        // K order (dt, dh, channel chunk, dw): the same accumulation order as the kw-reuse kernel, so which kernel a call
+        // is dispatched to (it depends on the number of tiles, i.e. on the temporal chunking) never changes the bits
+        const int grp = kb / g.kw;
+        const int dw = kb - grp * g.kw;
+        const int dtdh = grp / cchunks;
+        const int cc = grp - dtdh * cchunks;
+        const int dt = dtdh / g.kh, dh = dtdh - dt * g.kh;
+        const int wk = (dtdh * g.kw + dw) * cchunks + cc;     // K block of tap (dt, dh, dw), chunk cc in the weight matrix
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
         else mbar_arrive_remote(&full_bar[stage], 0);
         tma_load_5d_2cta(sa, &tm_x, &full_bar[stage], cc * CBK, w0 * g.sw + dw - pw, h0 * g.sh + dh - ph, tt * g.st + dt, bb);
-        tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], kb * CBK, nt * BN + static_cast<int>(rank) * (BN / 2));
+        tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, &full_bar[stage], wk * CBK, nt * BN + static_cast<int>(rank) * (BN / 2));
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
