@@ -17,7 +17,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Sequence, Tuple
+from typing import Dict, Tuple
 
 import torch
 import torch.nn.functional as F

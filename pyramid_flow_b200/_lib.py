@@ -6,7 +6,6 @@ There is no fallback: if the library is missing or the device is not sm_100, cal
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent

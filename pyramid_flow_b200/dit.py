@@ -25,15 +25,14 @@ Data layout in HBM (B = CFG batch, S = text + all clip tokens, D = heads*64):
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
 
 from . import _lib, ops
-from ._lib import (PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_QKV_GELU, PF_EPI_QKV_ROPE, PF_EPI_STORE_BF16,
-                   PF_EPI_STORE_F32)
+from ._lib import PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_QKV_ROPE, PF_EPI_STORE_F32
 
 
 @dataclass

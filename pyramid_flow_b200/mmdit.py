@@ -13,7 +13,7 @@ Reuses the miniFLUX kernels unchanged — 24 double blocks at D=1536 / 24 heads 
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
