@@ -21,6 +21,7 @@ SYMBOLS = [
     "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent",
     "pf_debug_umma",
     "pf_debug_attn_trace",
+    "pf_debug_attn_cta_trace",
 ]
 
 PF_EPI_STORE_BF16, PF_EPI_GELU_BF16, PF_EPI_STORE_F32, PF_EPI_GATE_RESID, PF_EPI_QKV_ROPE, PF_EPI_QKV_GELU = range(6)
@@ -111,6 +112,7 @@ def load() -> C.CDLL:
     lib.pf_cfg_euler_step.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.pf_debug_umma.argtypes = [C.POINTER(UmmaProbe), C.c_void_p]
     lib.pf_debug_attn_trace.argtypes = [C.c_void_p]
+    lib.pf_debug_attn_cta_trace.argtypes = [C.c_void_p, C.c_int64]
     lib.pf_causal_conv3d.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
     lib.pf_groupnorm_stats.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_void_p]

@@ -56,6 +56,10 @@ struct AttnArgs {
 constexpr int ATT_TRACE_ITERS = 48;
 constexpr int ATT_TRACE_SLOTS = 8;
 __device__ unsigned long long* g_attn_trace = nullptr;
+// Per-CTA records of the trace variant: [linear CTA index][4] = (clock64 at entry, clock64 at exit, kv tiles, SM id) --
+// to separate the fixed per-CTA cost from the per-tile cost (regression over all CTAs in tools/gpu_check.py).
+__device__ unsigned long long* g_attn_cta_trace = nullptr;
+__device__ long long g_attn_cta_trace_cap = 0;
 template <int TRACE>
 __device__ __forceinline__ void trace_stamp(unsigned long long* tr, int role, int j, int slot) {
   if (TRACE) {
@@ -159,6 +163,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int bh = b * a.heads + h;
   const int* sched = a.sched + (static_cast<size_t>(b) * a.q_tiles + qt) * a.sched_stride;
   const int n_kv = sched[0];
+  unsigned long long cta_t0 = 0;
+  if (TRACE) cta_t0 = clock64();
   unsigned long long* tr_cta = nullptr;   // trace buffer if this CTA is the traced one
   if (TRACE) {
     if (b == 0 && h == 0 && qt == a.q_tiles / 2) tr_cta = g_attn_trace;
@@ -454,6 +460,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
+  if (TRACE) {
+    if (threadIdx.x == 0 && g_attn_cta_trace != nullptr) {
+      const long long idx = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      if (idx < g_attn_cta_trace_cap) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* r = g_attn_cta_trace + idx * 4;
+        r[0] = cta_t0;
+        r[1] = clock64();
+        r[2] = static_cast<unsigned long long>(n_kv);
+        r[3] = smid;
+      }
+    }
+  }
 }
 
 }  // namespace pf
@@ -569,6 +589,19 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   else
     attn_fwd_kernel<0, 0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked");
+}
+
+// Debug: per-CTA records (4 uint64 each, `capacity` CTAs) filled by the variant-2 (trace) kernel; NULL disables.
+extern "C" int pf_debug_attn_cta_trace(void* device_buf, int64_t capacity) {
+  unsigned long long* p = static_cast<unsigned long long*>(device_buf);
+  long long cap = device_buf ? capacity : 0;
+  cudaError_t e = cudaMemcpyToSymbol(pf::g_attn_cta_trace, &p, sizeof(p));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(pf::g_attn_cta_trace_cap, &cap, sizeof(cap));
+  if (e != cudaSuccess) {
+    pf::set_error("pf_debug_attn_cta_trace: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
 }
 
 // Debug: device buffer of 3 * 48 * 8 uint64 clock stamps filled by the variant-2 (trace) kernel; NULL disables.

@@ -15,7 +15,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
-GROUPS = ["probe", "probe_rowoff", "conv_kwreuse", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "gemm_qkv_perf", "attn_perf", "attn_trace", "vae_perf"]
+GROUPS = ["probe", "probe_rowoff", "conv_kwreuse", "probe_ts", "gemm", "epilogue", "elementwise", "attn", "gemm_perf", "gemm_epi_perf", "gemm_qkv_perf", "attn_perf", "attn_trace", "attn_cta_trace", "vae_perf"]
 
 
 def _rel_err(a, b):
@@ -503,6 +503,53 @@ def group_attn_trace():
     print(f"[attn_trace] MMA: arrive(half0)->p_full seen {float((d[2,:,2]-d[0,:,6]).mean()):.0f}, p_full->PV issued "
           f"{ph(2,2,4):.0f}, ld_done(half0)->s_free seen {float((d[2,:,0]-d[0,:,1]).mean()):.0f}, "
           f"QK issue {ph(2,0,1):.0f}, QK(j+1) issued->S_full(j+1) seen {float((d[0,1:,0]-d[2,:-1,1]).mean()):.0f}")
+
+
+def group_attn_cta_trace():
+    """Per-CTA cost model of the attention kernel at the bench shape: cycles(CTA) ~ F + c * kv_tiles (least squares over all
+    7260 CTAs of one launch of the trace variant), plus how busy each SM's two CTA slots were."""
+    import torch
+    from pyramid_flow_b200 import ops, _lib
+    dev = "cuda"
+    B, H = 2, 30
+    lens = [128 + 240] + [240] * 27 + [960, 3840, 3840]
+    tim = torch.cat([torch.full((n,), float(i)) for i, n in enumerate(lens)]).int()[None].repeat(B, 1)
+    S = tim.shape[1]
+    seg = torch.ones(B, S, dtype=torch.int32)
+    q = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    k = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    v = torch.randn(B, H, S, 64, device=dev).bfloat16()
+    out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
+    sched, pairs = ops.attn_build_schedule(seg, tim)
+    sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
+    n_cta = ((S + 127) // 128) * H * B
+    buf = torch.zeros(n_cta * 4, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.pf_debug_attn_cta_trace(buf.data_ptr(), n_cta), "cta trace")
+    for _ in range(2):
+        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, 2)
+    torch.cuda.synchronize()
+    _lib.check(lib.pf_debug_attn_cta_trace(None, 0), "cta trace")
+    r = buf.cpu().view(n_cta, 4).double()
+    dur, nkv, sm = r[:, 1] - r[:, 0], r[:, 2], r[:, 3].long()
+    A = torch.stack([torch.ones_like(nkv), nkv], 1)
+    sol = torch.linalg.lstsq(A, dur[:, None]).solution.flatten()
+    print(f"[attn_cta_trace] {n_cta} CTAs, kv tiles per CTA mean {nkv.mean():.1f}: cycles(CTA) = {sol[0]:.0f} + {sol[1]:.0f} * kv_tiles "
+          f"(fixed part = {100 * sol[0] * n_cta / dur.sum():.1f} % of all CTA cycles)")
+    for lo, hi in [(1, 8), (8, 32), (32, 64), (64, 200)]:
+        m = (nkv >= lo) & (nkv < hi)
+        if m.any():
+            print(f"[attn_cta_trace] CTAs with {lo:3d} <= kv tiles < {hi:3d}: {int(m.sum()):5d}, cycles per kv tile {float((dur[m] / nkv[m]).mean()):.0f}")
+    t_begin, t_end = r[:, 0].min(), r[:, 1].max()
+    busy = torch.zeros(int(sm.max()) + 1, dtype=torch.float64).index_add_(0, sm, dur)
+    # clock64 is per SM: spans are only comparable within one SM
+    span = torch.zeros_like(busy)
+    for s_id in range(busy.numel()):
+        m = sm == s_id
+        if m.any():
+            span[s_id] = r[m, 1].max() - r[m, 0].min()
+    print(f"[attn_cta_trace] per SM: CTA-slot occupancy (sum of CTA cycles / (2 * span)) mean {float((busy / (2 * span)).mean()):.3f} "
+          f"min {float((busy / (2 * span)).min()):.3f}; span mean {float(span.mean()):.0f} cycles, max {float(span.max()):.0f}")
 
 
 def group_vae_perf():
