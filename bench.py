@@ -303,6 +303,8 @@ def run_ours(args):
     use_graph = world == 1 and not args.no_graph
     model.use_cuda_graph = use_graph
 
+    host_ms = {}
+
     def timed(fn, steps, events=False):
         barrier()
         if events:
@@ -310,8 +312,10 @@ def run_ours(args):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.launch_count() + model.graph_launches_replayed
         s.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_ms["last"] = (time.perf_counter() - h0) * 1e3 / steps     # host time to ENQUEUE a step (no sync inside)
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -332,6 +336,7 @@ def run_ours(args):
     time.sleep(0.25)
     t0 = time.time()
     ms_step, launches = timed(step_resident, args.steps, events=not use_graph)
+    host_enqueue_ms = host_ms["last"]
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
     ms_eager = ms_step
@@ -392,6 +397,8 @@ def run_ours(args):
                                    "launch durations from the host-launched steps timed right after"
                                    if use_graph else "host-launched (one C-ABI call per kernel)"),
                    "ms_per_step_host_launched": ms_eager,
+                   # host wall time to enqueue one step of the timed region (rank 0): close to ms_per_step = launch-bound
+                   "host_enqueue_ms_per_step": host_enqueue_ms,
                    "breakdown_ms_one_step": {k_: round(v_, 3) for k_, v_ in sorted(breakdown.items())}},
         "clocks": clocks,
         "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
