@@ -29,6 +29,10 @@ PF_API const char* pf_last_error(void);
 PF_API int pf_version(void);
 /* 0 if the current CUDA device is sm_100 (B200) and the driver exposes cuTensorMapEncodeTiled; <0 otherwise. */
 PF_API int pf_device_check(void);
+/* Loads every kernel instantiation of the library on the CURRENT device and sets its dynamic shared-memory attribute, so
+ * that no later launch initialises anything host-side (required before capturing launches into a CUDA graph; also what makes
+ * a second GPU driven from the same process work).  Idempotent, thread-safe. */
+PF_API int pf_warmup(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 PF_API int64_t pf_launch_count(void);
 
@@ -77,6 +81,8 @@ typedef struct pf_gemm_desc {
   float norm_eps;
   int32_t heads, head_dim, seq_len;
   int32_t n_split; /* QKV_GELU: first n_split (=3*H*hd) columns are q|k|v */
+  int32_t kernel_variant; /* 0 = auto (measured policy); 1 = force 1-CTA tiles; 2 = force 2-CTA (cta_group::2) tiles.
+                           * Same bits either way (same K order); exists so tests can pin each kernel. */
 } pf_gemm_desc;
 
 PF_API int pf_gemm_bf16(const pf_gemm_desc* desc, void* stream);
@@ -175,6 +181,9 @@ typedef struct pf_conv3d_desc {
   int32_t stride_t, stride_h, stride_w; /* 0/1 = unit stride; 2 = the encoder's down-samplers (C:66-67: CausalDownsample2x
                                          * stride (1,2,2) R:322, CausalTemporalDownsample2x stride (2,1,1) R:486).  b,t,h,w
                                          * stay OUTPUT dims; x is [B, (t-1)*stride_t + kt, h*stride_h, w*stride_w, cin]. */
+  int32_t kernel_variant; /* 0 = auto; 1 = 1-CTA tiles (conv3d); 2 = 2-CTA pairs, one TMA box per tap (conv3d2);
+                           * 3 = 2-CTA pairs with kw-tap reuse (conv3d2w: needs 128-voxel rows, 3x3x3, unit stride).
+                           * Every kernel accumulates in the same K order: the choice never changes the bits. */
 } pf_conv3d_desc;
 PF_API int pf_causal_conv3d(const pf_conv3d_desc* desc, void* stream);
 

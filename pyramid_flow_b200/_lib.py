@@ -13,7 +13,7 @@ LIB_PATH = _HERE / "lib" / "libpf_b200.so"
 
 # every symbol include/pf_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
-    "pf_last_error", "pf_version", "pf_device_check", "pf_launch_count",
+    "pf_last_error", "pf_version", "pf_device_check", "pf_warmup", "pf_launch_count",
     "pf_gemm_bf16",
     "pf_attn_build_schedule", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
         ("rope", C.c_void_p), ("q_norm_w", C.c_void_p), ("k_norm_w", C.c_void_p),
         ("norm_eps", C.c_float),
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("seq_len", C.c_int32),
-        ("n_split", C.c_int32),
+        ("n_split", C.c_int32), ("kernel_variant", C.c_int32),
     ]
 
 
@@ -65,7 +65,7 @@ class ConvDesc(C.Structure):
         ("out_t_total", C.c_int32), ("out_t_offset", C.c_int32), ("out_c", C.c_int32),
         ("store_channels", C.c_int32),
         ("residual", C.c_void_p), ("res_t_total", C.c_int32), ("res_t_offset", C.c_int32),
-        ("stride_t", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32),
+        ("stride_t", C.c_int32), ("stride_h", C.c_int32), ("stride_w", C.c_int32), ("kernel_variant", C.c_int32),
     ]
 
 
@@ -80,6 +80,7 @@ class UmmaProbe(C.Structure):
 
 
 _lib = None
+_warm_devices = set()
 
 
 def load() -> C.CDLL:
@@ -134,6 +135,11 @@ def require_device() -> None:
     """Fail loudly unless the CUDA extension is usable on this machine (no CPU fallback exists)."""
     lib = load()
     check(lib.pf_device_check(), "pf_device_check")
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _warm_devices:
+        check(lib.pf_warmup(), "pf_warmup")
+        _warm_devices.add(dev)
 
 
 def stream_ptr() -> int:

@@ -74,6 +74,34 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
   return 0;
 }
 
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
+  struct Entry { const void* k; unsigned long long devmask; };
+  static std::mutex mu;
+  static Entry table[128];
+  static int n_entries = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("%s: no CUDA device", what);
+    return -2;
+  }
+  const unsigned long long bit = 1ull << (dev & 63);
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* e = nullptr;
+  for (int i = 0; i < n_entries; ++i)
+    if (table[i].k == kernel) { e = &table[i]; break; }
+  if (e != nullptr && (e->devmask & bit)) return 0;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cudaFuncSetAttribute(%s, dynamic smem %d): %s", what, bytes, cudaGetErrorString(err));
+    return -2;
+  }
+  if (e == nullptr && n_entries < 128) { e = &table[n_entries++]; e->k = kernel; e->devmask = 0; }
+  if (e != nullptr) e->devmask |= bit;
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -86,9 +114,20 @@ int num_sms() {
   return n;
 }
 
+int warmup_gemm();
+int warmup_conv();
+int warmup_attn();
+
 }  // namespace pf
 
 extern "C" {
+
+int pf_warmup(void) {
+  int rc = pf::warmup_gemm();
+  if (!rc) rc = pf::warmup_conv();
+  if (!rc) rc = pf::warmup_attn();
+  return rc;
+}
 
 const char* pf_last_error(void) { return pf::g_err; }
 int pf_version(void) { return 100; }

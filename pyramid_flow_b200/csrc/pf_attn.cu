@@ -476,6 +476,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
+int warmup_attn() {
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,0>");
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<1, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<1,0>");
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 1>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,1>");
+  return rc;
+}
+
 }  // namespace pf
 
 extern "C" int pf_attn_build_schedule(const int32_t* seg, const int32_t* time, int32_t batch, int32_t seq,
@@ -567,19 +574,7 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   a.sched = d->tile_sched;
   a.sched_stride = d->sched_stride;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("pf_attn_fwd_masked: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  if (int rc = warmup_attn()) return rc;
   // q tile index = q_tiles - 1 - blockIdx.x: a shorter grid.x drops the leading (lowest) q tiles
   dim3 grid(q_tiles - d->q_row_begin / ATT_BM, d->heads, d->batch);
   if (d->variant & 2)

@@ -473,15 +473,7 @@ template <int BN>
 static int launch_conv2(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
   using Cfg = Conv2Cfg<BN>;
   auto kern = conv3d2_tc_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv2 smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "conv2")) return rc;
   const int sp_pairs = (g.tiles_h * g.tiles_w + 1) / 2;
   const long long total = static_cast<long long>(g.b) * g.t * sp_pairs * g.n_tiles;
   int sms = num_sms();
@@ -678,15 +670,7 @@ template <int BN>
 static int launch_conv2w(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
   using Cfg = Conv2wCfg<BN>;
   auto kern = conv3d2w_tc_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv2 smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "conv2")) return rc;
   const int sp_pairs = (g.tiles_h * g.tiles_w + 1) / 2;
   const long long total = static_cast<long long>(g.b) * g.t * sp_pairs * g.n_tiles;
   int sms = num_sms();
@@ -701,21 +685,27 @@ template <int BN>
 static int launch_conv(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const ConvArgs& g, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   auto kern = conv3d_tc_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "conv")) return rc;
   const long long total = static_cast<long long>(g.b) * g.t * g.tiles_h * g.tiles_w * g.n_tiles;
   int grid = num_sms();
   if (grid <= 0) grid = 148;
   if (total < grid) grid = static_cast<int>(total);
   kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_x, tm_w, g);
   return check_launch("pf_causal_conv3d");
+}
+
+int warmup_conv() {
+  int rc = 0;
+#define PF_WARM(KERN, CFG) if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(KERN), CFG::SMEM_BYTES, #KERN)
+  PF_WARM((conv3d_tc_kernel<256>), ConvCfg<256>);
+  PF_WARM((conv3d_tc_kernel<128>), ConvCfg<128>);
+  PF_WARM((conv3d_tc_kernel<64>), ConvCfg<64>);
+  PF_WARM((conv3d2_tc_kernel<256>), Conv2Cfg<256>);
+  PF_WARM((conv3d2_tc_kernel<128>), Conv2Cfg<128>);
+  PF_WARM((conv3d2w_tc_kernel<256>), Conv2wCfg<256>);
+  PF_WARM((conv3d2w_tc_kernel<128>), Conv2wCfg<128>);
+#undef PF_WARM
+  return rc;
 }
 
 }  // namespace pf
@@ -759,21 +749,22 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   g.residual = static_cast<const __nv_bfloat16*>(d->residual);
   g.res_t_total = d->res_t_total; g.res_t_offset = d->res_t_offset;
 
-  // 2-CTA tiles when there is enough work for 74 CTA pairs; PF_CONV_2CTA=0/1 overrides
-  const char* env_s = getenv("PF_CONV_2CTA");
-  const int env_2cta = env_s ? atoi(env_s) : -1;
+  // 2-CTA tiles when there is enough work for 74 CTA pairs; kernel_variant pins a kernel (tests)
+  PF_REQUIRE(d->kernel_variant >= 0 && d->kernel_variant <= 3, "pf_causal_conv3d: bad kernel_variant %d", d->kernel_variant);
   bool two_cta = bn >= 128 && static_cast<long long>(d->b) * d->t * g.tiles_h * g.tiles_w * g.n_tiles >= 296;
-  if (env_2cta == 0) two_cta = false;
-  if (env_2cta == 1 && bn >= 128) two_cta = true;
+  if (d->kernel_variant == 1) two_cta = false;
+  if (d->kernel_variant >= 2) {
+    PF_REQUIRE(bn >= 128, "pf_causal_conv3d: kernel_variant %d (2-CTA) needs cout %% 128 == 0", d->kernel_variant);
+    two_cta = true;
+  }
   // input geometry: (t-1)*st + kt frames (the kt-1 causal frames physically first), h*sh x w*sw voxels (symmetric pad 1 is
   // the TMA's out-of-bounds zero fill).  A strided conv loads every sh-th / sw-th voxel of a (th*sh) x (tw*sw) box.
-  // kw-tap reuse (conv3d2w): full 128-voxel rows, 3x3x3, unit stride; PF_CONV_KWREUSE=0 falls back to one box per tap.
+  // kw-tap reuse (conv3d2w): full 128-voxel rows, 3x3x3, unit stride.
   // Measured on B200: 128->128 on 2x768x1280 1.65 -> 1.01 ms (1057 -> 1724 TFLOP/s), 256->256 on 2x384x640 1765 -> 1888.
-  const char* env_kw = getenv("PF_CONV_KWREUSE");
-  const bool kwr = two_cta && !(env_kw && atoi(env_kw) == 0) && g.th == 1 && g.tw == 128 && d->kt == 3 && d->kh == 3 &&
-                   st == 1 && sh == 1;
-  const char* env_bo = getenv("PF_CONV_KW_BASEOFF");   // debug: the probe showed the base-offset field must stay 0
-  g.kw_baseoff = env_bo ? atoi(env_bo) : 0;
+  const bool kwr_ok = g.th == 1 && g.tw == 128 && d->kt == 3 && d->kh == 3 && st == 1 && sh == 1;
+  if (d->kernel_variant == 3) PF_REQUIRE(kwr_ok, "pf_causal_conv3d: kernel_variant 3 (kw reuse) needs w > 64, a 3x3x3 kernel and unit stride");
+  const bool kwr = two_cta && kwr_ok && d->kernel_variant != 2;
+  g.kw_baseoff = 0;   // the UMMA descriptor's base-offset field must stay 0 (pinned by the probe, tools/gpu_check.py probe_rowoff)
   const int tin = (d->t - 1) * st + d->kt;
   const int hin = d->h * sh, win = d->w * sw;
   CUtensorMap tm_x, tm_w;

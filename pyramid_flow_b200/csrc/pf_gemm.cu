@@ -522,15 +522,7 @@ template <int BN, int EPI>
 static int launch_gemm2(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   auto kern = gemm2_bf16_tc_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm2 smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "gemm2")) return rc;
   const int m2_tiles = (g.row_count + 2 * BM - 1) / (2 * BM);
   const int total = g.batches * m2_tiles * g.n_tiles;
   int sms = num_sms();
@@ -545,15 +537,7 @@ template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_tc_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm smem %d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "gemm")) return rc;
   const int total = g.batches * g.m_tiles * g.n_tiles;
   int grid = num_sms();
   if (grid <= 0) grid = 148;
@@ -580,6 +564,32 @@ static int dispatch_bn(int bn, const CUtensorMap& tm_a, const CUtensorMap& tm_b,
   }
   set_error("unsupported BLOCK_N %d", bn);
   return -1;
+}
+
+template <int EPI>
+static int warm_epi() {
+  int rc = 0;
+#define PF_WARM(KERN, CFG) if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(KERN), CFG::SMEM_BYTES, #KERN)
+  PF_WARM((gemm_bf16_tc_kernel<256, EPI>), GemmCfg<256>);
+  PF_WARM((gemm_bf16_tc_kernel<192, EPI>), GemmCfg<192>);
+  PF_WARM((gemm_bf16_tc_kernel<128, EPI>), GemmCfg<128>);
+  PF_WARM((gemm_bf16_tc_kernel<64, EPI>), GemmCfg<64>);
+  PF_WARM((gemm2_bf16_tc_kernel<256, EPI>), Gemm2Cfg<256>);
+  PF_WARM((gemm2_bf16_tc_kernel<192, EPI>), Gemm2Cfg<192>);
+  PF_WARM((gemm2_bf16_tc_kernel<128, EPI>), Gemm2Cfg<128>);
+#undef PF_WARM
+  return rc;
+}
+// load every instantiation and set its dynamic-smem attribute on the current device (so nothing initialises inside a
+// CUDA-graph capture)
+int warmup_gemm() {
+  int rc = warm_epi<PF_EPI_STORE_BF16>();
+  if (!rc) rc = warm_epi<PF_EPI_GELU_BF16>();
+  if (!rc) rc = warm_epi<PF_EPI_STORE_F32>();
+  if (!rc) rc = warm_epi<PF_EPI_GATE_RESID>();
+  if (!rc) rc = warm_epi<PF_EPI_QKV_ROPE>();
+  if (!rc) rc = warm_epi<PF_EPI_QKV_GELU>();
+  return rc;
 }
 
 }  // namespace pf
@@ -671,9 +681,9 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   g.n_split = d->n_split;
 
   // 2-CTA tiles (256 x BN, cta_group::2) pay off for 256-wide tiles and for short-K 192-wide ones (measured A/B on
-  // B200: +11 % at N=7680/K=1920, -1..3 % at N=1920/K>=7680); PF_GEMM_2CTA=0/1 overrides
-  const char* env_s = getenv("PF_GEMM_2CTA");
-  const int env_2cta = env_s ? atoi(env_s) : -1;
+  // B200: +11 % at N=7680/K=1920, -1..3 % at N=1920/K>=7680); kernel_variant 1/2 pins the 1-CTA / 2-CTA kernel
+  PF_REQUIRE(d->kernel_variant >= 0 && d->kernel_variant <= 2, "pf_gemm_bf16: bad kernel_variant %d", d->kernel_variant);
+  const int env_2cta = d->kernel_variant == 1 ? 0 : d->kernel_variant == 2 ? 1 : -1;
   auto want_2cta = [&](int tile_n) {
     bool t = d->row_count >= 1024 && (tile_n == 256 || (tile_n == 192 && d->k <= 2048));
     if (env_2cta == 0) t = false;

@@ -131,11 +131,13 @@ class B200MMDiT(torch.nn.Module):
 
     # ---- plan: ids / rope / mask schedule / positional table for this (clips, mask) ----------------------------------
     def plan_for(self, clip_shapes, mask: torch.Tensor):
-        fast = (mask.data_ptr(), mask._version, tuple(mask.shape), tuple(tuple(int(x) for x in s) for s in clip_shapes))
-        if self._last_key is not None and self._last_key[0] == fast:
-            return self._last_key[1]
+        # fast path keyed on the mask tensor OBJECT (kept alive: its address cannot be recycled), see dit.py
+        shapes = tuple(tuple(int(x) for x in s) for s in clip_shapes)
+        lk = self._last_key
+        if lk is not None and lk[0] is mask and lk[1] == mask._version and lk[2] == shapes:
+            return lk[3]
         mask_cpu = mask.detach().to("cpu", torch.int64)
-        key = (fast[3], mask_cpu.shape, bytes(mask_cpu.numpy().tobytes()))
+        key = (shapes, mask_cpu.shape, bytes(mask_cpu.numpy().tobytes()))
         hit = self._plans.get(key)
         if hit is None:
             if len(self._plans) >= 16:
@@ -170,7 +172,7 @@ class B200MMDiT(torch.nn.Module):
                            time.to(dev), sched.to(dev), int(pairs.sum()))
             hit = (plan, torch.cat(pos, 0).to(dev).contiguous())
             self._plans[key] = hit
-        self._last_key = (fast, hit)
+        self._last_key = (mask, mask._version, shapes, hit)
         return hit
 
     def _workspace(self, b: int, plan: SeqPlan) -> dict:

@@ -24,7 +24,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
          out_row_begin: Optional[int] = None, out_col_begin: int = 0,
          gate: Optional[torch.Tensor] = None, gate_batch_stride: int = 0,
          q_out=None, k_out=None, v_out=None, rope=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
-         heads: int = 0, head_dim: int = 0, seq_len: int = 0, n_split: int = 0) -> None:
+         heads: int = 0, head_dim: int = 0, seq_len: int = 0, n_split: int = 0, kernel_variant: int = 0) -> None:
     """epilogue(A . W^T + bias); see pf_gemm_bf16 in include/pf_b200.h for the addressing rules."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_cuda and w.is_cuda
     assert a.stride(-1) == 1 and w.is_contiguous()
@@ -58,6 +58,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
     d.rope, d.q_norm_w, d.k_norm_w = _ptr(rope), _ptr(q_norm_w), _ptr(k_norm_w)
     d.norm_eps = norm_eps
     d.heads, d.head_dim, d.seq_len, d.n_split = heads, head_dim, seq_len, n_split
+    d.kernel_variant = kernel_variant
     _lib.check(_lib.load().pf_gemm_bf16(C.byref(d), _lib.stream_ptr()), "pf_gemm_bf16")
 
 

@@ -218,7 +218,7 @@ class B200CausalVAE(torch.nn.Module):
     # ---- kernel wrappers (single sample: tensors are [T, H, W, C]) ---------------------------------------------------
     def _conv(self, cv: _Conv, x: torch.Tensor, t: int, h: int, w: int, *, out: torch.Tensor, out_t_offset: int = 0,
               store_mode: int = 0, residual: Optional[torch.Tensor] = None, res_t_offset: int = 0,
-              store_channels: Optional[int] = None, out_f32: bool = False) -> None:
+              store_channels: Optional[int] = None, out_f32: bool = False, kernel_variant: int = 0) -> None:
         """t, h, w = OUTPUT dims.  x: [(t-1)*st + kt, h*sh, w*sw, cin_p] (halo frames first); out: [out_t_total, H', W', out_c]."""
         st, sh, sw = cv.stride
         assert x.is_contiguous() and out.is_contiguous() and x.shape[-1] == cv.cin_p
@@ -233,6 +233,7 @@ class B200CausalVAE(torch.nn.Module):
         d.out, d.out_f32 = out.data_ptr(), int(out_f32)
         d.out_t_total, d.out_t_offset, d.out_c = out.shape[0], out_t_offset, out.shape[-1]
         d.store_channels = store_channels if store_channels is not None else cv.cout_p
+        d.kernel_variant = kernel_variant
         if residual is not None:
             d.residual, d.res_t_total, d.res_t_offset = residual.data_ptr(), residual.shape[0], res_t_offset
         _lib.check(_lib.load().pf_causal_conv3d(C.byref(d), _lib.stream_ptr()), "pf_causal_conv3d")

@@ -86,7 +86,7 @@ def group_probe_rowoff():
 
 
 def group_conv_kwreuse():
-    """kw-tap reuse conv kernel (PF_CONV_KWREUSE=1) vs the default 2-CTA kernel and F.conv3d: correctness + time."""
+    """kw-tap reuse conv kernel (kernel_variant 3) vs the default 2-CTA kernel and F.conv3d: correctness + time."""
     import torch
     import torch.nn.functional as F
     from pyramid_flow_b200.vae import B200CausalVAE, _Conv
@@ -106,17 +106,37 @@ def group_conv_kwreuse():
             xr = F.pad(x.permute(3, 0, 1, 2)[None].float(), (1, 1, 1, 1, 2, 0))
             ref = F.conv3d(xr, wt.to(dev), bias.to(dev))[0].permute(1, 2, 3, 0)
         fl = 2.0 * 27 * ci * co * t * h * w / 1e9
-        for (kwr, bo) in [("0", "1"), ("1", "1"), ("1", "0")]:
-            os.environ["PF_CONV_KWREUSE"], os.environ["PF_CONV_KW_BASEOFF"] = kwr, bo
+        for kv in (2, 3):     # 2 = 2-CTA one box per tap, 3 = 2-CTA kw-tap reuse (pf_conv3d_desc.kernel_variant)
             out = torch.zeros(t, h, w, co, device=dev, dtype=torch.bfloat16)
             try:
-                ms = _time_cuda(lambda: B200CausalVAE._conv(holder, cv, xin, t, h, w, out=out), iters=5, warm=2)
-                err = (out.float() - ref).abs().max().item() if ref is not None else float("nan")
-                print(f"[conv_kwreuse] {ci}->{co} on {t}x{h}x{w}: kwreuse={kwr} base_offset={bo}: {ms:.3f} ms = {fl/ms:.0f} TF/s, max_abs_err {err:.3e}", flush=True)
+                ms = _time_cuda(lambda: B200CausalVAE._conv(holder, cv, xin, t, h, w, out=out, kernel_variant=kv), iters=5, warm=2)
+                if ref is not None:
+                    err = (out.float() - ref).abs().max().item()
+                else:   # big shapes: sampled output voxels against an fp32 reference of those voxels only
+                    err = _conv_sampled_err(x, wt.to(dev), bias.to(dev), out)
+                print(f"[conv_kwreuse] {ci}->{co} on {t}x{h}x{w}: kernel_variant={kv}: {ms:.3f} ms = {fl/ms:.0f} TF/s, max_abs_err {err:.3e}", flush=True)
             except Exception as e:  # noqa: BLE001
-                print(f"[conv_kwreuse] {ci}->{co} kwreuse={kwr} bo={bo}: EXC {e}", flush=True)
-    os.environ.pop("PF_CONV_KWREUSE", None)
-    os.environ.pop("PF_CONV_KW_BASEOFF", None)
+                print(f"[conv_kwreuse] {ci}->{co} kernel_variant={kv}: EXC {e}", flush=True)
+
+
+def _conv_sampled_err(x, wt, bias, out, n=4096):
+    """max |out - conv(x)| over n random output voxels (x [T,H,W,Cin] channels-last, causal 3x3x3, zero spatial pad)."""
+    import torch
+    t, h, w, ci = x.shape
+    g = torch.Generator(device=x.device).manual_seed(0)
+    ts = torch.randint(0, t, (n,), device=x.device, generator=g)
+    hs = torch.randint(0, h, (n,), device=x.device, generator=g)
+    ws_ = torch.randint(0, w, (n,), device=x.device, generator=g)
+    hs[: n // 8] = torch.where(torch.arange(n // 8, device=x.device) % 2 == 0, 0, h - 1)     # borders
+    ws_[n // 8: n // 4] = torch.where(torch.arange(n // 8, device=x.device) % 2 == 0, 0, w - 1)
+    xp = torch.nn.functional.pad(x.float(), (0, 0, 1, 1, 1, 1, 2, 0))                       # [T+2, H+2, W+2, C]
+    acc = bias.float()[None].repeat(n, 1)
+    for dt in range(3):
+        for dh in range(3):
+            for dw in range(3):
+                patch = xp[ts + dt, hs + dh, ws_ + dw]                                       # [n, Cin]
+                acc += patch @ wt[:, :, dt, dh, dw].float().t()
+    return (out[ts, hs, ws_].float() - acc).abs().max().item()
 
 
 def group_probe_ts():
@@ -335,16 +355,11 @@ def group_gemm_perf():
         w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
         out = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
         res = {}
-        for mode in ("0", "1", "auto"):
-            if mode == "auto":
-                os.environ.pop("PF_GEMM_2CTA", None)
-            else:
-                os.environ["PF_GEMM_2CTA"] = mode
-            res[mode] = _time_cuda(lambda: ops.gemm(x, w, None, 0, rows_per_batch=m, out=out))
+        for mode, kvar in (("0", 1), ("1", 2), ("auto", 0)):
+            res[mode] = _time_cuda(lambda: ops.gemm(x, w, None, 0, rows_per_batch=m, out=out, kernel_variant=kvar))
         ms_ref = _time_cuda(lambda: torch.matmul(x, w.t(), out=out))
         fl = 2.0 * m * n * k / 1e9
         print(f"[gemm_perf] m={m} n={n} k={k}: 1-CTA {res['0']:.3f} ms = {fl/res['0']:.0f} TF/s | 2-CTA {res['1']:.3f} ms = {fl/res['1']:.0f} | auto {res['auto']:.3f} ms = {fl/res['auto']:.0f} | cuBLAS {ms_ref:.3f} ms = {fl/ms_ref:.0f}", flush=True)
-    os.environ.pop("PF_GEMM_2CTA", None)
 
 
 def group_attn():
