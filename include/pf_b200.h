@@ -108,6 +108,8 @@ typedef struct pf_attn_desc {
   int32_t variant;           /* 0 = default; other values select experimental data paths (see pf_attn.cu) */
   int32_t q_row_begin;       /* only q rows >= q_row_begin are computed (multiple of 128; 0 = all).  The last single block
                               * needs the current clip's rows only (history outputs are discarded, reference F:380). */
+  const int32_t* pair_sched; /* device; built by pf_attn_build_pair_schedule from tile_sched, same sched_stride.  When set (and
+                              * variant does not ask for the one-tile kernel) the launch uses the two-q-tiles-per-CTA kernel. */
 } pf_attn_desc;
 
 /* Host helper: from host copies of seg/time ids builds, for each (batch, 128-row q tile), the list of 128-wide kv
@@ -116,6 +118,12 @@ typedef struct pf_attn_desc {
  * (sched_stride) or <0 on error.  `out` may be NULL to query the size: stride = 1 + ceil(seq/128). */
 PF_API int pf_attn_build_schedule(const int32_t* seg_host, const int32_t* time_host, int32_t batch, int32_t seq,
                                   int32_t* out, int64_t* allowed_pairs /* [batch] or NULL */);
+/* Host helper: pairs the q tiles from the end of the sequence (pair p = tiles q_tiles-2-2p and q_tiles-1-2p; the first tile is
+ * alone when q_tiles is odd) and merges their kv lists.  Row layout per (batch, pair): [count, entry...], entry =
+ * (kv_tile << 4) | flags_lo | (flags_hi << 2), flags = bit0: the tile has an allowed pair in this kv tile, bit1: it needs the
+ * element mask (a tile without bit0 is computed fully masked).  `out` holds batch * ceil(q_tiles/2) rows of sched_stride. */
+PF_API int pf_attn_build_pair_schedule(const int32_t* tile_sched_host, int32_t batch, int32_t seq, int32_t sched_stride,
+                                       int32_t* out);
 PF_API int pf_attn_fwd_masked(const pf_attn_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm + AdaLN modulate pre-pass (HBM-bound)

@@ -15,7 +15,7 @@ LIB_PATH = _HERE / "lib" / "libpf_b200.so"
 SYMBOLS = [
     "pf_last_error", "pf_version", "pf_device_check", "pf_warmup", "pf_launch_count",
     "pf_gemm_bf16",
-    "pf_attn_build_schedule", "pf_attn_fwd_masked",
+    "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step",
     "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent",
@@ -51,6 +51,7 @@ class AttnDesc(C.Structure):
         ("scale", C.c_float),
         ("seg", C.c_void_p), ("time", C.c_void_p), ("tile_sched", C.c_void_p),
         ("sched_stride", C.c_int32), ("variant", C.c_int32), ("q_row_begin", C.c_int32),
+        ("pair_sched", C.c_void_p),
     ]
 
 
@@ -101,6 +102,7 @@ def load() -> C.CDLL:
     lib.pf_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.pf_attn_fwd_masked.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     lib.pf_attn_build_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.pf_attn_build_pair_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.pf_ln_modulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
     lib.pf_small_linear.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

@@ -127,10 +127,12 @@ template <int POLY>
 __device__ __forceinline__ void exp32(const uint32_t (&v)[32], uint32_t (&pk)[16], float c, float m_ref, float (&l)[4]) {
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
-    const float p0 = ex2f(fmaf(__uint_as_float(v[2 * i + 0]), c, -m_ref));
-    const float p1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), c, -m_ref));
-    const float p2 = ex2f(fmaf(__uint_as_float(v[2 * i + 2]), c, -m_ref));
-    const float x3 = fmaf(__uint_as_float(v[2 * i + 3]), c, -m_ref);
+    // the reference max is one tile stale: clamp the argument so a tile that overshoots it by > 2^126 saturates instead of
+    // producing inf/NaN (the two-q-tile kernel in pf_attn2.cu has an exact max and needs no clamp)
+    const float p0 = ex2f(fminf(fmaf(__uint_as_float(v[2 * i + 0]), c, -m_ref), 126.f));
+    const float p1 = ex2f(fminf(fmaf(__uint_as_float(v[2 * i + 1]), c, -m_ref), 126.f));
+    const float p2 = ex2f(fminf(fmaf(__uint_as_float(v[2 * i + 2]), c, -m_ref), 126.f));
+    const float x3 = fminf(fmaf(__uint_as_float(v[2 * i + 3]), c, -m_ref), 126.f);
     const float p3 = POLY ? ex2_poly(x3) : ex2f(x3);
     l[0] += p0; l[1] += p1; l[2] += p2; l[3] += p3;
     pk[i] = pack_bf16x2(p0, p1);
@@ -476,8 +478,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
+int warmup_attn2();
+int attn2_launch(const pf_attn_desc* d, int poly, cudaStream_t stream);
+constexpr int ATT2_DEFAULT_POLY = 1;   // exponentials on the FMA pipe: 2 of every 8 (tuned on B200)
+
 int warmup_attn() {
-  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,0>");
+  int rc = warmup_attn2();
+ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,0>");
   if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<1, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<1,0>");
   if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 1>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,1>");
   return rc;
@@ -551,6 +558,15 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
              "pf_attn_fwd_masked: q_row_begin %d must be a multiple of %d inside the sequence", d->q_row_begin, ATT_BM);
   PF_REQUIRE(d->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pf_attn_fwd_masked: out must be 16-byte aligned");
 
+  // variant: 0 = default (two-q-tile kernel when a pair schedule is given, else the one-tile kernel); 0x10 | k = two-q-tile
+  // kernel with k of every 4 exponential pairs on the FMA pipe (k = 0..3); 1 / 2 / 3 = one-tile kernel (polynomial mix / clock
+  // trace / plain)
+  if ((d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr)) {
+    PF_REQUIRE(d->pair_sched != nullptr, "pf_attn_fwd_masked: variant 0x%x needs pair_sched", d->variant);
+    const int poly = (d->variant & 0x10) ? (d->variant & 0xf) : ATT2_DEFAULT_POLY;
+    PF_REQUIRE(poly >= 0 && poly <= 3, "pf_attn_fwd_masked: bad polynomial share %d", poly);
+    return attn2_launch(d, poly, stream);
+  }
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};
   for (int i = 0; i < 3; ++i) {
@@ -577,9 +593,9 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   if (int rc = warmup_attn()) return rc;
   // q tile index = q_tiles - 1 - blockIdx.x: a shorter grid.x drops the leading (lowest) q tiles
   dim3 grid(q_tiles - d->q_row_begin / ATT_BM, d->heads, d->batch);
-  if (d->variant & 2)
+  if (d->variant == 2)
     attn_fwd_kernel<0, 1><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
-  else if (d->variant & 1)
+  else if (d->variant == 1)
     attn_fwd_kernel<1, 0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   else
     attn_fwd_kernel<0, 0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);

@@ -100,6 +100,7 @@ class SeqPlan:
     seg: torch.Tensor         # device int32 [B, S]
     time: torch.Tensor        # device int32 [B, S]
     sched: torch.Tensor       # device int32 [B, q_tiles, stride]
+    sched2: torch.Tensor      # device int32 [B, ceil(q_tiles/2), stride]: pair schedule of the two-q-tile attention kernel
     allowed_pairs: int        # sum over batch of allowed (q, kv) pairs (attention FLOP accounting)
 
 
@@ -115,9 +116,10 @@ def build_seq_plan(clip_shapes: Sequence[Sequence[int]], mask_cpu: torch.Tensor,
     seg[:, :text_len][mask_cpu == 0] = 0
     time = ids[:, 0].to(torch.int32)[None].repeat(b, 1).contiguous()
     sched, pairs = ops.attn_build_schedule(seg, time)
+    sched2 = ops.attn_build_pair_schedule(sched, seq)
     t, h, w = clip_thw[-1]
     return SeqPlan(text_len, video_len, seq, t * h * w, clip_thw, rope.to(device), seg.to(device), time.to(device),
-                   sched.to(device), int(pairs.sum()))
+                   sched.to(device), sched2.to(device), int(pairs.sum()))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -194,6 +196,7 @@ class B200FluxTransformer(torch.nn.Module):
         # does not depend on how fast the host can walk the launch sequence (ctypes + descriptor encoding per launch).
         # Off by default: callers that reuse shapes for many steps (sampler, bench) turn it on.
         self.trim_last_block = True     # last single block on the current clip's rows only (exact; see forward)
+        self.attn_variant = 0           # pf_attn_desc.variant (0 = the default two-q-tile kernel); bench/tests A/B others
         self.use_cuda_graph = False
         self._graphs: "Dict[tuple, dict]" = {}
         self._graph_warm = False
@@ -391,7 +394,7 @@ class B200FluxTransformer(torch.nn.Module):
         plan = self.plan_for([cl.shape for cl in clips], mask)
         ins = [*clips, timestep_ratio, enc, pooled]
         key = (id(plan), bool(getattr(self, "output_fp32", False)), bool(self.trim_last_block),
-               bool(self.emulate_bf16_rounding), tuple((tuple(x.shape), x.dtype) for x in ins))
+               bool(self.emulate_bf16_rounding), int(self.attn_variant), tuple((tuple(x.shape), x.dtype) for x in ins))
         ent = self._graphs.get(key)
         if ent is None:
             while len(self._graphs) >= 3:                      # every entry pins a workspace (~1.5 GB at 768p)
@@ -514,7 +517,8 @@ class B200FluxTransformer(torch.nn.Module):
                              seq_len=sl)
 
         scale = 1.0 / math.sqrt(64)
-        seg, tim, sched = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b]
+        seg, tim, sched, sched2 = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b], plan.sched2[b0:b0 + b]
+        av = self.attn_variant
 
         def exchange_begin():
             return SP.heads_to_sequence_qkv_begin(q[0], k[0], v[0], lay) if nsp > 1 else None
@@ -526,7 +530,7 @@ class B200FluxTransformer(torch.nn.Module):
             if nsp == 1:
                 if ev:
                     e0.record()
-                ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale, q_row_begin=q_row_begin)
+                ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale, variant=av, q_row_begin=q_row_begin, pair_sched=sched2)
                 if ev:
                     e1.record()
             else:
@@ -535,7 +539,7 @@ class B200FluxTransformer(torch.nn.Module):
                 of = ws["of"]
                 if ev:
                     e0.record()
-                ops.attn_fwd(qf[None], kf[None], vf[None], of[None], seg, tim, sched, scale)
+                ops.attn_fwd(qf[None], kf[None], vf[None], of[None], seg, tim, sched, scale, variant=av, pair_sched=sched2)
                 if ev:
                     e1.record()
                 cat[0, :, :wa].copy_(SP.sequence_to_heads(of, lay))

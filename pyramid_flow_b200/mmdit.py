@@ -169,7 +169,7 @@ class B200MMDiT(torch.nn.Module):
             dev = self.device
             t, h, w = thw[-1]
             plan = SeqPlan(t_len, video_len, seq, t * h * w, thw, build_rope_table(tid[:, None], (64,)).to(dev), seg.to(dev),
-                           time.to(dev), sched.to(dev), int(pairs.sum()))
+                           time.to(dev), sched.to(dev), ops.attn_build_pair_schedule(sched, seq).to(dev), int(pairs.sum()))
             hit = (plan, torch.cat(pos, 0).to(dev).contiguous())
             self._plans[key] = hit
         self._last_key = (mask, mask._version, shapes, hit)
@@ -259,7 +259,7 @@ class B200MMDiT(torch.nn.Module):
                          rows_per_batch=s, row_begin=r0, row_count=rc, q_out=q, k_out=k, v_out=v, rope=plan.rope,
                          q_norm_w=(w["cnq"], w["nq"])[j], k_norm_w=(w["cnk"], w["nk"])[j], norm_eps=1e-5, heads=hn,
                          head_dim=64, seq_len=s)
-            ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, scale)
+            ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, scale, pair_sched=plan.sched2)
             for j, (r0, rc) in enumerate(ranges):
                 if j == 0 and last:
                     continue   # context_pre_only: the text stream ends here (MB:659-660)

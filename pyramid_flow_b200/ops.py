@@ -139,8 +139,20 @@ def attn_build_schedule(seg: torch.Tensor, time: torch.Tensor):
     return sched, pairs
 
 
+def attn_build_pair_schedule(sched: torch.Tensor, seq: int) -> torch.Tensor:
+    """Tile schedule (int32 CPU [batch, q_tiles, stride]) -> pair schedule [batch, ceil(q_tiles/2), stride] of the two-q-tile
+    kernel (pf_attn_build_pair_schedule)."""
+    sched = sched.to(torch.int32).contiguous().cpu()
+    batch, qt, stride = sched.shape
+    out = torch.zeros(batch, (qt + 1) // 2, stride, dtype=torch.int32)
+    _lib.check(_lib.load().pf_attn_build_pair_schedule(sched.data_ptr(), batch, seq, stride, out.data_ptr()),
+               "pf_attn_build_pair_schedule")
+    return out
+
+
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, seg: torch.Tensor,
-             time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0, q_row_begin: int = 0) -> None:
+             time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0, q_row_begin: int = 0,
+             pair_sched: Optional[torch.Tensor] = None) -> None:
     """q,k,v bf16 [B,H,S,64]; out bf16 [B,S,*] (row stride = out.stride(1)); seg/time/sched int32 on device.
     Only q rows >= q_row_begin (multiple of 128) are computed; other rows of `out` are left untouched."""
     assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
@@ -154,6 +166,9 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
     d.sched_stride = sched.shape[-1]
     d.variant = variant
     d.q_row_begin = q_row_begin
+    if pair_sched is not None:
+        assert pair_sched.dtype == torch.int32 and pair_sched.shape[-1] == sched.shape[-1]
+        d.pair_sched = pair_sched.data_ptr()
     _lib.check(_lib.load().pf_attn_fwd_masked(C.byref(d), _lib.stream_ptr()), "pf_attn_fwd_masked")
 
 

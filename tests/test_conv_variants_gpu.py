@@ -123,5 +123,5 @@ def test_vae_decode_full_resolution_matches_oracle():
     print(f"VAE 96x160 latent -> {tuple(out.shape)}: ours vs fp32 oracle max_abs {err:.3e} mse {mse:.3e} | reference bf16 policy "
           f"max_abs {e2:.3e} mse {m2:.3e} | |ref| mean {ref.abs().mean():.3f}")
     assert out.shape == ref.shape == (1, 3, 17, 768, 1280)
-    assert err < 1.5e-1 and mse < 1e-4                 # max over 5e7 values; RMS error 1e-2
+    assert err < 8.8e-2 and mse < 7.3e-5               # measured 6.70e-2 / 5.61e-5 (max over 5e7 values) x 1.3
     assert mse <= 2.0 * m2 + 1e-5, "must be comparable to the reference's own bf16 error"

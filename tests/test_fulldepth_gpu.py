@@ -10,11 +10,13 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# measured on B200 (round 2): full depth 8+16 @ S=15488 max-abs / mse are printed by the test; the thresholds are those x1.3
-TOL_FULL_MAX_ABS = 2.0e-2
-TOL_FULL_MSE = 1.2e-5
-TOL_MMDIT24_MAX_ABS = 2.0e-2
-TOL_MMDIT24_MSE = 1.2e-5
+# Measured on B200 (round 2, gpurun_out/r2_tests1.log): 8+16 blocks @ S=15488: max-abs 1.159e-2, mse 5.80e-6 (2+2 blocks at the
+# same size: 9.84e-3 / 4.37e-6 -- the fp32 residual stream keeps the growth over 24 blocks at ~18 %); MMDiT 24 blocks:
+# 1.129e-2 / 6.10e-6 (3 blocks: 8.6e-3 / 4.0e-6).  Thresholds = measured x 1.3.
+TOL_FULL_MAX_ABS = 1.5e-2
+TOL_FULL_MSE = 7.6e-6
+TOL_MMDIT24_MAX_ABS = 1.47e-2
+TOL_MMDIT24_MSE = 8.0e-6
 
 
 def _oracle_on_gpu(fn, head_chunk):
@@ -46,12 +48,15 @@ def test_full_depth_full_size_flux_step_matches_oracle():
     t = torch.tensor([3.0, 3.0])
 
     model = B200FluxTransformer(FluxConfigB200(), params, device=dev)
-    call = dict(sample=[[c.to(dev) for c in clips]], timestep_ratio=t.to(dev), encoder_hidden_states=enc.to(dev),
+    call = dict(sample=[[c.to(dev).bfloat16() for c in clips]], timestep_ratio=t.to(dev), encoder_hidden_states=enc.to(dev),
                 encoder_attention_mask=mask.to(dev), pooled_projections=pooled.to(dev))
-    out = model(**call)[0].float().cpu()
-    assert model.last_plan.seq == 15488
-    model.output_fp32 = True
-    out32 = model(**call)[0].float().cpu()
+    o = model(**call)[0]                                  # bf16 latents in -> bf16 velocity out (what the pipeline sees)
+    assert o.dtype == torch.bfloat16 and model.last_plan.seq == 15488
+    out = o.float().cpu()
+    model.output_fp32 = True                              # same step, velocity stored in fp32: isolates the bf16 store
+    o32 = model(**call)[0]
+    assert o32.dtype == torch.float32
+    out32 = o32.float().cpu()
     model.output_fp32 = False
 
     pd = {k: v.to(dev) for k, v in params.items()}
@@ -66,7 +71,7 @@ def test_full_depth_full_size_flux_step_matches_oracle():
           f"| |v| mean {ref.abs().mean():.3f} max {ref.abs().max():.2f}")
     assert ref.abs().mean().item() > 0.1, "degenerate oracle output"
     assert err < TOL_FULL_MAX_ABS and mse < TOL_FULL_MSE
-    assert err32 <= err + 1e-6
+    assert err32 <= err + 4e-3 and mse32 <= mse * 1.05      # the bf16 store can only add up to half an ulp
 
 
 def test_24_block_mmdit_step_matches_oracle():

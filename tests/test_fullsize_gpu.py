@@ -43,7 +43,7 @@ def test_full_size_step_two_plus_two_blocks_matches_oracle():
     assert model.last_plan.seq == 15488
     err, mse = (out - ref).abs().max().item(), ((out - ref) ** 2).mean().item()
     print(f"full-size (S=15488, 2+2 blocks): max_abs {err:.3e} mse {mse:.3e} |v| mean {ref.abs().mean():.3f}")
-    assert err < 3e-2 and mse < 5e-5
+    assert err < 1.3e-2 and mse < 5.7e-6     # measured 9.84e-3 / 4.37e-6 (round 2) x 1.3
 
 
 def test_attention_full_size_sampled_rows_and_properties():

@@ -95,20 +95,43 @@ def test_gemm_epilogues_row_ranges():
     assert _rel(cat[..., D:], F.gelu(x.float() @ wm.float().t() + bm, approximate="tanh")) < 8e-3
 
 
-def _attn_case(B, H, S, seg, tim):
+# pf_attn_desc.variant: 3 = one-q-tile kernel, 0x10 | k = two-q-tile kernel with k of every 4 exponential pairs on the FMA pipe
+ATTN_VARIANTS = [3, 0x10, 0x11, 0x12, 0x13, 0]
+
+
+def _attn_ref(q, k, v, sg, tm):
+    B, H, S, _ = q.shape
+    mask = (sg[:, :, None] == sg[:, None, :]) & (tm[:, :, None] >= tm[:, None, :])
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=mask[:, None])
+    return ref.transpose(1, 2).reshape(B, S, H * 64), mask
+
+
+def _attn_case(B, H, S, seg, tim, scale_q=1.0):
+    """max |out - fp32 SDPA(dense mask)| over every kernel variant; also q_row_begin (rows below it stay untouched)."""
     from pyramid_flow_b200 import ops
-    q = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    q = (torch.randn(B, H, S, 64, device=DEV) * scale_q).bfloat16()
     k = torch.randn(B, H, S, 64, device=DEV).bfloat16()
     v = torch.randn(B, H, S, 64, device=DEV).bfloat16()
-    out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
     sched, pairs = ops.attn_build_schedule(seg, tim)
-    ops.attn_fwd(q, k, v, out, seg.to(DEV).int(), tim.to(DEV).int(), sched.to(DEV), 0.125)
-    torch.cuda.synchronize()
-    sg, tm = seg.to(DEV), tim.to(DEV)
-    mask = (sg[:, :, None] == sg[:, None, :]) & (tm[:, :, None] >= tm[:, None, :])
+    psched = ops.attn_build_pair_schedule(sched, S).to(DEV)
+    sg, tm = seg.to(DEV).int(), tim.to(DEV).int()
+    ref, mask = _attn_ref(q, k, v, sg, tm)
     assert int(pairs.sum()) == int(mask.sum())
-    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), attn_mask=mask[:, None]).transpose(1, 2).reshape(B, S, H * 64)
-    return (out.float() - ref).abs().max().item()
+    worst = 0.0
+    for variant in ATTN_VARIANTS:
+        out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
+        ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=psched)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out.float()).all()), variant
+        worst = max(worst, (out.float() - ref).abs().max().item())
+        for qb in sorted({((S - 1) // 128) * 128, (S // 256) * 128}):
+            if qb == 0:
+                continue
+            o2 = torch.full((B, S, H * 64), 7.0, device=DEV, dtype=torch.bfloat16)
+            ops.attn_fwd(q, k, v, o2, sg, tm, sched.to(DEV), 0.125, variant=variant, q_row_begin=qb, pair_sched=psched)
+            torch.cuda.synchronize()
+            assert torch.equal(o2[:, qb:], out[:, qb:]) and bool((o2[:, :qb] == 7.0).all()), (variant, qb)
+    return worst
 
 
 def test_attention_mask_cases():
@@ -128,6 +151,50 @@ def test_attention_mask_cases():
     seg = torch.ones(2, S, dtype=torch.int32)
     seg[1, 50:77] = 0
     assert _attn_case(2, 4, S, seg, tim) < 2e-2
+    # long frames (q-tile pairs whose kv lists differ by many tiles), odd tile count
+    S = 128 + 200 + 1000 + 1700
+    tim = torch.cat([torch.zeros(128 + 200), torch.ones(1000), 2 * torch.ones(1700)]).int()[None].repeat(2, 1)
+    seg = torch.ones(2, S, dtype=torch.int32)
+    seg[0, 100:128] = 0
+    assert _attn_case(2, 2, S, seg, tim) < 2e-2
+
+
+def test_attention_adversarial_score_jumps():
+    """Scores that jump by hundreds of log2 units between neighbouring kv tiles, rising and falling (the exponent argument must
+    never overflow; rows dominated by one tile must come out exact), and a pair schedule consistent with the tile schedule."""
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(11)
+    B, H, S = 1, 2, 1024
+    q = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    k = torch.randn(B, H, S, 64, device=DEV)
+    amp = torch.tensor([1.0, 60.0, 0.02, 250.0, 1.0, 0.001, 120.0, 5.0], device=DEV)       # per kv tile
+    k = (k * amp.repeat_interleave(128)[None, None, :, None]).bfloat16()
+    v = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    seg = torch.ones(B, S, dtype=torch.int32)
+    tim = (torch.arange(S) // 256).int()[None]
+    sched, _ = ops.attn_build_schedule(seg, tim)
+    psched = ops.attn_build_pair_schedule(sched, S)
+    # pair rows: union of the two tiles' lists, flags consistent with the tile rows
+    qt = S // 128
+    for p in range((qt + 1) // 2):
+        hi, lo = qt - 1 - 2 * p, qt - 2 - 2 * p
+        n = int(psched[0, p, 0])
+        ent = psched[0, p, 1:1 + n].tolist()
+        for x, t in ((0, lo), (1, hi)):
+            if t < 0:
+                assert all(((e >> (2 * x)) & 3) == 0 for e in ent)
+                continue
+            own = [((e >> 4) << 1) | (((e >> (2 * x)) & 2) >> 1) for e in ent if (e >> (2 * x)) & 1]
+            assert own == sched[0, t, 1:1 + int(sched[0, t, 0])].tolist()
+    sg, tm = seg.to(DEV), tim.to(DEV)
+    ref, _ = _attn_ref(q, k, v, sg, tm)
+    for variant in ATTN_VARIANTS:
+        out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
+        ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=psched.to(DEV))
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out.float()).all()), variant
+        if variant != 3:      # the one-tile kernel's reference max is one tile stale: it saturates (finite) on such jumps
+            assert (out.float() - ref).abs().max().item() < 3e-2, variant
 
 
 def test_elementwise_kernels():

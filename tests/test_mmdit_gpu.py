@@ -3,8 +3,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-TOL_MAX_ABS = 3e-2     # same stated tolerance as the miniFLUX step (tests/test_dit_gpu.py)
-TOL_MSE = 5e-5
+TOL_MAX_ABS = 1.55e-2  # measured 8.6e-3 .. 1.195e-2 (round 2) x 1.3
+TOL_MSE = 6e-6         # measured 4.0e-6 .. 4.4e-6
 
 
 def _run(cfg_kw, params, clips, t, enc, mask, pooled):

@@ -8,8 +8,9 @@ pytestmark = pytest.mark.gpu
 # bf16 activations through ~60 convs + 30 GroupNorms; decoded samples are O(0.5) (|ref| mean ~0.43, range ~[-2, 2]).
 # Stated tolerance on the decoded sample vs the fp32 oracle: max-abs 0.1 (the max over ~2.6e5 values), MSE 1e-4
 # (RMS error 1e-2), and no worse than 1.5x the error of the reference's own dtype policy (oracle under bf16 autocast).
-TOL_MAX_ABS = 1e-1
-TOL_MSE = 1e-4
+# Measured (round 2): max-abs 5.5e-2 .. 6.1e-2, mse 5.5e-5 .. 5.9e-5 (reference bf16 policy: 6.7e-2 / 9.5e-5); thresholds x 1.3.
+TOL_MAX_ABS = 8e-2
+TOL_MSE = 7.7e-5
 
 
 def _conv_ref(x_cl, w, b, kt):

@@ -424,9 +424,16 @@ def group_attn_perf():
     sched, pairs = ops.attn_build_schedule(seg, tim)
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
     flops = 4.0 * 64 * H * float(pairs.sum())
-    for variant in (0, 1):
-        ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant), iters=5)
-        print(f"[attn_perf] variant {variant} S={S} B={B} H={H}: {ms:.3f} ms, allowed pairs {pairs.tolist()}, {flops/ms/1e9:.0f} TFLOP/s (masked-pair flops)", flush=True)
+    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    ref = None
+    for variant in (3, 0x10, 0x11, 0x12, 0x13):
+        out.zero_()
+        ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps), iters=8, warm=2)
+        if ref is None:
+            ref = out.clone()
+        dev_ = (out.float() - ref.float()).abs().max().item()
+        print(f"[attn_perf] variant {variant:#x} S={S} B={B} H={H}: {ms:.3f} ms, {flops/ms/1e9:.0f} TFLOP/s (masked-pair flops), "
+              f"max |out - one-tile kernel| {dev_:.2e}", flush=True)
 
 
 def group_gemm_epi_perf():
