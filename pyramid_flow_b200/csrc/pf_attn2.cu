@@ -17,7 +17,7 @@
 //     exponent argument is therefore always <= 8: no overflow for any input);
 //   * warp 8/9 = MMA issuers of tile A/B (one elected lane each), warp 10 = TMA producer (Q once, K through a 4-stage and V
 //     through a 3-stage mbarrier ring shared by both tiles), warp 11 allocates TMEM; setmaxnreg moves registers from
-//     warps 8-11 (48) to the softmax warpgroups (232).
+//     warps 8-11 (40) to the softmax warpgroups (232).
 // TMEM (512 columns): tile X at column 256 X: S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256).
 #include <algorithm>
 #include <vector>
@@ -37,7 +37,7 @@ constexpr int A2_TILE_BYTES = A2_BN * A2_HD * 2;  // 16 KB
 constexpr int A2_SMEM_BYTES = (2 + A2_KSTAGES + A2_VSTAGES) * A2_TILE_BYTES + 1024;
 constexpr uint32_t A2_TMEM_COLS = 512;
 constexpr uint32_t A2_TM_TILE = 256, A2_TM_S = 0, A2_TM_O = 128, A2_TM_P = 192;
-constexpr int A2_REGS_SOFTMAX = 232, A2_REGS_OTHER = 48;
+constexpr int A2_REGS_SOFTMAX = 232, A2_REGS_OTHER = 40;   // 256*232 + 128*40 = 384*168: exactly the CTA's launch allocation (more would block setmaxnreg.inc forever)
 
 struct Attn2Args {
   __nv_bfloat16* out;
