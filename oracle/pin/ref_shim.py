@@ -23,7 +23,16 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = "/root/reference"
+import os as _os
+
+# /root/reference in the build container; on the GPU box the byte-for-byte copy staged by oracle/pin/stage_reference.py
+_STAGED = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))), "baseline", "_ref")
+REFERENCE_ROOT = "/root/reference" if _os.path.isdir("/root/reference") else _STAGED
+
+
+def reference_available() -> bool:
+    return _os.path.isdir(_os.path.join(REFERENCE_ROOT, "pyramid_dit"))
+
 
 
 def _mod(name: str) -> types.ModuleType:

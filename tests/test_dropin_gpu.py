@@ -1,0 +1,143 @@
+"""THE DROP-IN, exercised as a drop-in: the UNMODIFIED reference pipeline class
+`PyramidDiTForVideoGeneration` (imported from the byte-for-byte copy staged in baseline/_ref by oracle/pin/stage_reference.py;
+the GPU box has no /root/reference) runs its own `generate()` / `generate_i2v()` / `decode_latent()` twice on the same B200:
+
+    (a) with the reference's own modules   (bf16 weights under torch.autocast, the README's way of running it), and
+    (b) with  pipe.dit = B200FluxTransformer.from_reference(ref_dit)   and   pipe.vae = B200CausalVAE.from_reference(ref_vae)
+
+on identical seeds, text embeddings and injected block noise, and both are compared with the CPU fp32 goldens the reference
+produced in the build container (tests/golden/sampler_small.pt, sampler_i2v_small.pt).  No mirror of the sampler is involved:
+the loop, the scheduler and the latent bookkeeping are the reference's code (P:706-788, 791-1003, 1006-1243)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle.pin import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference packages not staged (run `python oracle/pin/stage_reference.py` where /root/reference exists)")
+    ref_shim.install()
+    import diffusion_schedulers
+    import pyramid_dit
+    import video_vae
+    return dict(pipeline=pyramid_dit.PyramidDiTForVideoGeneration,
+                flux=__import__("pyramid_dit.flux_modules", fromlist=["PyramidFluxTransformer"]).PyramidFluxTransformer,
+                sched=diffusion_schedulers.PyramidFlowMatchEulerDiscreteScheduler, vae=video_vae.CausalVideoVAE)
+
+
+class _FakeText:
+    """generate() asks for the prompt first, then for the negative prompt (P:1066-1067)."""
+
+    def __init__(self, enc, mask, pooled):
+        self.enc, self.mask, self.pooled, self.calls = enc, mask, pooled, 0
+
+    def __call__(self, prompt, device):
+        i = 1 if self.calls % 2 == 0 else 0
+        self.calls += 1
+        return self.enc[i:i + 1], self.mask[i:i + 1], self.pooled[i:i + 1]
+
+
+def _make_pipe(ref, dit, vae, g, dev):
+    pipe = object.__new__(ref["pipeline"])
+    pipe.dit = dit
+    pipe.vae = vae
+    pipe.text_encoder = _FakeText(g["enc"].to(dev).bfloat16(), g["mask"].to(dev), g["pooled"].to(dev).bfloat16())
+    pipe.scheduler = ref["sched"](shift=1.0, stages=3, stage_range=[0, 1 / 3, 2 / 3, 1], gamma=1 / 3)
+    pipe.stages = [1, 2, 4]
+    pipe.frame_per_unit = 1
+    pipe.model_name = "pyramid_flux"
+    pipe.sequential_offload_enabled = False
+    pipe.downsample = 8
+    pipe.vae_shift_factor, pipe.vae_scale_factor = -0.04, 1 / 1.8726
+    pipe.vae_video_shift_factor, pipe.vae_video_scale_factor = -0.2343, 1 / 3.0986
+    noises = [n.clone() for n in g["noises"]]
+    pipe.sample_block_noise = lambda bs, ch, temp, height, width: noises.pop(0)
+    return pipe
+
+
+def _ref_dit(ref, g, dev):
+    from oracle import flux_oracle as FO
+    cfg = FO.FluxConfig(**g["cfg"])
+    params = FO.synthetic_flux_params(cfg, seed=g["param_seed"])
+    dit = ref["flux"](**g["cfg"]).eval()
+    dit.load_state_dict(params, strict=True)
+    return dit.to(dev, torch.bfloat16)
+
+
+def _rel_mse(a, b):
+    return (((a - b) ** 2).mean() / (b ** 2).mean()).item()
+
+
+def test_unmodified_generate_with_swapped_dit(ref, golden_dir):
+    from pyramid_flow_b200.dit import B200FluxTransformer
+    dev = torch.device("cuda:0")
+    g = torch.load(golden_dir / "sampler_small.pt", weights_only=False)
+    rdit = _ref_dit(ref, g, dev)
+    ours = B200FluxTransformer.from_reference(rdit, device=dev)
+    assert ours.config.in_channels == rdit.config.in_channels and next(ours.parameters()).device == next(rdit.parameters()).device
+    outs = {}
+    for name, dit in (("reference", rdit), ("b200", ours)):
+        pipe = _make_pipe(ref, dit, None, g, dev)
+        gen = torch.Generator().manual_seed(g["latent_seed"])
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            lat = pipe.generate(prompt="x", generator=gen, output_type="latent", save_memory=True, **g["args"])
+        torch.cuda.synchronize()
+        assert lat.shape == g["latents"].shape
+        outs[name] = lat.float().cpu()
+    gold = g["latents"]
+    r_ref, r_ours, r_pair = _rel_mse(outs["reference"], gold), _rel_mse(outs["b200"], gold), _rel_mse(outs["b200"], outs["reference"])
+    print(f"generate() final latents, relative MSE vs the CPU fp32 golden: reference-on-GPU (bf16 autocast) {r_ref:.3e}, "
+          f"B200 drop-in {r_ours:.3e}; drop-in vs reference-on-GPU {r_pair:.3e}; |latent| mean {gold.abs().mean():.3f}")
+    assert r_ours < 2e-3 and r_ours <= 1.5 * r_ref + 2e-4, "the drop-in must be as close to the fp32 loop as the reference's own bf16 run"
+
+
+def test_unmodified_generate_i2v_and_decode_latent_with_swapped_vae(ref, golden_dir):
+    """generate_i2v() needs vae.encode (image latent, P:911) and, with output_type='pil', decode_latent (P:1221-1243): the
+    whole call runs on the swapped B200 objects and on the reference modules; frames are compared as uint8 images."""
+    from PIL import Image
+    from oracle import vae_oracle as VO
+    from pyramid_flow_b200.dit import B200FluxTransformer
+    from pyramid_flow_b200.vae import B200CausalVAE
+    dev = torch.device("cuda:0")
+    g = torch.load(golden_dir / "sampler_i2v_small.pt", weights_only=False)
+    rdit = _ref_dit(ref, g, dev)
+    # a small reference VAE with non-degenerate weights on both sides (decoder: the small golden config; encoder likewise)
+    dcfg = VO.VaeDecoderConfig(block_out_channels=(64, 64, 128, 128), layers_per_block=(1, 1, 1, 1))
+    ecfg = VO.VaeEncoderConfig(block_out_channels=(64, 64, 128, 128), layers_per_block=(1, 1, 1, 1))
+    rvae = ref["vae"](encoder_out_channels=16, decoder_in_channels=16, encoder_block_out_channels=ecfg.block_out_channels,
+                      encoder_layers_per_block=ecfg.layers_per_block, decoder_block_out_channels=dcfg.block_out_channels,
+                      decoder_layers_per_block=dcfg.layers_per_block).eval()
+    sd = rvae.state_dict()
+    new = {**VO.synthetic_vae_params(dcfg, seed=4), **VO.synthetic_vae_params(ecfg, seed=5)}
+    assert set(new) <= set(sd)
+    # latent_dist.sample() draws from the global RNG (D:381-389): pin log-variance at -30 so the image latent is its mean
+    new["quant_conv.conv.weight"][16:] = 0
+    new["quant_conv.conv.bias"][16:] = -30.0
+    sd.update(new)
+    rvae.load_state_dict(sd, strict=True)
+    rvae = rvae.to(dev, torch.bfloat16)
+    rvae.enable_tiling()
+    ovae = B200CausalVAE.from_reference(rvae, device=dev)
+    ovae.enable_tiling()
+    odit = B200FluxTransformer.from_reference(rdit, device=dev)
+    img = Image.fromarray((g["image_tensor"][0, :, 0].permute(1, 2, 0) * 127.5 + 127.5).round().clamp(0, 255).byte().numpy())
+    frames = {}
+    for name, dit, vae in (("reference", rdit, rvae), ("b200", odit, ovae)):
+        pipe = _make_pipe(ref, dit, vae, g, dev)
+        gen = torch.Generator().manual_seed(g["latent_seed"])
+        args = {k: v for k, v in g["args"].items() if k not in ("height", "width")}
+        torch.manual_seed(123)                       # latent_dist.sample() draws from the global CUDA RNG (D:381-389)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            out = pipe.generate_i2v(prompt="x", input_image=img, generator=gen, output_type="pil", save_memory=True, **args)
+        torch.cuda.synchronize()
+        import numpy as np
+        frames[name] = torch.from_numpy(np.stack([np.asarray(f) for f in out])).float()
+    a, b = frames["b200"], frames["reference"]
+    assert a.shape == b.shape and a.shape[0] == 1 + 8 * (g["args"]["temp"] - 1)
+    diff = (a - b).abs()
+    print(f"generate_i2v -> decode_latent, uint8 frames {tuple(a.shape)}: mean |diff| {diff.mean():.3f} / 255, "
+          f"99.9th pct {diff.flatten().kthvalue(int(0.999 * diff.numel())).values.item():.0f}, max {diff.max():.0f}; frame std {b.std():.1f}")
+    assert diff.mean().item() < 2.0 and b.std().item() > 5.0
