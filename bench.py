@@ -5,7 +5,12 @@ A "step" is ONE DiT forward (the pipeline's `self.dit(...)` call, P:760-766) at 
 768p / 10 s configuration: unit 30, stage 2 — CFG batch B=2, S = 128 text + 28x240 + 960 + 3840 history
 + 3840 current = 15488 tokens, full 8+16-block miniFLUX (D=1920, 30 heads), synthetic latents / text embeddings and
 random-init weights (no checkpoints offline).  tokens/s = B * S / t_step; with --gpus N the SAME step is sharded over
-the N GPUs (CFG pair first, then Ulysses sequence parallel; strong scaling).
+the N GPUs (CFG pair first, then Ulysses sequence parallel with the exchange fused into the kernels over NVLink peer
+memory; strong scaling, `parity_vs_n1` = max |sharded - single-GPU| of the step's output on the same inputs).
+The line also carries the second half of BASELINE's metric: `vae_decode` (768p causal-VAE decode, frames/s + conv roofline)
+and `video_e2e` (the whole 768p / 10 s pyramidal sampler + decode, frames/s), and two baselines timed in the same run: the
+reference algorithm on the host cores (`cpu_baseline`) and the UNMODIFIED reference modules in eager PyTorch bf16 on the
+same B200 (`gpu_eager_baseline`, from the copy staged in baseline/_ref).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA kernels through the C-ABI)
   python bench.py --impl reference ...                           the reference algorithm's CPU path (oracle port), host cores
@@ -26,6 +31,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+ATTN_TRAFFIC_BYTES = None   # filled from the committed ncu capture of the attention kernel (profiles/r02_attn2_ncu.txt)
 METRIC = "dit_step_latent_tokens_per_sec"
 UNIT = "tokens/s"
 WORKLOAD = ("miniFLUX 768p/10s (BASELINE configs[2]) — one DiT forward at unit 30 / stage 2: CFG batch 2, "
@@ -105,8 +111,8 @@ def cpu_reference_sample(n_double=1, n_single=2, threads=None, repeats=1):
     the full 8+16-block forward, and a description of the sample."""
     import torch
     from oracle import flux_oracle as FO
-    if threads:
-        torch.set_num_threads(threads)
+    # every host core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1: round 1's N>1 CPU arm ran on one thread)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     threads = torch.get_num_threads()
     cfg = FO.FluxConfig(num_layers=n_double, num_single_layers=n_single)
     params = FO.synthetic_flux_params(cfg, seed=0)
@@ -133,26 +139,78 @@ def cpu_reference_sample(n_double=1, n_single=2, threads=None, repeats=1):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path (oracle port) on this box's host cores."""
+    """--impl reference: the reference's own CPU path (oracle port) on this box's host cores.  A step = one bounded sample
+    (1 double + 2 single blocks at the 768p unit-30 / stage-0 sequence, scaled x8 to the 24-block forward): `warmup` untimed
+    samples, then exactly `steps` timed ones; `value` is the mean over the timed samples."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    for _ in range(args.warmup):
-        pass  # the sample is deterministic dense math; warm-up is folded into the first (discarded) repeat below
-    reps = max(1, args.steps)
-    r0 = cpu_reference_sample(repeats=1)            # discarded warm-up (page-in, thread pool)
-    vals = [cpu_reference_sample(repeats=1) for _ in range(min(reps, 3))]
-    v = sorted(vals, key=lambda x: x["tokens_per_s"])[len(vals) // 2]
-    line = {"metric": METRIC, "value": v["tokens_per_s"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * v["tokens"] / v["tokens_per_s"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm is timed on a bounded sample, see cpu_baseline.sample"},
-            "cpu_baseline": {"value": v["tokens_per_s"], "unit": UNIT, "cores": v["threads"], "kind": "port",
-                             "sample": v["sample"] + f"; median of {len(vals)} samples after 1 warm-up"},
-            "e2e": {"value": v["tokens_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    for _ in range(max(1, args.warmup)):
+        cpu_reference_sample(repeats=1)             # untimed: page-in, thread pool
+    t0 = time.perf_counter()
+    vals = [cpu_reference_sample(repeats=1) for _ in range(max(1, args.steps))]
+    wall = time.perf_counter() - t0
+    tok = vals[0]["tokens"]
+    mean_full_s = sum(v["tokens"] / v["tokens_per_s"] for v in vals) / len(vals)     # extrapolated 24-block seconds per step
+    value = tok / mean_full_s
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": max(1, args.warmup), "ms_per_step": 1e3 * mean_full_s,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "same_config": False,
+            "config": {"workload": WORKLOAD,
+                       "note": ("CPU arm: every step is a bounded SAMPLE of the workload, not the S=15488 step itself (see "
+                                "cpu_baseline.sample); ms_per_step is the sample time x8; the timed samples took "
+                                f"{wall:.1f} s of wall clock")},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": vals[0]["threads"], "kind": "port",
+                             "sample": vals[0]["sample"] + f"; mean of {len(vals)} timed samples after {max(1, args.warmup)} warm-up"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_reference(dev, host, steps=2):
+    """The UNMODIFIED reference `PyramidFluxTransformer` (baseline/_ref copy through oracle/pin/ref_shim.py) in eager PyTorch
+    under bf16 autocast on this GPU: the full 8+16-block forward at the bench shape, dense [B,1,S,S] bool mask + SDPA as the
+    reference builds them (F:318-350, B:363-365).  A reported baseline, never on the product path."""
+    import torch
+    try:
+        from oracle.pin import ref_shim
+        if not ref_shim.reference_available():
+            return {"unavailable": "reference packages not staged in baseline/_ref (oracle/pin/stage_reference.py)"}
+        ref_shim.install()
+        from pyramid_dit.flux_modules import PyramidFluxTransformer
+        with torch.device(dev):
+            m = PyramidFluxTransformer(num_layers=8, num_single_layers=16, num_attention_heads=30, attention_head_dim=64,
+                                       in_channels=64, joint_attention_dim=4096, pooled_projection_dim=768).eval()
+        g = torch.Generator(device=dev).manual_seed(0)
+        with torch.no_grad():
+            for prm in m.parameters():                      # the reference zero-inits AdaLN/proj_out (F:168-183)
+                prm.copy_(torch.randn(prm.shape, device=dev, generator=g) * 0.02)
+        m = m.to(torch.bfloat16)
+        clips = [x.to(dev) for x in host["clips"]]
+        kw = dict(sample=[clips], timestep_ratio=host["t"].to(dev), encoder_hidden_states=host["enc"].to(dev),
+                  encoder_attention_mask=host["mask"].to(dev), pooled_projections=host["pooled"].to(dev))
+        times = []
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for i in range(1 + steps):
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = m(**kw)[0]
+                e.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    times.append(s.elapsed_time(e))
+        ms = sum(times) / len(times)
+        b, seq = clips[-1].shape[0], 128 + sum(c.shape[2] * (c.shape[3] // 2) * (c.shape[4] // 2) for c in clips)
+        res = {"value": b * seq / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": 1,
+               "kind": "reference (unmodified modules, eager PyTorch, bf16 autocast, SDPA with the dense bool mask)",
+               "same_config": True, "output_finite": bool(torch.isfinite(out.float()).all())}
+        del m, out
+        torch.cuda.empty_cache()
+        return res
+    except Exception as ex:  # noqa: BLE001  (a baseline leg must never take the bench line down)
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -238,6 +296,111 @@ def random_vae_state_dict(device, seed=0, block_out_channels=(128, 256, 512, 512
     return sd
 
 
+def vae_decode_leg(dev, world, rank):
+    """Causal-VAE decode at 768p (BASELINE configs[2], second half of the metric): un-tiled, temporally chunked (window 4),
+    5 latent -> 33 video frames on one GPU; with N GPUs 1 + 4 N latent frames, context-parallel (temporal split + 2-frame
+    halo exchange per causal conv).  Conv roofline: 1.10e7 MAC per output pixel-frame against the measured
+    sustained bf16 peak."""
+    import torch
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    vae = B200CausalVAE(VaeConfigB200(), random_vae_state_dict(dev), device=dev)
+    t_lat = 5 if world == 1 else 1 + 4 * world
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(1, 16, t_lat, 96, 160, generator=g).bfloat16().to(dev)
+    if world > 1:
+        vae.set_context_parallel(None)
+
+    def run():
+        return vae.decode(z, temporal_chunk=True, window_size=4).sample
+
+    run()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    s.record()
+    for _ in range(reps):
+        out = run()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    frames = 1 + 8 * (t_lat - 1)
+    flops = 2.0 * 1.10e7 * frames * 768 * 1280
+    peaks = measured_peaks()
+    res = {"ms": ms, "frames": frames, "frames_per_s": frames / (ms * 1e-3), "latent": [1, 16, t_lat, 96, 160],
+           "out_shape": list(out.shape), "mode": "un-tiled, temporal chunks of 4 latent frames" + (", context-parallel over %d GPUs" % world if world > 1 else ""),
+           "tflops": flops / (ms * 1e-3) / 1e12, "frac_of_sustained_bf16": flops / (ms * 1e-3) / 1e12 / (peaks["tflops_sustained"] * world),
+           "algorithmic_flops": flops, "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30,
+           "output_finite": bool(torch.isfinite(out.float()).all())}
+    del vae, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def video_e2e_leg(dit, dev, world, rank):
+    """frames/s end to end at 768p / 10 s (temp 31 -> 241 frames): the 3-stage pyramidal sampler loop (960 DiT calls, steps
+    20/10, CFG) + causal-VAE decode, text embeddings synthetic (text encoding excluded as SURVEY.md §8d defines).  Every rank
+    runs the same loop; the DiT step is CFG x SP sharded, the decode context-parallel."""
+    import torch
+    from pyramid_flow_b200.sampler import B200PyramidSampler
+    from pyramid_flow_b200.scheduler import B200FlowMatchScheduler
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    vae = B200CausalVAE(VaeConfigB200(), random_vae_state_dict(dev), device=dev)
+    if world > 1:
+        vae.set_context_parallel(None)
+    torch.manual_seed(1234)                              # block noise comes from the global CPU RNG: identical on every rank
+    g = torch.Generator().manual_seed(0)
+    enc = (torch.randn(2, 128, 4096, generator=g) * 0.2).bfloat16().to(dev)
+    mask = torch.ones(2, 128, dtype=torch.long, device=dev)
+    pooled = torch.randn(2, 768, generator=g).bfloat16().to(dev)
+    tokens = [0]
+    orig = dit.forward
+
+    def counting(*a, **k):
+        out = orig(*a, **k)
+        tokens[0] += 2 * dit.last_plan.seq
+        return out
+
+    dit.forward = counting
+    try:
+        sampler = B200PyramidSampler(dit, B200FlowMatchScheduler(), vae=vae)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        t0 = time.time()
+        lat = sampler.generate(enc, mask, pooled, height=768, width=1280, temp=31, num_inference_steps=[20, 20, 20],
+                               video_num_inference_steps=[10, 10, 10], guidance_scale=7.0, video_guidance_scale=5.0,
+                               generator=torch.Generator().manual_seed(1), output_type="latent")
+        torch.cuda.synchronize()
+        t1 = time.time()
+        lat = torch.nan_to_num(lat.float()).clamp(-4, 4).to(lat.dtype)    # random weights: keep the decoder input sane
+        lat_n = lat.clone()
+        lat_n[:, :, :1] = lat_n[:, :, :1] / sampler.vae_scale_factor + sampler.vae_shift_factor
+        lat_n[:, :, 1:] = lat_n[:, :, 1:] / sampler.vae_video_scale_factor + sampler.vae_video_shift_factor
+        img = vae.decode(lat_n, temporal_chunk=True, window_size=4).sample
+        u8 = img.float().mul(127.5).add(127.5).clamp(0, 255).byte().permute(0, 2, 3, 4, 1).contiguous().cpu()
+        torch.cuda.synchronize()
+        t2 = time.time()
+    finally:
+        dit.forward = orig
+    frames = 241
+    res = {"config": "miniFLUX 768x1280, temp=31 (241 frames), steps 20/10, guidance 7/5, un-tiled decode (window 4)",
+           "frames_per_s_end_to_end": frames / (t2 - t0), "seconds": t2 - t0, "dit_seconds": t1 - t0,
+           "decode_seconds": t2 - t1, "dit_calls": sampler.dit_calls, "dit_token_passes_per_s": tokens[0] / (t1 - t0),
+           "video_shape": list(u8.shape), "latent_finite": bool(torch.isfinite(lat.float()).all())}
+    del vae, img, u8
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -261,11 +424,6 @@ def run_ours(args):
     del sd
     torch.cuda.empty_cache()
     lay = None
-    if world > 1:
-        from pyramid_flow_b200 import sp as SP
-        lay = SP.make_layout()
-        model.set_parallel_layout(lay)
-
     b = 2
     g = torch.Generator().manual_seed(100)
     shapes = step_clip_shapes(b)
@@ -300,7 +458,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    parity_ref = None
+    if world > 1:
+        # the SAME step on one GPU (every rank computes it, host-launched) before the layout is attached: the reference the
+        # sharded step's output is compared with (`parity_vs_n1`)
+        parity_ref = step_resident().float().clone()
+        torch.cuda.synchronize()
+        from pyramid_flow_b200 import sp as SP
+        lay = SP.make_layout()
+        model.peer_max_seq, model.peer_max_last = 15488, 3840          # one peer arena for every shape of the 768p run
+        model.peer_max_vel_bytes = 16 * 96 * 160 * 4
+        model.set_parallel_layout(lay, exchange=args.exchange)
+    # CUDA-graph replay at every N: the peer-memory exchange is plain kernels (no NCCL call inside the step)
+    use_graph = not args.no_graph and not (world > 1 and args.exchange == "nccl")
     model.use_cuda_graph = use_graph
 
     host_ms = {}
@@ -335,15 +505,14 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.25)
     t0 = time.time()
-    ms_step, launches = timed(step_resident, args.steps, events=not use_graph)
+    ms_step, launches = timed(step_resident, args.steps, events=False)
     host_enqueue_ms = host_ms["last"]
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
-    ms_eager = ms_step
-    if use_graph:
-        # the timed region above replayed the captured graph (no per-launch events possible); the dominant kernel's launch
-        # durations come from the same number of host-launched steps run right after it, CUDA events around each launch
-        ms_eager, _ = timed(step_resident, args.steps, events=True)
+    # the timed region above carries no per-launch instrumentation (graph replay, or plain host launches with --no-graph);
+    # the dominant kernel's launch durations come from the same number of host-launched steps run right after it, with CUDA
+    # events around each attention launch
+    ms_eager, _ = timed(step_resident, args.steps, events=True)
     # dominant kernel: the masked attention; per-launch duration from CUDA events recorded around each launch
     ev = model.attn_events or []
     model.attn_events = None
@@ -367,6 +536,23 @@ def run_ours(args):
     model.timer.enabled = False
     model.attn_events = None
 
+    parity_vs_n1 = None
+    if parity_ref is not None:
+        parity_vs_n1 = (step_resident().float() - parity_ref).abs().max().item()       # graph-replayed sharded step
+        tt = torch.tensor([parity_vs_n1], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        parity_vs_n1 = float(tt.item())
+        del parity_ref
+
+    vae_leg = None if args.no_vae else vae_decode_leg(dev, world, rank)
+    video_leg = None if args.no_video else video_e2e_leg(model, dev, world, rank)
+    eager_leg = None
+    if world == 1 and not args.no_eager:
+        model._graphs.clear()
+        model._ws.clear()
+        torch.cuda.empty_cache()
+        eager_leg = gpu_eager_reference(dev, host)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -385,17 +571,21 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": b, "seq_len": plan.seq,
                    "parallelism": ("single GPU" if world == 1 else
                                    f"cfg{lay.cfg_ways} x sp{lay.sp}: CFG pair split first, then Ulysses sequence parallel "
-                                   f"(heads 30 -> {model._hp}, one NCCL all-to-all each side of attention)"),
+                                   f"(heads 30 -> {model._hp}); exchange = " +
+                                   ("remote stores fused into the QKV-GEMM / attention epilogues over NVLink peer memory + "
+                                    "flag barriers, no NCCL call in the step" if args.exchange == "peer" else
+                                    "NCCL all_to_all_single each side of attention")),
                    "layers": list(args.layers), "l2": "per-step working set (>1.5 GB of activations + 3.9 GB weights) exceeds the 126 MB L2; no explicit flush",
                    "step_tflop": {"gemm": fl["gemm"] / 1e12, "attention_masked": fl["attention"] / 1e12},
                    "step_tflops_achieved": (fl["gemm"] + fl["attention"]) / (ms_step * 1e-3) / 1e12,
-                   "launch_mode": ("CUDA graph replay of the step's launch sequence (captured once in warm-up); roofline "
-                                   "launch durations from the host-launched steps timed right after"
-                                   if use_graph else "host-launched (one C-ABI call per kernel)"),
+                   "launch_mode": ("CUDA graph replay of the step's launch sequence (captured once in warm-up), no per-launch "
+                                   "instrumentation in the timed region; roofline launch durations from the host-launched "
+                                   "steps timed right after"
+                                   if use_graph else "host-launched (one C-ABI call per kernel), no per-launch instrumentation"),
                    "ms_per_step_host_launched": ms_eager,
                    # host wall time to enqueue one step of the timed region (rank 0): close to ms_per_step = launch-bound
                    "host_enqueue_ms_per_step": host_enqueue_ms,
@@ -405,15 +595,17 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "B200FluxTransformer.__call__(sample=[clips], timestep_ratio, encoder_hidden_states, encoder_attention_mask, pooled_projections) with pinned host inputs, result copied back to host"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "pf::attn_fwd_kernel (masked joint attention, tcgen05)", "bound": "tensor",
+        "parity_vs_n1": parity_vs_n1,
+        "vae_decode": vae_leg, "video_e2e": video_leg, "gpu_eager_baseline": eager_leg,
+        "roofline": {"kernel": "pf::attn2_fwd_kernel (masked joint attention, two q tiles per CTA, tcgen05)", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                      "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
                      "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg,
                      "share_of_step": (attn_avg * n_attn / ms_eager) if ms_eager else None,
                      "algorithmic_flops_per_launch": attn_flops_launch,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
-                     # shape (profiles/r01_attn_v2_ncu.txt: 357.3 MB + 103.9 MB) = the algorithmic Q+K+V+O bytes
-                     "traffic": 461.2e6 if lay is None else None, "traffic_unit": "B/launch",
+                     # shape (profiles/r02_attn2_ncu.txt) -- the algorithmic bytes are Q+K+V+O
+                     "traffic": ATTN_TRAFFIC_BYTES if lay is None else None, "traffic_unit": "B/launch",
                      "algorithmic_bytes_per_launch": 4.0 * b * plan.seq * cfg.inner_dim * 2},
     }
     if args.no_cpu:
@@ -436,6 +628,10 @@ def main():
     ap.add_argument("--layers", type=int, nargs=2, default=[8, 16], help="(debug) double/single block counts")
     ap.add_argument("--no-cpu", action="store_true", help="(debug) skip the CPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="(debug) launch every kernel from the host instead of replaying the captured CUDA graph")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: peer-memory fused exchange (default) or NCCL all-to-all (A/B)")
+    ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
+    ap.add_argument("--no-video", action="store_true", help="skip the 768p/10s end-to-end sampler + decode leg (~1 min at N=1)")
+    ap.add_argument("--no-eager", action="store_true", help="skip the reference-eager-on-GPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,6 +36,29 @@ PF_API int pf_warmup(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 PF_API int64_t pf_launch_count(void);
 
+/* ------------------------------------------------------------------ peer memory (sequence parallel over NVLink / NVSwitch)
+ * Replaces the reference's all-to-all at the attention boundary (trainer_misc/communicate.py:7-24, called at
+ * modeling_flux_block.py:285-295, 314-321, 535-560) and its contiguous()/cat copies: producers store straight into the owning
+ * rank's buffer through mapped peer pointers (pf_gemm_desc.peer_qkv, pf_attn_desc.peer_out); pf_peer_barrier orders those
+ * stores against their consumers.  One process per GPU on one node; buffers come from pf_peer_alloc (cudaMalloc + CUDA IPC). */
+#define PF_MAX_PEERS 8
+typedef struct PfPeerGroup {
+  void* ptr[PF_MAX_PEERS]; /* one mapped pointer per group member (ptr[my_index] = the local buffer) */
+  int32_t n;               /* members */
+  int32_t my_index;
+} PfPeerGroup;
+PF_API int pf_peer_alloc(int64_t bytes, void** ptr);   /* zero-filled device memory that peers can map */
+PF_API int pf_peer_free(void* ptr);
+PF_API int pf_peer_export(void* ptr, void* handle64);  /* 64-byte CUDA IPC handle of a pf_peer_alloc buffer */
+PF_API int pf_peer_open(const void* handle64, void** peer_ptr);
+PF_API int pf_peer_close(void* peer_ptr);
+/* Barrier over the group: grp->ptr[i] = member i's flag array (PF_MAX_PEERS uint32, zero-initialised, peer memory);
+ * epoch_counter = one uint32 in local device memory, advanced by the kernel (graph-replay safe).  Everything this rank's
+ * earlier kernels stored to peers is visible to a peer's kernels launched after ITS matching barrier. */
+PF_API int pf_peer_barrier(const PfPeerGroup* grp, uint32_t* epoch_counter, void* stream);
+/* dst->ptr[i][dst_offset_bytes ...] = src[0 .. bytes) for every member (16-byte granularity). */
+PF_API int pf_peer_bcast(const PfPeerGroup* dst, const void* src, int64_t bytes, int64_t dst_offset_bytes, void* stream);
+
 /* ------------------------------------------------------------------ GEMM (tcgen05 + TMA)
  * out = epilogue(A[rows, K] . W[N, K]^T + bias).  bf16 operands, fp32 accumulation in TMEM.
  * Replaces every nn.Linear on the DiT path: x_embedder/context_embedder F:290,F:401; to_q/k/v, add_*_proj B:816-835;
@@ -83,6 +106,11 @@ typedef struct pf_gemm_desc {
   int32_t n_split; /* QKV_GELU: first n_split (=3*H*hd) columns are q|k|v */
   int32_t kernel_variant; /* 0 = auto (measured policy); 1 = force 1-CTA tiles; 2 = force 2-CTA (cta_group::2) tiles.
                            * Same bits either way (same K order); exists so tests can pin each kernel. */
+  /* QKV_ROPE under sequence parallelism (peer_count > 1): head h of this rank's token chunk is stored into rank
+   * (h / peer_heads)'s buffer peer_qkv[h / peer_heads], laid out [3 (q,k,v)][peer_heads][peer_seq][head_dim], at sequence
+   * position peer_row0 + (out_row_begin + m).  q_out/k_out/v_out are ignored.  batches must be 1. */
+  void* peer_qkv[PF_MAX_PEERS];
+  int32_t peer_count, peer_heads, peer_seq, peer_row0;
 } pf_gemm_desc;
 
 PF_API int pf_gemm_bf16(const pf_gemm_desc* desc, void* stream);
@@ -110,6 +138,11 @@ typedef struct pf_attn_desc {
                               * needs the current clip's rows only (history outputs are discarded, reference F:380). */
   const int32_t* pair_sched; /* device; built by pf_attn_build_pair_schedule from tile_sched, same sched_stride.  When set (and
                               * variant does not ask for the one-tile kernel) the launch uses the two-q-tiles-per-CTA kernel. */
+  /* sequence parallelism (peer_count > 1, batch 1, two-q-tile kernel): row q of this rank's head group is stored into rank
+   * (q / peer_chunk_rows)'s buffer peer_out[...] at row q % peer_chunk_rows, columns peer_col_begin + h*64 (row stride ldo);
+   * `out` is ignored. */
+  void* peer_out[PF_MAX_PEERS];
+  int32_t peer_count, peer_chunk_rows, peer_col_begin;
 } pf_attn_desc;
 
 /* Host helper: from host copies of seg/time ids builds, for each (batch, 128-row q tile), the list of 128-wide kv

@@ -19,6 +19,7 @@ SYMBOLS = [
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step",
     "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent",
+    "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close", "pf_peer_barrier", "pf_peer_bcast",
     "pf_debug_umma",
     "pf_debug_attn_trace",
     "pf_debug_attn_cta_trace",
@@ -41,6 +42,8 @@ class GemmDesc(C.Structure):
         ("norm_eps", C.c_float),
         ("heads", C.c_int32), ("head_dim", C.c_int32), ("seq_len", C.c_int32),
         ("n_split", C.c_int32), ("kernel_variant", C.c_int32),
+        ("peer_qkv", C.c_void_p * 8),
+        ("peer_count", C.c_int32), ("peer_heads", C.c_int32), ("peer_seq", C.c_int32), ("peer_row0", C.c_int32),
     ]
 
 
@@ -52,7 +55,13 @@ class AttnDesc(C.Structure):
         ("seg", C.c_void_p), ("time", C.c_void_p), ("tile_sched", C.c_void_p),
         ("sched_stride", C.c_int32), ("variant", C.c_int32), ("q_row_begin", C.c_int32),
         ("pair_sched", C.c_void_p),
+        ("peer_out", C.c_void_p * 8),
+        ("peer_count", C.c_int32), ("peer_chunk_rows", C.c_int32), ("peer_col_begin", C.c_int32),
     ]
+
+
+class PeerGroup(C.Structure):
+    _fields_ = [("ptr", C.c_void_p * 8), ("n", C.c_int32), ("my_index", C.c_int32)]
 
 
 class ConvDesc(C.Structure):
@@ -103,6 +112,13 @@ def load() -> C.CDLL:
     lib.pf_attn_fwd_masked.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     lib.pf_attn_build_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.pf_attn_build_pair_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.pf_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+    lib.pf_peer_free.argtypes = [C.c_void_p]
+    lib.pf_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pf_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.pf_peer_close.argtypes = [C.c_void_p]
+    lib.pf_peer_barrier.argtypes = [C.POINTER(PeerGroup), C.c_void_p, C.c_void_p]
+    lib.pf_peer_bcast.argtypes = [C.POINTER(PeerGroup), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.pf_ln_modulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
     lib.pf_small_linear.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,

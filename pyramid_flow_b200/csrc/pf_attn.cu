@@ -549,7 +549,7 @@ extern "C" int pf_attn_build_schedule(const int32_t* seg, const int32_t* time, i
 extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   using namespace pf;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PF_REQUIRE(d && d->q && d->k && d->v && d->out && d->seg && d->time && d->tile_sched, "pf_attn_fwd_masked: null pointer");
+  PF_REQUIRE(d && d->q && d->k && d->v && (d->out || d->peer_count > 1) && d->seg && d->time && d->tile_sched, "pf_attn_fwd_masked: null pointer");
   PF_REQUIRE(d->head_dim == ATT_HD, "pf_attn_fwd_masked: head_dim %d unsupported (64 only)", d->head_dim);
   PF_REQUIRE(d->batch > 0 && d->heads > 0 && d->seq > 0, "pf_attn_fwd_masked: bad shape");
   const int q_tiles = (d->seq + ATT_BM - 1) / ATT_BM;
@@ -557,11 +557,14 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   PF_REQUIRE(d->q_row_begin >= 0 && d->q_row_begin % ATT_BM == 0 && d->q_row_begin < d->seq,
              "pf_attn_fwd_masked: q_row_begin %d must be a multiple of %d inside the sequence", d->q_row_begin, ATT_BM);
   PF_REQUIRE(d->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pf_attn_fwd_masked: out must be 16-byte aligned");
+  PF_REQUIRE(d->peer_count <= 1 || d->pair_sched != nullptr, "pf_attn_fwd_masked: peer stores need the two-q-tile kernel (pair_sched)");
 
   // variant: 0 = default (two-q-tile kernel when a pair schedule is given, else the one-tile kernel); 0x10 | k = two-q-tile
   // kernel with k of every 4 exponential pairs on the FMA pipe (k = 0..3); 1 / 2 / 3 = one-tile kernel (polynomial mix / clock
   // trace / plain)
-  if ((d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr)) {
+  const bool use_pair = (d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr);
+  PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
+  if (use_pair) {
     PF_REQUIRE(d->pair_sched != nullptr, "pf_attn_fwd_masked: variant 0x%x needs pair_sched", d->variant);
     const int poly = (d->variant & 0x10) ? (d->variant & 0xf) : ATT2_DEFAULT_POLY;
     PF_REQUIRE(poly >= 0 && poly <= 3, "pf_attn_fwd_masked: bad polynomial share %d", poly);

@@ -48,6 +48,9 @@ struct Attn2Args {
   const int* time;
   const int* psched;
   int sched_stride;
+  // sequence parallel: output rows go straight into the owning rank's buffer (pf_b200.h)
+  __nv_bfloat16* peer_out[PF_MAX_PEERS];
+  int peer_count, peer_chunk_rows, peer_col_begin;
 };
 
 // ---- packed fp32x2 helpers (sm_100: FFMA2 / FADD2) -------------------------------------------------------------------
@@ -414,7 +417,13 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_wait(&bar_pv_done[X], (n_kv - 1) & 1);
       tc_fence_after();
       const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
-      __nv_bfloat16* dst = a.out + (static_cast<size_t>(b) * a.seq + qpos) * a.ldo + h * A2_HD;
+      __nv_bfloat16* dst;
+      if (a.peer_count > 1) {
+        const int r = min(qpos / a.peer_chunk_rows, a.peer_count - 1);
+        dst = a.peer_out[r] + static_cast<size_t>(qpos - r * a.peer_chunk_rows) * a.ldo + a.peer_col_begin + h * A2_HD;
+      } else {
+        dst = a.out + (static_cast<size_t>(b) * a.seq + qpos) * a.ldo + h * A2_HD;
+      }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t o[32];
@@ -486,6 +495,23 @@ int attn2_launch(const pf_attn_desc* d, int poly, cudaStream_t stream) {
   a.time = d->time;
   a.psched = d->pair_sched;
   a.sched_stride = d->sched_stride;
+  a.peer_count = d->peer_count;
+  a.peer_chunk_rows = d->peer_chunk_rows;
+  a.peer_col_begin = d->peer_col_begin;
+  for (int i = 0; i < PF_MAX_PEERS; ++i) a.peer_out[i] = static_cast<__nv_bfloat16*>(d->peer_out[i]);
+  if (d->peer_count > 1) {
+    if (d->batch != 1 || d->peer_count > PF_MAX_PEERS || d->peer_chunk_rows <= 0 ||
+        static_cast<long long>(d->peer_chunk_rows) * d->peer_count < d->seq || d->peer_col_begin % 8 != 0) {
+      set_error("pf_attn_fwd_masked: bad peer layout (batch %d, count %d, chunk rows %d, seq %d)", d->batch, d->peer_count,
+                d->peer_chunk_rows, d->seq);
+      return -1;
+    }
+    for (int i = 0; i < d->peer_count; ++i)
+      if (d->peer_out[i] == nullptr) {
+        set_error("pf_attn_fwd_masked: peer_out[%d] is null", i);
+        return -1;
+      }
+  }
   // pair p covers tiles q_tiles-2-2p and q_tiles-1-2p: launch the pairs whose upper tile is >= q_tile_begin
   const int pairs = (a.q_tiles - a.q_tile_begin + 1) / 2;
   dim3 grid(pairs, d->heads, d->batch);

@@ -39,6 +39,9 @@ struct GemmArgs {
   float norm_eps;
   int heads, head_dim, seq_len;
   int n_split;
+  // sequence parallel: q/k/v heads go straight into the owning rank's [3][peer_heads][peer_seq][64] buffer (pf_b200.h)
+  __nv_bfloat16* peer_qkv[PF_MAX_PEERS];
+  int peer_count, peer_heads, peer_seq, peer_row0;
 };
 
 constexpr int BM = 128;
@@ -144,7 +147,13 @@ __device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t ta
     }
   }
   if (valid) {
-    __nv_bfloat16* dst = base + ((static_cast<size_t>(b) * g.heads + head) * g.seq_len + pos) * 64;
+    __nv_bfloat16* dst;
+    if (g.peer_count > 1) {
+      const int r = head / g.peer_heads, hl = head - r * g.peer_heads;
+      dst = g.peer_qkv[r] + ((static_cast<size_t>(section) * g.peer_heads + hl) * g.peer_seq + g.peer_row0 + pos) * 64;
+    } else {
+      dst = base + ((static_cast<size_t>(b) * g.heads + head) * g.seq_len + pos) * 64;
+    }
     float lo[32], hi[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -679,6 +688,18 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   g.head_dim = d->head_dim;
   g.seq_len = d->seq_len;
   g.n_split = d->n_split;
+  g.peer_count = d->peer_count;
+  g.peer_heads = d->peer_heads;
+  g.peer_seq = d->peer_seq;
+  g.peer_row0 = d->peer_row0;
+  for (int i = 0; i < PF_MAX_PEERS; ++i) g.peer_qkv[i] = static_cast<__nv_bfloat16*>(d->peer_qkv[i]);
+  if (d->peer_count > 1) {
+    PF_REQUIRE(epi == PF_EPI_QKV_ROPE && d->batches == 1, "pf_gemm_bf16: peer stores need the QKV_ROPE epilogue and batches == 1");
+    PF_REQUIRE(d->peer_count <= PF_MAX_PEERS && d->peer_heads > 0 && d->peer_heads * d->peer_count >= d->heads &&
+                   d->peer_row0 >= 0 && d->peer_row0 + d->out_row_begin + d->row_count <= d->peer_seq,
+               "pf_gemm_bf16: bad peer layout (count %d heads/rank %d seq %d row0 %d)", d->peer_count, d->peer_heads, d->peer_seq, d->peer_row0);
+    for (int i = 0; i < d->peer_count; ++i) PF_REQUIRE(d->peer_qkv[i] != nullptr, "pf_gemm_bf16: peer_qkv[%d] is null", i);
+  }
 
   // 2-CTA tiles (256 x BN, cta_group::2) pay off for 256-wide tiles and for short-K 192-wide ones (measured A/B on
   // B200: +11 % at N=7680/K=1920, -1..3 % at N=1920/K>=7680); kernel_variant 1/2 pins the 1-CTA / 2-CTA kernel

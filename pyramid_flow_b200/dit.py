@@ -350,9 +350,16 @@ class B200FluxTransformer(torch.nn.Module):
         return plan
 
     # -- parallel layout (CFG x sequence parallel, sp.py) ---------------------------------------------------------------
-    def set_parallel_layout(self, layout) -> None:
-        """Attach a `sp.ParallelLayout` (after torch.distributed is initialised); weights are replicated."""
+    def set_parallel_layout(self, layout, exchange: str = "peer") -> None:
+        """Attach a `sp.ParallelLayout` (after torch.distributed is initialised); weights are replicated.
+        exchange = "peer": q/k/v and the attention output cross NVLink as remote stores fused into the QKV GEMM / attention
+        epilogues + flag barriers (csrc/pf_peer.cu): no NCCL call in the step, CUDA-graph capturable.  "nccl": the
+        all_to_all_single formulation (kept for A/B measurements)."""
+        assert exchange in ("peer", "nccl")
         self.layout = layout
+        self.exchange = exchange
+        self._px = None
+        self._graphs.clear()
         self._ws.clear()
         hn = self.cfg.num_attention_heads
         from .sp import padded_heads
@@ -371,6 +378,27 @@ class B200FluxTransformer(torch.nn.Module):
                 blk["w_out_p"] = padk(blk["w_out"])
             self._padded = True
 
+    def _peer_exchange(self, plan: SeqPlan, hp: int, ldc: int):
+        """The peer arena (sp.PeerExchange), (re)built collectively when a call needs more room than it has.  Every rank sees
+        the same shapes, so every rank takes the same decision."""
+        from . import sp as SP
+        c = self.cfg
+        ct, chh, cww = plan.clip_thw[-1]
+        vel_bytes = (c.in_channels // 4) * ct * chh * 2 * cww * 2 * 4
+        px = getattr(self, "_px", None)
+        if (px is None or plan.seq > px.max_seq or plan.last_tokens > px.max_last or vel_bytes > px.vel_bytes
+                or px.ldc != ldc):
+            if px is not None:
+                torch.cuda.synchronize()
+                torch.distributed.barrier()
+                self._graphs.clear()            # captured launches point into the old arena
+                px.close()
+            cap = max(plan.seq, getattr(self, "peer_max_seq", 0))
+            last = max(plan.last_tokens, getattr(self, "peer_max_last", 0))
+            px = SP.PeerExchange(self.layout, cap, hp, ldc, c.in_channels, last, max(vel_bytes, getattr(self, "peer_max_vel_bytes", 0)))
+            self._px = px
+        return px
+
     # -- the step ------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, sample, timestep_ratio=None, encoder_hidden_states=None, encoder_attention_mask=None,
@@ -379,10 +407,10 @@ class B200FluxTransformer(torch.nn.Module):
         assert len(sample) == 1, "inference passes one stage per call (pipeline P:760-766)"
         clips = sample[0] if isinstance(sample[0], (list, tuple)) else [sample[0]]
         lay = getattr(self, "layout", None)
-        # single-GPU layout only: capturing the NCCL all-to-alls of the CFG x SP layout hung on the 2-GPU box (round 1),
-        # so the parallel step stays host-launched
-        if (self.use_cuda_graph and not (lay is not None and lay.enabled) and not self.timer.enabled
-                and self.attn_events is None):
+        # the NCCL formulation of the parallel step stays host-launched (capturing its all-to-alls hung on the 2-GPU box in
+        # round 1); the peer-memory formulation is plain kernels and is captured like the single-GPU step
+        nccl_par = lay is not None and lay.enabled and getattr(self, "exchange", "peer") == "nccl"
+        if self.use_cuda_graph and not nccl_par and not self.timer.enabled and self.attn_events is None:
             return self._forward_graphed(list(clips), timestep_ratio, encoder_hidden_states, encoder_attention_mask,
                                          pooled_projections)
         return self._forward_eager(clips, timestep_ratio, encoder_hidden_states, encoder_attention_mask,
@@ -407,7 +435,17 @@ class B200FluxTransformer(torch.nn.Module):
             def run():
                 return self._forward_eager(static[:nclip], static[nclip], static[nclip + 1], mask, static[nclip + 2])[0]
 
-            self._workspace(clips[-1].shape[0], plan)          # allocate outside the capture (ordinary allocator pool)
+            # allocate outside the capture (ordinary allocator pool); the parallel layout also (re)builds its peer arena here,
+            # a collective that must not happen inside stream capture
+            lay = getattr(self, "layout", None)
+            if lay is not None and lay.enabled:
+                from . import sp as SP
+                c0, c1 = SP.chunk_bounds(plan.seq, lay.sp, lay.sp_rank)
+                self._workspace(1, plan, c1 - c0, self._hp)
+                if getattr(self, "exchange", "peer") == "peer":
+                    self._peer_exchange(plan, self._hp, self._hp * 64 + 4 * self.cfg.inner_dim)
+            else:
+                self._workspace(clips[-1].shape[0], plan)
             # Nothing host-side may initialise inside stream capture: `_lib.require_device()` has already loaded every kernel
             # instantiation and set its shared-memory attribute on this device (pf_warmup), so a new shape that
             # dispatches to a not-yet-used template instantiation is safe to capture; the first capture of the process
@@ -468,6 +506,11 @@ class B200FluxTransformer(torch.nn.Module):
         h, xn, q, k, v, cat, mod = ws["h"], ws["xn"], ws["q"], ws["k"], ws["v"], ws["cat"], ws["mod"]
         nm = self.n_mod
         ldc = wa + 4 * d
+        # peer-memory formulation of the exchanges (sp.PeerExchange): `cat` and the gathered q/k/v live in the peer arena
+        px = self._peer_exchange(plan, hp, ldc) if (par and getattr(self, "exchange", "peer") == "peer") else None
+        if px is not None and nsp > 1:
+            cat = px.cat(sl)
+            qkv_x = px.qkv(s)                          # [3, Hg, S, 64]: my head group over the whole sequence
         rope = plan.rope[c0:c1]
         # local (row_begin, row_count) of the text / video ranges inside this rank's chunk, and their global starts
         tb, te = max(0, c0), min(t_len, c1)
@@ -509,19 +552,26 @@ class B200FluxTransformer(torch.nn.Module):
                     ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=sl,
                                     row_begin=r0, row_count=rc)
 
+        peer_qkv = None
+        if px is not None and nsp > 1:
+            # QKV epilogue stores head h of my rows into rank (h // Hg)'s gathered buffer at sequence position c0 + row
+            peer_qkv = dict(peer_ptrs=[pp + px.off_qkv for pp in px.sp_buf.ptrs], peer_heads=hp // nsp, peer_seq=s, peer_row0=c0)
+
         def qkv(wq, bq, nq, nk, r0, rc):
             if rc > 0:
                 with T("gemm_qkv"):
                     ops.gemm(xn, wq, bq, PF_EPI_QKV_ROPE, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc,
                              q_out=q, k_out=k, v_out=v, rope=rope, q_norm_w=nq, k_norm_w=nk, heads=hn, head_dim=64,
-                             seq_len=sl)
+                             seq_len=sl, peer=peer_qkv)
 
         scale = 1.0 / math.sqrt(64)
         seg, tim, sched, sched2 = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b], plan.sched2[b0:b0 + b]
         av = self.attn_variant
 
         def exchange_begin():
-            return SP.heads_to_sequence_qkv_begin(q[0], k[0], v[0], lay) if nsp > 1 else None
+            if nsp > 1 and px is None:
+                return SP.heads_to_sequence_qkv_begin(q[0], k[0], v[0], lay)
+            return None
 
         def attention(pending=None, q_row_begin=0):
             ev = self.attn_events is not None
@@ -533,6 +583,20 @@ class B200FluxTransformer(torch.nn.Module):
                 ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale, variant=av, q_row_begin=q_row_begin, pair_sched=sched2)
                 if ev:
                     e1.record()
+            elif px is not None:
+                # every rank's QKV epilogue has stored into every rank's gathered buffer: order those stores before the reads;
+                # the attention epilogue then stores each token chunk's rows straight into its owner's `cat`; the second
+                # barrier orders those stores before the projections that read `cat`
+                px.barrier_sp()
+                if ev:
+                    e0.record()
+                ops.attn_fwd(qkv_x[0][None], qkv_x[1][None], qkv_x[2][None], None, seg, tim, sched, scale, variant=av,
+                             pair_sched=sched2, ldo=ldc,
+                             peer=dict(peer_ptrs=[pp + px.off_cat for pp in px.sp_buf.ptrs], peer_chunk_rows=sl,
+                                       peer_col_begin=lay.sp_rank * (hp // nsp) * 64))
+                if ev:
+                    e1.record()
+                px.barrier_sp()
             else:
                 # Ulysses exchange: all (padded) heads of my token chunk -> my head group over the whole sequence
                 qf, kf, vf = SP.heads_to_sequence_qkv_end(pending if pending is not None else exchange_begin())
@@ -599,14 +663,22 @@ class B200FluxTransformer(torch.nn.Module):
         o = self.mod_off["norm_out"]
         g0, g1 = max(s - n_last, c0), c1                 # my part of the last n_last tokens
         head = ws["head"]
-        if par and nsp > 1:
+        peer_head = px is not None and nsp > 1
+        if peer_head:
+            head = px.head(n_last)                    # peer arena: every sp rank publishes its rows to every sp rank
+        elif par and nsp > 1:
             head.zero_()
         if g1 > g0:
             lnmod(o + d, o, g0 - c0, g1 - g0)
             ops.gemm(xn, self.w_out, self.b_out, PF_EPI_STORE_F32, batches=b, rows_per_batch=sl, row_begin=g0 - c0,
                      row_count=g1 - g0, out=head, ldo=c.in_channels, out_batch_rows=n_last,
                      out_row_begin=g0 - (s - n_last))
-        if par and nsp > 1:
+            if peer_head:
+                r0h = g0 - (s - n_last)
+                px.bcast(px.sp_buf, head[0, r0h:r0h + (g1 - g0)], px.off_head + r0h * c.in_channels * 4)
+        if peer_head:
+            px.barrier_sp()
+        elif par and nsp > 1:
             torch.distributed.all_reduce(head, group=lay.sp_group)       # disjoint row blocks: sum == gather
         ct, chh, cww = plan.clip_thw[-1]
         odt = clips[-1].dtype if clips[-1].dtype in (torch.float32, torch.bfloat16) else torch.float32
@@ -614,7 +686,14 @@ class B200FluxTransformer(torch.nn.Module):
             odt = torch.float32
         out = torch.empty(b, c.in_channels // 4, ct, chh * 2, cww * 2, device=self.device, dtype=odt)
         ops.unpatchify(head, n_last, 0, out)
-        if par:
+        if par and px is not None:
+            # [uncond ; cond]: the first sp rank of each branch publishes its velocity to every rank of the world
+            vel = px.vel((bg, *out.shape[1:]), odt)
+            if lay.sp_rank == 0:
+                px.bcast(px.world_buf, out.view(-1), px.w_off_vel + lay.cfg_rank * px.vel_bytes)
+            px.barrier_world()
+            out = vel.clone()
+        elif par:
             full = torch.empty(bg, *out.shape[1:], device=self.device, dtype=odt)
             torch.distributed.all_gather_into_tensor(full, out, group=lay.cfg_group)   # [uncond ; cond]
             out = full

@@ -24,7 +24,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
          out_row_begin: Optional[int] = None, out_col_begin: int = 0,
          gate: Optional[torch.Tensor] = None, gate_batch_stride: int = 0,
          q_out=None, k_out=None, v_out=None, rope=None, q_norm_w=None, k_norm_w=None, norm_eps: float = 1e-6,
-         heads: int = 0, head_dim: int = 0, seq_len: int = 0, n_split: int = 0, kernel_variant: int = 0) -> None:
+         heads: int = 0, head_dim: int = 0, seq_len: int = 0, n_split: int = 0, kernel_variant: int = 0,
+         peer: Optional[dict] = None) -> None:
     """epilogue(A . W^T + bias); see pf_gemm_bf16 in include/pf_b200.h for the addressing rules."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_cuda and w.is_cuda
     assert a.stride(-1) == 1 and w.is_contiguous()
@@ -59,6 +60,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogu
     d.norm_eps = norm_eps
     d.heads, d.head_dim, d.seq_len, d.n_split = heads, head_dim, seq_len, n_split
     d.kernel_variant = kernel_variant
+    if peer is not None:      # sequence parallel: QKV heads stored straight into the owning rank's buffer (pf_b200.h)
+        for i, pp in enumerate(peer["peer_ptrs"]):
+            d.peer_qkv[i] = pp
+        d.peer_count, d.peer_heads = len(peer["peer_ptrs"]), peer["peer_heads"]
+        d.peer_seq, d.peer_row0 = peer["peer_seq"], peer["peer_row0"]
     _lib.check(_lib.load().pf_gemm_bf16(C.byref(d), _lib.stream_ptr()), "pf_gemm_bf16")
 
 
@@ -152,14 +158,22 @@ def attn_build_pair_schedule(sched: torch.Tensor, seq: int) -> torch.Tensor:
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, seg: torch.Tensor,
              time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0, q_row_begin: int = 0,
-             pair_sched: Optional[torch.Tensor] = None) -> None:
+             pair_sched: Optional[torch.Tensor] = None, ldo: Optional[int] = None, peer: Optional[dict] = None) -> None:
     """q,k,v bf16 [B,H,S,64]; out bf16 [B,S,*] (row stride = out.stride(1)); seg/time/sched int32 on device.
     Only q rows >= q_row_begin (multiple of 128) are computed; other rows of `out` are left untouched."""
     assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
     b, h, s, hd = q.shape
     d = AttnDesc()
-    d.q, d.k, d.v, d.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
-    d.ldo = out.stride(-2)
+    d.q, d.k, d.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    if out is not None:
+        d.out = out.data_ptr()
+        d.ldo = out.stride(-2)
+    if ldo is not None:
+        d.ldo = ldo
+    if peer is not None:      # sequence parallel: output rows stored straight into the owning rank's buffer (pf_b200.h)
+        for i, pp in enumerate(peer["peer_ptrs"]):
+            d.peer_out[i] = pp
+        d.peer_count, d.peer_chunk_rows, d.peer_col_begin = len(peer["peer_ptrs"]), peer["peer_chunk_rows"], peer["peer_col_begin"]
     d.batch, d.heads, d.seq, d.head_dim = b, h, s, hd
     d.scale = scale
     d.seg, d.time, d.tile_sched = seg.data_ptr(), time.data_ptr(), sched.data_ptr()

@@ -44,16 +44,21 @@ for name, kw, clip_shapes, tlen in [
         if rank == 0:
             print(f"[sp_check] {name}: S={seq} not divisible by sp={lay.sp}, skipped")
         continue
-    model.set_parallel_layout(lay)
-    out = model(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask,
-                pooled_projections=pooled)[0].float()
-    torch.cuda.synchronize()
-    err = (out - ref).abs().max().item()
-    errs = [None] * world
-    dist.all_gather_object(errs, err)
-    if rank == 0:
-        print(f"[sp_check] {name}: world {world} = cfg {lay.cfg_ways} x sp {lay.sp} (heads {cfg.num_attention_heads} -> "
-              f"{SP.padded_heads(cfg.num_attention_heads, lay.sp)}), S={seq}: max|parallel - single| per rank = "
-              f"{['%.2e' % e for e in errs]}  |ref| mean {ref.abs().mean().item():.3f}", flush=True)
-    assert err < 2e-2, err
+    for exchange, graph in (("nccl", False), ("peer", False), ("peer", True)):
+        model.set_parallel_layout(lay, exchange=exchange)
+        model.use_cuda_graph = graph
+        worst = 0.0
+        for rep in range(3 if graph else 1):            # capture, then replays
+            out = model(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask,
+                        pooled_projections=pooled)[0].float()
+            torch.cuda.synchronize()
+            worst = max(worst, (out - ref).abs().max().item())
+        errs = [None] * world
+        dist.all_gather_object(errs, worst)
+        if rank == 0:
+            print(f"[sp_check] {name}: world {world} = cfg {lay.cfg_ways} x sp {lay.sp} (heads {cfg.num_attention_heads} -> "
+                  f"{SP.padded_heads(cfg.num_attention_heads, lay.sp)}), S={seq}, exchange={exchange}, graph={graph}: "
+                  f"max|parallel - single| per rank = {['%.2e' % e for e in errs]}  |ref| mean {ref.abs().mean().item():.3f}", flush=True)
+        assert worst < 2e-2, worst
+    model.use_cuda_graph = False
 dist.destroy_process_group()
