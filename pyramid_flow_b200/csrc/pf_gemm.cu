@@ -166,8 +166,13 @@ __device__ __forceinline__ void qkv_head_epilogue(const GemmArgs& g, uint32_t ta
 }
 
 // Epilogue of one 128-row accumulator slice: this thread owns output row `m` (TMEM lane), columns [n_base, n_base + BN).
+// `stage`: this warp's 32 x EPI_PITCH fp32 staging block in shared memory (GATE_RESID only): the accumulators arrive one
+// thread per ROW (TMEM lane); the read-modify-write of the fp32 residual stream is done transposed, 8 lanes per row
+// (4 rows x 128 contiguous bytes per warp instruction instead of 32 rows x 16 bytes).
+constexpr int EPI_PITCH = 36;   // floats per staged row: 16-byte aligned, conflict-free for quarter-warp float4 accesses
+
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int b, int m, int n_base) {
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int b, int m, int n_base, float* stage) {
   const bool valid = m < g.row_count;
   const size_t out_row = static_cast<size_t>(b) * g.out_batch_rows + g.out_row_begin + m;
   bool qkv_tile = (EPI == PF_EPI_QKV_ROPE);
@@ -210,21 +215,36 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
           for (int i = 0; i < 8; ++i) d4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
         }
       } else if (EPI == PF_EPI_GATE_RESID) {
-        if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
-                                                 g.out_col_begin + n0);
-          const float4* g4 = reinterpret_cast<const float4*>(g.gate + b * g.gate_batch_stride + n0);
+        const int lane = threadIdx.x & 31;
+        float4* st4 = reinterpret_cast<float4*>(stage + lane * EPI_PITCH);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 rr = d4[i];
-            const float4 gg = __ldg(g4 + i);
-            rr.x += gg.x * x[4 * i + 0];
-            rr.y += gg.y * x[4 * i + 1];
-            rr.z += gg.z * x[4 * i + 2];
-            rr.w += gg.w * x[4 * i + 3];
-            d4[i] = rr;
+        for (int i = 0; i < 8; ++i) st4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        __syncwarp();
+        const int c4 = lane & 7, rsub = lane >> 3;
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g.gate + b * g.gate_batch_stride + n0) + c4);
+        const int m0 = m - lane;                               // first row of this warp's 32-row slice
+        float* obase = reinterpret_cast<float*>(g.out) + g.out_col_begin + n0 + 4 * c4;
+        const size_t row0 = static_cast<size_t>(b) * g.out_batch_rows + g.out_row_begin + m0;
+        float4 acc4[8], res4[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {                       // all loads first: 8 independent 128-byte row segments in flight
+          const int rr = it * 4 + rsub;
+          acc4[it] = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + 4 * c4);
+          if (m0 + rr < g.row_count) res4[it] = *reinterpret_cast<const float4*>(obase + (row0 + rr) * g.ldo);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rsub;
+          if (m0 + rr < g.row_count) {
+            float4 r4 = res4[it];
+            r4.x += gg.x * acc4[it].x;
+            r4.y += gg.y * acc4[it].y;
+            r4.z += gg.z * acc4[it].z;
+            r4.w += gg.w * acc4[it].w;
+            *reinterpret_cast<float4*>(obase + (row0 + rr) * g.ldo) = r4;
           }
         }
+        __syncwarp();
       }
     }
   }
@@ -244,6 +264,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float epi_stage[EPI == PF_EPI_GATE_RESID ? 4 * 32 * EPI_PITCH : 4];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -349,7 +370,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      epilogue_tile<BN, EPI>(g, taddr, b, m, n_base);
+      epilogue_tile<BN, EPI>(g, taddr, b, m, n_base, epi_stage + (EPI == PF_EPI_GATE_RESID ? q * 32 * EPI_PITCH : 0));
       // all tcgen05.ld of this accumulator have completed (wait::ld above) -> hand the buffer back
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -401,6 +422,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float epi_stage[EPI == PF_EPI_GATE_RESID ? 4 * 32 * EPI_PITCH : 4];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -508,7 +530,7 @@ gemm2_bf16_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN, EPI>(g, taddr, b, m, n_base);
+      epilogue_tile<BN, EPI>(g, taddr, b, m, n_base, epi_stage + (EPI == PF_EPI_GATE_RESID ? q * 32 * EPI_PITCH : 0));
       tc_fence_before();
       if (leader) mbar_arrive(&tmem_empty_bar[acc]);
       else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
