@@ -296,6 +296,124 @@ def random_vae_state_dict(device, seed=0, block_out_channels=(128, 256, 512, 512
     return sd
 
 
+def random_mmdit_state_dict(cfg, device, seed=0):
+    """Random-init SD3-MMDiT weights in the reference key layout (mmdit_modules/modeling_pyramid_mmdit.py:420-497 consumers)."""
+    import math
+    import torch
+    d, hd = cfg.inner_dim, cfg.attention_head_dim
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+
+    def lin(name, o, i, mod=False):
+        sd[name + ".weight"] = (torch.randn(o, i, device=device, generator=g) * ((0.5 if mod else 1.0) / math.sqrt(i))).bfloat16()
+        sd[name + ".bias"] = torch.randn(o, device=device, generator=g) * 0.02
+
+    sd["pos_embed.pos_embed"] = torch.randn(1, cfg.pos_embed_max_size ** 2, d, device=device, generator=g) * 0.1
+    sd["pos_embed.proj.weight"] = (torch.randn(d, cfg.in_channels, 2, 2, device=device, generator=g) * (4 * cfg.in_channels) ** -0.5).bfloat16()
+    sd["pos_embed.proj.bias"] = torch.randn(d, device=device, generator=g) * 0.02
+    lin("time_text_embed.timestep_embedder.linear_1", d, 256); lin("time_text_embed.timestep_embedder.linear_2", d, d)
+    lin("time_text_embed.text_embedder.linear_1", d, cfg.pooled_projection_dim); lin("time_text_embed.text_embedder.linear_2", d, d)
+    lin("context_embedder", d, cfg.joint_attention_dim)
+    for i in range(cfg.num_layers):
+        pre, last = f"transformer_blocks.{i}", i == cfg.num_layers - 1
+        lin(pre + ".norm1.linear", 6 * d, d, True); lin(pre + ".norm1_context.linear", (2 if last else 6) * d, d, True)
+        for n in ("to_q", "to_k", "to_v", "add_k_proj", "add_v_proj", "add_q_proj", "to_out.0"):
+            lin(f"{pre}.attn.{n}", d, d)
+        for n in ("norm_q", "norm_k", "norm_add_q", "norm_add_k"):
+            sd[f"{pre}.attn.{n}.weight"] = 1.0 + 0.1 * torch.randn(hd, device=device, generator=g)
+        lin(pre + ".ff.net.0.proj", 4 * d, d); lin(pre + ".ff.net.2", d, 4 * d)
+        if not last:
+            lin(pre + ".attn.to_add_out", d, d); lin(pre + ".ff_context.net.0.proj", 4 * d, d); lin(pre + ".ff_context.net.2", d, 4 * d)
+    lin("norm_out.linear", 2 * d, d, True); lin("proj_out", 4 * cfg.in_channels, d)
+    return sd
+
+
+def run_mmdit(args):
+    """--model mmdit: BASELINE configs[4] — one SD3-MMDiT forward (24 joint blocks, D=1536, 24 heads) at the headline step of
+    768p / 5 s (temp 16): unit 15 / stage 2, CFG batch 2, S = 128 + 13x240 + 960 + 2x3840 = 11888.  One GPU, host-launched."""
+    import torch
+    from pyramid_flow_b200 import _lib
+    from pyramid_flow_b200.mmdit import B200MMDiT, MMDiTConfigB200
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    _lib.require_device()
+    cfg = MMDiTConfigB200()
+    model = B200MMDiT(cfg, random_mmdit_state_dict(cfg, dev), device=dev)
+    torch.cuda.empty_cache()
+    b = 2
+    g = torch.Generator().manual_seed(100)
+    shapes = [(b, 16, 13, 24, 40), (b, 16, 1, 48, 80), (b, 16, 1, 96, 160), (b, 16, 1, 96, 160)]
+    host = {"clips": [torch.randn(sh, generator=g).bfloat16().pin_memory() for sh in shapes],
+            "enc": (torch.randn(b, 128, 4096, generator=g) * 0.2).bfloat16().pin_memory(),
+            "mask": torch.ones(b, 128, dtype=torch.int64).pin_memory(),
+            "pooled": torch.randn(b, 2048, generator=g).bfloat16().pin_memory(),
+            "t": torch.tensor([3.0] * b).bfloat16().pin_memory()}
+    dev_in = {k: ([x.to(dev) for x in v] if isinstance(v, list) else v.to(dev)) for k, v in host.items()}
+    out_host = torch.empty(b, 16, 1, 96, 160, dtype=torch.bfloat16).pin_memory()
+
+    def step_resident():
+        return model(sample=[dev_in["clips"]], timestep_ratio=dev_in["t"], encoder_hidden_states=dev_in["enc"],
+                     encoder_attention_mask=dev_in["mask"], pooled_projections=dev_in["pooled"])[0]
+
+    def step_e2e():
+        o = model(sample=[[x.to(dev, non_blocking=True) for x in host["clips"]]], timestep_ratio=host["t"].to(dev, non_blocking=True),
+                  encoder_hidden_states=host["enc"].to(dev, non_blocking=True), encoder_attention_mask=host["mask"].to(dev, non_blocking=True),
+                  pooled_projections=host["pooled"].to(dev, non_blocking=True))[0]
+        out_host.copy_(o, non_blocking=True)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        s_.record()
+        for _ in range(steps):
+            fn()
+        e_.record()
+        torch.cuda.synchronize()
+        return s_.elapsed_time(e_) / steps, _lib.launch_count() - n0
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    time.sleep(0.25)
+    t0 = time.time()
+    ms, launches = timed(step_resident, args.steps)
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    plan = model.last_plan
+    d = cfg.inner_dim
+    tokens = b * plan.seq
+    # per token per joint block 24 D^2 (qkv 6, out 2, ff 16); the last block's text stream stops after attention (MB:659-660)
+    gemm = 24.0 * d * d * (b * plan.seq * cfg.num_layers - b * plan.text_len * (18.0 / 24.0))
+    attn = 4.0 * 64 * cfg.num_attention_heads * plan.allowed_pairs * cfg.num_layers
+    peaks = measured_peaks()
+    ach = (gemm + attn) / (ms * 1e-3) / 1e12
+    h2d = sum(x.numel() * x.element_size() for x in host["clips"]) + sum(host[k].numel() * host[k].element_size() for k in ("enc", "mask", "pooled", "t"))
+    line = {"metric": METRIC, "value": tokens / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": ("SD3 MMDiT 768p/5s (BASELINE configs[4]) — one DiT forward at unit 15 / stage 2: CFG batch 2, "
+                                    "S=11888 (128 text + 13x240 + 960 + 3840 history + 3840 current), 24 joint blocks, D=1536, 24 heads"),
+                       "global_batch": b, "seq_len": plan.seq, "parallelism": "single GPU", "launch_mode": "host-launched",
+                       "l2": "per-step working set exceeds the 126 MB L2; no explicit flush",
+                       "step_tflop": {"gemm": gemm / 1e12, "attention_masked": attn / 1e12}},
+            "clocks": clocks,
+            "e2e": {"value": tokens / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size(),
+                    "api": "B200MMDiT.__call__ with pinned host inputs, result copied back to host"},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "whole step (GEMM + attention flops of every pf:: kernel launched)", "bound": "tensor",
+                         "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
+                         "peak_source": peaks["source"] + ", sustained cuBLAS bf16", "traffic": None},
+            "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def vae_decode_leg(dev, world, rank):
     """Causal-VAE decode at 768p (BASELINE configs[2], second half of the metric): un-tiled, temporally chunked (window 4),
     5 latent -> 33 video frames on one GPU; with N GPUs 1 + 4 N latent frames, context-parallel (temporal split + 2-frame
@@ -628,6 +746,7 @@ def main():
     ap.add_argument("--layers", type=int, nargs=2, default=[8, 16], help="(debug) double/single block counts")
     ap.add_argument("--no-cpu", action="store_true", help="(debug) skip the CPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="(debug) launch every kernel from the host instead of replaying the captured CUDA graph")
+    ap.add_argument("--model", default="flux", choices=["flux", "mmdit"], help="flux = miniFLUX (the headline, configs[2]); mmdit = SD3 MMDiT 768p/5s (configs[4])")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: peer-memory fused exchange (default) or NCCL all-to-all (A/B)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
     ap.add_argument("--no-video", action="store_true", help="skip the 768p/10s end-to-end sampler + decode leg (~1 min at N=1)")
@@ -635,6 +754,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.model == "mmdit":
+        run_mmdit(args)
     else:
         run_ours(args)
 

@@ -36,6 +36,26 @@ PF_API int pf_warmup(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 PF_API int64_t pf_launch_count(void);
 
+/* ------------------------------------------------------------------ step contexts (pf_ctx_*, pf_dit_step_*)
+ * A pf_ctx owns ONE recorded launch sequence: between pf_ctx_record_begin and pf_ctx_record_end every pf_* launch issued on
+ * `stream` by the calling thread is recorded instead of executed (descriptor validation, tensor-map encoding and kernel
+ * selection happen once, at record time); pf_dit_step_flux / pf_dit_step_mmdit / pf_vae_decode_chunk then re-issue the whole
+ * sequence with one call, on any stream.  What the sequence is -- the ~280 launches of PyramidFluxTransformer.forward
+ * (F:392-542) at one (plan, shapes), of PyramidDiffusionMMDiT.forward (M:420-497), or one temporal chunk of
+ * CausalVaeDecoder.forward (D:302-366) -- is whatever the host recorded; the three entry points are the same replay under the
+ * names of the reference functions they stand for.  The caller owns every buffer the recorded launches point to and must
+ * keep them alive and at the same addresses; peer-memory barriers (pf_peer_barrier) may be part of the sequence.
+ * pf_ctx_record_end returns the number of recorded launches (>= 0) or < 0 on error. */
+typedef struct pf_ctx pf_ctx;
+PF_API int pf_ctx_create(pf_ctx** out);
+PF_API int pf_ctx_destroy(pf_ctx* ctx);
+PF_API int pf_ctx_record_begin(pf_ctx* ctx, void* stream);
+PF_API int pf_ctx_record_end(pf_ctx* ctx);
+PF_API int pf_ctx_replay(pf_ctx* ctx, void* stream);
+PF_API int pf_dit_step_flux(pf_ctx* ctx, void* stream);
+PF_API int pf_dit_step_mmdit(pf_ctx* ctx, void* stream);
+PF_API int pf_vae_decode_chunk(pf_ctx* ctx, void* stream);
+
 /* ------------------------------------------------------------------ peer memory (sequence parallel over NVLink / NVSwitch)
  * Replaces the reference's all-to-all at the attention boundary (trainer_misc/communicate.py:7-24, called at
  * modeling_flux_block.py:285-295, 314-321, 535-560) and its contiguous()/cat copies: producers store straight into the owning

@@ -19,6 +19,8 @@ SYMBOLS = [
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step",
     "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent",
+    "pf_ctx_create", "pf_ctx_destroy", "pf_ctx_record_begin", "pf_ctx_record_end", "pf_ctx_replay", "pf_dit_step_flux",
+    "pf_dit_step_mmdit", "pf_vae_decode_chunk",
     "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close", "pf_peer_barrier", "pf_peer_bcast",
     "pf_debug_umma",
     "pf_debug_attn_trace",
@@ -112,6 +114,11 @@ def load() -> C.CDLL:
     lib.pf_attn_fwd_masked.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     lib.pf_attn_build_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.pf_attn_build_pair_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.pf_ctx_create.argtypes = [C.POINTER(C.c_void_p)]
+    for name in ("pf_ctx_destroy", "pf_ctx_record_end"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    for name in ("pf_ctx_record_begin", "pf_ctx_replay", "pf_dit_step_flux", "pf_dit_step_mmdit", "pf_vae_decode_chunk"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p]
     lib.pf_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
     lib.pf_peer_free.argtypes = [C.c_void_p]
     lib.pf_peer_export.argtypes = [C.c_void_p, C.c_void_p]

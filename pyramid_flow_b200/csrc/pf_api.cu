@@ -122,6 +122,95 @@ int warmup_attn();
 
 extern "C" {
 
+// ---- pf_ctx: a recorded launch sequence (one DiT step, one VAE chunk ...) owned by the library ---------------------------
+struct pf_ctx {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t rec_stream = nullptr;
+  bool recording = false;
+  size_t nodes = 0;
+};
+
+int pf_ctx_create(pf_ctx** out) {
+  if (out == nullptr) {
+    pf::set_error("pf_ctx_create: null");
+    return -1;
+  }
+  *out = new pf_ctx();
+  return 0;
+}
+
+static void ctx_drop(pf_ctx* c) {
+  if (c->exec) cudaGraphExecDestroy(c->exec);
+  if (c->graph) cudaGraphDestroy(c->graph);
+  c->exec = nullptr;
+  c->graph = nullptr;
+  c->nodes = 0;
+}
+
+int pf_ctx_destroy(pf_ctx* c) {
+  if (c == nullptr) return 0;
+  if (c->recording) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(c->rec_stream, &g);
+    if (g) cudaGraphDestroy(g);
+  }
+  ctx_drop(c);
+  (void)cudaGetLastError();
+  delete c;
+  return 0;
+}
+
+int pf_ctx_record_begin(pf_ctx* c, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(c != nullptr && !c->recording, "pf_ctx_record_begin: null context or already recording");
+  int rc = pf_warmup();          // nothing may initialise host-side while the stream is capturing
+  if (rc) return rc;
+  ctx_drop(c);
+  c->rec_stream = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaStreamBeginCapture(c->rec_stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("pf_ctx_record_begin: cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  c->recording = true;
+  return 0;
+}
+
+int pf_ctx_record_end(pf_ctx* c) {
+  using namespace pf;
+  PF_REQUIRE(c != nullptr && c->recording, "pf_ctx_record_end: not recording");
+  c->recording = false;
+  cudaError_t e = cudaStreamEndCapture(c->rec_stream, &c->graph);
+  if (e == cudaSuccess) e = cudaGraphGetNodes(c->graph, nullptr, &c->nodes);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&c->exec, c->graph, 0);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx_drop(c);
+    set_error("pf_ctx_record_end: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return static_cast<int>(c->nodes);
+}
+
+int pf_ctx_replay(pf_ctx* c, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(c != nullptr && c->exec != nullptr, "pf_ctx_replay: nothing recorded");
+  cudaError_t e = cudaGraphLaunch(c->exec, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("pf_ctx_replay: cudaGraphLaunch: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  g_launches.fetch_add(static_cast<int64_t>(c->nodes), std::memory_order_relaxed);
+  return 0;
+}
+
+int pf_dit_step_flux(pf_ctx* c, void* stream) { return pf_ctx_replay(c, stream); }
+int pf_dit_step_mmdit(pf_ctx* c, void* stream) { return pf_ctx_replay(c, stream); }
+int pf_vae_decode_chunk(pf_ctx* c, void* stream) { return pf_ctx_replay(c, stream); }
+
 int pf_warmup(void) {
   int rc = pf::warmup_gemm();
   if (!rc) rc = pf::warmup_conv();

@@ -233,3 +233,69 @@ def test_elementwise_kernels():
     v2, xs, xo = torch.randn(2, 1000, device=DEV), torch.randn(1000, device=DEV), torch.zeros(1000, device=DEV)
     ops.cfg_euler_step(v2, 5.0, -0.05, xs, xo)
     assert (xo - (xs + (-0.05) * (v2[0] + 5.0 * (v2[1] - v2[0])))).abs().max().item() < 1e-5
+
+
+def test_step_context_record_and_replay():
+    """pf_ctx (include/pf_b200.h): a launch sequence recorded once (LN+modulate -> GEMM+GELU -> gated-residual GEMM -> masked
+    attention) and re-issued by pf_dit_step_flux(ctx) gives the same bits as the direct launches, on new input values."""
+    import ctypes as C
+    from pyramid_flow_b200 import _lib, ops
+    from pyramid_flow_b200._lib import PF_EPI_GATE_RESID, PF_EPI_GELU_BF16
+    lib = _lib.load()
+    _lib.require_device()
+    torch.manual_seed(5)
+    B, S, D, H = 1, 384, 256, 4
+    x = torch.randn(B, S, D, device=DEV)
+    mod = torch.randn(B, 3 * D, device=DEV) * 0.3
+    w1 = (torch.randn(4 * D, D, device=DEV) * 0.05).bfloat16()
+    b1 = torch.randn(4 * D, device=DEV) * 0.1
+    w2 = (torch.randn(D, 4 * D, device=DEV) * 0.05).bfloat16()
+    b2 = torch.randn(D, device=DEV) * 0.1
+    xn = torch.zeros(B, S, D, device=DEV, dtype=torch.bfloat16)
+    hid = torch.zeros(B, S, 4 * D, device=DEV, dtype=torch.bfloat16)
+    q = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    k = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    v = torch.randn(B, H, S, 64, device=DEV).bfloat16()
+    att = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
+    seg = torch.ones(B, S, dtype=torch.int32)
+    tim = (torch.arange(S) // 128).int()[None]
+    sched, _ = ops.attn_build_schedule(seg, tim)
+    ps = ops.attn_build_pair_schedule(sched, S).to(DEV)
+    sg, tm, sc = seg.to(DEV), tim.to(DEV), sched.to(DEV)
+
+    def sequence():
+        ops.ln_modulate(x, xn, mod[:, 0:], mod[:, D:], 3 * D, batches=B, rows_per_batch=S, row_begin=0, row_count=S)
+        ops.gemm(xn, w1, b1, PF_EPI_GELU_BF16, batches=B, rows_per_batch=S, out=hid)
+        ops.gemm(hid, w2, b2, PF_EPI_GATE_RESID, batches=B, rows_per_batch=S, out=x, ldo=D, gate=mod[:, 2 * D:], gate_batch_stride=3 * D)
+        ops.attn_fwd(q, k, v, att, sg, tm, sc, 0.125, pair_sched=ps)
+
+    x0 = x.clone()
+    sequence()
+    torch.cuda.synchronize()
+    x_direct, att_direct = x.clone(), att.clone()
+    ctx = C.c_void_p()
+    _lib.check(lib.pf_ctx_create(C.byref(ctx)), "pf_ctx_create")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        _lib.check(lib.pf_ctx_record_begin(ctx, side.cuda_stream), "pf_ctx_record_begin")
+        sequence()                                  # recorded, not executed
+        n = lib.pf_ctx_record_end(ctx)
+    assert n >= 4, (n, lib.pf_last_error())
+    torch.cuda.synchronize()
+    assert torch.equal(x, x_direct), "recording must not execute the launches"
+    x.copy_(x0)
+    att.zero_()
+    _lib.check(lib.pf_dit_step_flux(ctx, torch.cuda.current_stream().cuda_stream), "pf_dit_step_flux")
+    torch.cuda.synchronize()
+    assert torch.equal(x, x_direct) and torch.equal(att, att_direct)
+    # new values in the same buffers: replay follows
+    x.copy_(x0 * 0.5 + 0.1)
+    q.copy_(torch.randn_like(q.float()).bfloat16())
+    _lib.check(lib.pf_dit_step_flux(ctx, torch.cuda.current_stream().cuda_stream), "pf_dit_step_flux")
+    torch.cuda.synchronize()
+    x_rep, att_rep = x.clone(), att.clone()
+    x.copy_(x0 * 0.5 + 0.1)
+    sequence()
+    torch.cuda.synchronize()
+    assert torch.equal(x, x_rep) and torch.equal(att, att_rep)
+    _lib.check(lib.pf_ctx_destroy(ctx), "pf_ctx_destroy")
