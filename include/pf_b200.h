@@ -234,7 +234,7 @@ typedef struct pf_conv3d_desc {
   int32_t cout, kt, kh, kw;
   int32_t store_mode;
   void* out;
-  int32_t out_f32;
+  int32_t out_f32; /* plain mode output type: 0 = bf16, 1 = fp32, 2 = uint8 image clamp(v*127.5+127.5, 0, 255) (decode_latent, P:1238) */
   int32_t out_t_total, out_t_offset, out_c;
   int32_t store_channels; /* first store_channels conv outputs are stored (the rest is filter padding) */
   const void* residual;   /* bf16 [B, res_t_total, H, W, out_c] read at frame t + res_t_offset, plain mode only */

@@ -85,7 +85,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& g, uint32_t t
         }
       }
       const int nvalid = g.store_channels - n0;
-      if (g.out_f32) {
+      if (g.out_f32 == 2) {
+        // uint8 image store of decode_latent (P:1238): clamp(v * 127.5 + 127.5, 0, 255), truncated like torch's .byte()
+        uint8_t* dst = reinterpret_cast<uint8_t*>(g.out) + vox * g.out_c + n0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nvalid) dst[i] = static_cast<uint8_t>(fminf(fmaxf(fmaf(x[i], 127.5f, 127.5f), 0.f), 255.f));
+      } else if (g.out_f32) {
         float* dst = reinterpret_cast<float*>(g.out) + vox * g.out_c + n0;
         if (nvalid >= 16 && (g.out_c & 3) == 0) {
 #pragma unroll
@@ -723,6 +729,7 @@ extern "C" int pf_causal_conv3d(const pf_conv3d_desc* d, void* stream_) {
   if (d->store_mode == 1) PF_REQUIRE(d->store_channels == d->cout && d->out_c * 4 == d->cout && !d->out_f32 && !d->residual, "pf_causal_conv3d: spatial depth-to-space needs out_c = cout/4, bf16, no residual");
   if (d->store_mode == 2) PF_REQUIRE(d->store_channels == d->cout && d->out_c * 2 == d->cout && !d->out_f32 && !d->residual, "pf_causal_conv3d: temporal depth-to-space needs out_c = cout/2, bf16, no residual");
   if (d->store_mode == 0) PF_REQUIRE(d->out_c >= d->store_channels, "pf_causal_conv3d: out_c < store_channels");
+  PF_REQUIRE(d->out_f32 >= 0 && d->out_f32 <= 2 && (d->out_f32 != 2 || !d->residual), "pf_causal_conv3d: out_f32 must be 0 (bf16), 1 (fp32) or 2 (uint8 image, no residual)");
   const int st = d->stride_t > 1 ? d->stride_t : 1, sh = d->stride_h > 1 ? d->stride_h : 1, sw = d->stride_w > 1 ? d->stride_w : 1;
   PF_REQUIRE(st <= 2 && sh <= 2 && sw <= 2 && sh == sw, "pf_causal_conv3d: strides must be 1 or 2 with stride_h == stride_w");
   if (st > 1 || sh > 1) PF_REQUIRE(d->store_mode == 0 && d->kt == 3 && d->kh == 3, "pf_causal_conv3d: strided convs are plain-store 3x3x3 (CausalDownsample2x R:322, CausalTemporalDownsample2x R:486)");

@@ -221,6 +221,12 @@ class B200PyramidSampler:
     @torch.no_grad()
     def decode_latent(self, latents: torch.Tensor, save_memory: bool = True) -> torch.Tensor:
         """P:1221-1243 up to the uint8 frames: returns uint8 `[(B T), H, W, C]` on the device."""
+        if hasattr(self.vae, "decode_latent_u8"):
+            # one pass: un-normalisation fused into the latent pack, uint8 conversion into conv_out's epilogue
+            return self.vae.decode_latent_u8(latents, self.vae_scale_factor, self.vae_shift_factor,
+                                             self.vae_video_scale_factor, self.vae_video_shift_factor,
+                                             window_size=1 if save_memory else 2,
+                                             tile_sample_min_size=256 if save_memory else 512)
         latents = latents.clone()
         if latents.shape[2] == 1:
             latents = (latents / self.vae_scale_factor) + self.vae_shift_factor

@@ -218,7 +218,7 @@ class B200CausalVAE(torch.nn.Module):
     # ---- kernel wrappers (single sample: tensors are [T, H, W, C]) ---------------------------------------------------
     def _conv(self, cv: _Conv, x: torch.Tensor, t: int, h: int, w: int, *, out: torch.Tensor, out_t_offset: int = 0,
               store_mode: int = 0, residual: Optional[torch.Tensor] = None, res_t_offset: int = 0,
-              store_channels: Optional[int] = None, out_f32: bool = False, kernel_variant: int = 0) -> None:
+              store_channels: Optional[int] = None, out_f32: int = 0, kernel_variant: int = 0) -> None:
         """t, h, w = OUTPUT dims.  x: [(t-1)*st + kt, h*sh, w*sw, cin_p] (halo frames first); out: [out_t_total, H', W', out_c]."""
         st, sh, sw = cv.stride
         assert x.is_contiguous() and out.is_contiguous() and x.shape[-1] == cv.cin_p
@@ -352,16 +352,19 @@ class B200CausalVAE(torch.nn.Module):
         for cv in self.convs.values():
             cv.cache = None
 
-    def _decode_chunk(self, z: torch.Tensor, first: bool) -> torch.Tensor:
-        """z: latent frames [1, C, T, h, w] of ONE chunk -> fp32 [T', 8h, 8w, 3]."""
+    def _decode_chunk(self, z: torch.Tensor, first: bool, affine=None, u8: bool = False) -> torch.Tensor:
+        """z: latent frames [1, C, T, h, w] of ONE chunk -> fp32 [T', 8h, 8w, 3] (uint8 frames with u8).
+        affine = (scale[T], shift[T]) fp32 device vectors: z*scale[t] + shift[t] fused into the latent pack (the
+        un-normalisation of decode_latent, P:1226-1230)."""
         cfg = self.cfg
         dev = self.device
         _, cl, t, h, w = z.shape
         pq, cin = self.convs["post_quant_conv"], self.convs["decoder.conv_in"]
         zin = torch.empty(t, h, w, pq.cin_p, device=dev, dtype=torch.bfloat16)
         zz = z if z.dtype in (torch.float32, torch.bfloat16) else z.float()
+        fs, fh = (None, None) if affine is None else (affine[0].data_ptr(), affine[1].data_ptr())
         _lib.check(_lib.load().pf_pack_latent(zz.contiguous().data_ptr(), int(zz.dtype == torch.float32), 1, cl, t, h, w,
-                                              zin.data_ptr(), pq.cin_p, t, 0, None, None, _lib.stream_ptr()), "pf_pack_latent")
+                                              zin.data_ptr(), pq.cin_p, t, 0, fs, fh, _lib.stream_ptr()), "pf_pack_latent")
         a = torch.empty(t + 2, h, w, cin.cin_p, device=dev, dtype=torch.bfloat16)
         self._conv(pq, zin, t, h, w, out=a, out_t_offset=2)                      # post_quant_conv (1x1x1), V:365/368
         self._halo(cin, a, first)
@@ -400,8 +403,8 @@ class B200CausalVAE(torch.nn.Module):
         a = torch.empty(t + 2, h, w, x.shape[-1], device=dev, dtype=torch.bfloat16)
         self._gn("decoder.conv_norm_out", x, a, 2, True)
         self._halo(co, a, first)
-        out = torch.empty(t, h, w, cfg.out_channels, device=dev, dtype=torch.float32)
-        self._conv(co, a, t, h, w, out=out, store_channels=cfg.out_channels, out_f32=True)
+        out = torch.empty(t, h, w, cfg.out_channels, device=dev, dtype=torch.uint8 if u8 else torch.float32)
+        self._conv(co, a, t, h, w, out=out, store_channels=cfg.out_channels, out_f32=2 if u8 else 1)
         return out
 
     # ---- encoder (i2v image latent, P:911) ----------------------------------------------------------------------------
@@ -513,9 +516,10 @@ class B200CausalVAE(torch.nn.Module):
         self._reset_caches()
         return torch.cat(outs, 0)
 
-    def _decode_sample(self, z: torch.Tensor, window_size: int) -> torch.Tensor:
+    def _decode_sample(self, z: torch.Tensor, window_size: int, affine=None, u8: bool = False) -> torch.Tensor:
         """chunk_decode (V:346-374) for one sample: first chunk window+1 latent frames, then `window` each."""
         if self._cp is not None:
+            assert affine is None and not u8, "the fused un-normalise / uint8 path is single-GPU (decode_latent_u8 falls back)"
             if z.shape[2] - 1 >= 2 * self._cp[2] and self.cp_frames_per_round >= 2:   # full shares own their halo source
                 return self._decode_sample_cp(z)
             saved, self._cp = self._cp, None              # short clip: every rank decodes all of it (replicas)
@@ -531,7 +535,11 @@ class B200CausalVAE(torch.nn.Module):
         while f < n:
             bounds.append((f, min(n, f + window_size)))
             f += window_size
-        outs = [self._decode_chunk(z[:, :, a:b], i == 0) for i, (a, b) in enumerate(bounds)]
+        if affine is None and not u8:
+            outs = [self._decode_chunk(z[:, :, a:b], i == 0) for i, (a, b) in enumerate(bounds)]
+        else:
+            outs = [self._decode_chunk(z[:, :, a:b], i == 0, None if affine is None else (affine[0][a:b], affine[1][a:b]), u8)
+                    for i, (a, b) in enumerate(bounds)]
         self._reset_caches()
         return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
 
@@ -551,6 +559,33 @@ class B200CausalVAE(torch.nn.Module):
         if not return_dict:
             return (dec,)
         return DecoderOutput(dec)
+
+    @torch.no_grad()
+    def decode_latent_u8(self, latents: torch.Tensor, scale: float, shift: float, video_scale: float, video_shift: float,
+                         window_size: int = 1, tile_sample_min_size: int = 256) -> torch.Tensor:
+        """decode_latent (P:1221-1243) in one pass: the per-frame un-normalisation  z / scale + shift  (first frame: image
+        constants, the rest: video constants, P:1226-1230) is fused into the latent pack kernel and the
+        `mul(127.5).add(127.5).clamp(0, 255).byte()` of P:1238 into conv_out's epilogue: the decoder writes uint8 frames
+        [(B T), H, W, 3] directly (1 B/value instead of a 4 B fp32 image + 3 torch passes).  Tiled or context-parallel
+        decodes blend / gather fp32 tiles, so they take the two-step path."""
+        _lib.require_device()
+        z = latents.to(self.device)
+        b, _, t = z.shape[:3]
+        tile_latent = int(tile_sample_min_size / self.cfg.downsample_scale)
+        if (self.use_tiling and (z.shape[-1] > tile_latent or z.shape[-2] > tile_latent)) or self._cp is not None:
+            zz = z.clone().float()
+            zz[:, :, :1] = zz[:, :, :1] / scale + shift
+            if t > 1:
+                zz[:, :, 1:] = zz[:, :, 1:] / video_scale + video_shift
+            img = self.decode(zz.to(z.dtype), temporal_chunk=True, window_size=window_size,
+                              tile_sample_min_size=tile_sample_min_size).sample
+            img = img.float().mul(127.5).add(127.5).clamp(0, 255).byte()
+            return img.permute(0, 2, 3, 4, 1).reshape(-1, img.shape[3], img.shape[4], img.shape[1])
+        fs = torch.full((t,), 1.0 / video_scale, device=self.device, dtype=torch.float32)
+        fh = torch.full((t,), float(video_shift), device=self.device, dtype=torch.float32)
+        fs[0], fh[0] = 1.0 / scale, float(shift)
+        outs = [self._decode_sample(z[i:i + 1], window_size, affine=(fs, fh), u8=True) for i in range(b)]
+        return torch.cat(outs, 0)                      # [(B T'), H, W, 3] uint8
 
     def _tiled_decode(self, z: torch.Tensor, window: int, tile_sample_min_size: int) -> torch.Tensor:
         """tiled_decode (V:468-519): independent tiles, linear cross-fade with the tile above and to the left."""

@@ -180,3 +180,29 @@ def test_vae_encoder_matches_reference_golden(golden_dir):
     gen = torch.Generator().manual_seed(0)
     z = dist.sample(gen)
     assert z.shape == dist.mean.shape and z.device.type == "cuda" and z.dtype == torch.bfloat16
+
+
+def test_decode_latent_u8_fused_matches_two_step(golden_dir):
+    """decode_latent_u8: un-normalisation fused into the latent pack + uint8 store in conv_out's epilogue == the reference's
+    order of operations (un-normalise in torch, decode, mul(127.5).add(127.5).clamp(0,255).byte(), P:1226-1238) to within one
+    grey level (the two-step path rounds the un-normalised latent to bf16 first)."""
+    from oracle import vae_oracle as VO
+    from pyramid_flow_b200.vae import B200CausalVAE, VaeConfigB200
+    g = torch.load(golden_dir / "vae_small.pt", weights_only=False)
+    cfg = VO.VaeDecoderConfig(**g["cfg"])
+    params = VO.synthetic_vae_params(cfg, seed=g["param_seed"])
+    dev = torch.device("cuda:0")
+    vae = B200CausalVAE(VaeConfigB200(**g["cfg"]), params, device=dev)
+    z = g["z"].to(dev).bfloat16()
+    sc, sh, vsc, vsh = 1 / 1.8726, -0.04, 1 / 3.0986, -0.2343
+    u8 = vae.decode_latent_u8(z, sc, sh, vsc, vsh, window_size=1)
+    zz = z.float().clone()
+    zz[:, :, :1] = zz[:, :, :1] / sc + sh
+    zz[:, :, 1:] = zz[:, :, 1:] / vsc + vsh
+    img = vae.decode(zz, temporal_chunk=True, window_size=1).sample
+    ref = img.float().mul(127.5).add(127.5).clamp(0, 255).byte().permute(0, 2, 3, 4, 1).reshape(-1, img.shape[3], img.shape[4], 3)
+    torch.cuda.synchronize()
+    assert u8.dtype == torch.uint8 and u8.shape == ref.shape
+    d = (u8.int() - ref.int()).abs()
+    assert d.max().item() <= 1 and d.float().mean().item() < 0.05, (d.max().item(), d.float().mean().item())
+    assert ref.float().std().item() > 5
