@@ -214,6 +214,13 @@ PF_API int pf_unpatchify(const float* x, int32_t rows_per_batch, int32_t row_beg
  * v = vu + g*(vc - vu); x_out = x + dsigma * v.  v: fp32 [2, n] (uncond, cond); x fp32 [n]. */
 PF_API int pf_cfg_euler_step(const float* v2, float guidance, float dsigma, const float* x, float* x_out, int64_t n,
                              void* stream);
+/* Stage hop of generate_one_unit (P:729-743) in one kernel: nearest x2 up-sampling of the latent planes x [planes, h, w]
+ * (bf16 or fp32), block noise of sample_block_noise (P:697-703: each 2x2 block ~ N(0, (1+gamma) I - gamma 11^T)) formed as L z
+ * from iid normals z [planes, 2h, 2w] (fp32, drawn on the device) with L = chol16 (host, row-major lower-triangular 4x4), and
+ * the renoise  out = alpha * up(x) + beta * noise.  Opt-in on the host side: same distribution as the reference's python loop
+ * of MultivariateNormal.sample() calls, different RNG consumption. */
+PF_API int pf_stage_hop(const void* x, int32_t x_is_f32, const float* z, void* out, int64_t planes, int32_t h, int32_t w,
+                        float alpha, float beta, const float* chol16, void* stream);
 
 /* ------------------------------------------------------------------ causal 3-D convolution (VAE decode, tcgen05 + TMA)
  * Replaces CausalConv3d -> nn.Conv3d (C:46-146), kernel 3x3x3 or 1x1x1, stride 1, on channels-last bf16 activations.

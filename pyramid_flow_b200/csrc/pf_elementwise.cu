@@ -205,9 +205,57 @@ __global__ void cfg_euler_kernel(const float* __restrict__ v2, float guidance, f
   x_out[i] = x[i] + dsigma * v;
 }
 
+// Stage hop of the pyramidal sampler (P:729-743): out[.., 2i+di, 2j+dj] = alpha * x[.., i, j] + beta * n[.., 2i+di, 2j+dj], where
+// every 2x2 block of n ~ N(0, (1+gamma) I - gamma 1 1^T) (sample_block_noise, P:697-703) is L z with z the block's four iid
+// normals (z_in, same layout as out) and L the Cholesky factor of the 4x4 covariance.  One thread per 2x2 block.
+template <typename T>
+__global__ void stage_hop_kernel(const T* __restrict__ x, const float* __restrict__ z, T* __restrict__ out, long long planes,
+                                 int h, int w, float alpha, float beta, float4 l0, float4 l1, float4 l2, float4 l3) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = planes * h * w;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % w);
+  const int i = static_cast<int>((idx / w) % h);
+  const long long p = idx / (static_cast<long long>(w) * h);
+  const float xv = alpha * static_cast<float>(x[idx]);
+  const long long o = (p * 2 * h + 2 * i) * (2 * w) + 2 * j;
+  const float2 za = *reinterpret_cast<const float2*>(z + o);              // block order (di, dj): (0,0), (0,1), (1,0), (1,1)
+  const float2 zb = *reinterpret_cast<const float2*>(z + o + 2 * w);
+  const float n0 = l0.x * za.x;
+  const float n1 = l1.x * za.x + l1.y * za.y;
+  const float n2 = l2.x * za.x + l2.y * za.y + l2.z * zb.x;
+  const float n3 = l3.x * za.x + l3.y * za.y + l3.z * zb.x + l3.w * zb.y;
+  out[o] = static_cast<T>(xv + beta * n0);
+  out[o + 1] = static_cast<T>(xv + beta * n1);
+  out[o + 2 * w] = static_cast<T>(xv + beta * n2);
+  out[o + 2 * w + 1] = static_cast<T>(xv + beta * n3);
+}
+
 }  // namespace pf
 
 extern "C" {
+
+int pf_stage_hop(const void* x, int32_t x_is_f32, const float* z, void* out, int64_t planes, int32_t h, int32_t w, float alpha,
+                 float beta, const float* chol16, void* stream_) {
+  using namespace pf;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PF_REQUIRE(x && z && out && chol16 && planes > 0 && h > 0 && w > 0, "pf_stage_hop: bad arguments");
+  PF_REQUIRE((reinterpret_cast<uintptr_t>(z) & 7) == 0, "pf_stage_hop: z must be 8-byte aligned");
+  const float4 l0 = make_float4(chol16[0], chol16[1], chol16[2], chol16[3]);
+  const float4 l1 = make_float4(chol16[4], chol16[5], chol16[6], chol16[7]);
+  const float4 l2 = make_float4(chol16[8], chol16[9], chol16[10], chol16[11]);
+  const float4 l3 = make_float4(chol16[12], chol16[13], chol16[14], chol16[15]);
+  const long long total = planes * h * w;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (x_is_f32)
+    stage_hop_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(x), z, static_cast<float*>(out), planes, h, w,
+                                                         alpha, beta, l0, l1, l2, l3);
+  else
+    stage_hop_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), z,
+                                                                 static_cast<__nv_bfloat16*>(out), planes, h, w, alpha, beta,
+                                                                 l0, l1, l2, l3);
+  return check_launch("pf_stage_hop");
+}
 
 int pf_ln_modulate(const float* x, void* y, int32_t batches, int32_t rows_per_batch, int32_t row_begin,
                    int32_t row_count, int32_t dim, const float* shift, const float* scale, int64_t mod_batch_stride,

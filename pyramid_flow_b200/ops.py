@@ -127,6 +127,23 @@ def cfg_euler_step(v2: torch.Tensor, guidance: float, dsigma: float, x: torch.Te
                                              _lib.stream_ptr()), "pf_cfg_euler_step")
 
 
+def stage_hop(x: torch.Tensor, z: torch.Tensor, alpha: float, beta: float, gamma: float) -> torch.Tensor:
+    """x [b, c, t, h, w] (bf16/fp32) -> alpha * nearest_x2(x) + beta * block_noise(z), z iid normal fp32 [b, c, t, 2h, 2w]
+    (pf_stage_hop; reference P:729-743 + P:697-703)."""
+    import ctypes as C
+    assert x.is_cuda and x.is_contiguous() and z.is_contiguous() and z.dtype == torch.float32
+    assert x.dtype in (torch.float32, torch.bfloat16)
+    b, c, t, h, w = x.shape
+    assert tuple(z.shape) == (b, c, t, 2 * h, 2 * w)
+    cov = torch.eye(4, dtype=torch.float64) * (1 + gamma) - torch.ones(4, 4, dtype=torch.float64) * gamma
+    chol = torch.linalg.cholesky(cov).to(torch.float32).flatten().tolist()
+    out = torch.empty(b, c, t, 2 * h, 2 * w, device=x.device, dtype=x.dtype)
+    arr = (C.c_float * 16)(*chol)
+    _lib.check(_lib.load().pf_stage_hop(x.data_ptr(), int(x.dtype == torch.float32), z.data_ptr(), out.data_ptr(), b * c * t, h, w,
+                                        alpha, beta, arr, _lib.stream_ptr()), "pf_stage_hop")
+    return out
+
+
 def attn_build_schedule(seg: torch.Tensor, time: torch.Tensor):
     """seg/time: int32 CPU tensors [batch, seq] -> (schedule int32 CPU [batch, q_tiles, stride], allowed_pairs [batch])."""
     seg = seg.to(torch.int32).contiguous().cpu()

@@ -42,7 +42,8 @@ def block_noise(bs: int, ch: int, temp: int, height: int, width: int, gamma: flo
 class B200PyramidSampler:
     def __init__(self, dit, scheduler, vae=None, stages: Sequence[int] = (1, 2, 4), frame_per_unit: int = 1,
                  model_name: str = "pyramid_flux", downsample: int = 8,
-                 block_noise_fn: Optional[Callable[..., torch.Tensor]] = None, fused_step: bool = False):
+                 block_noise_fn: Optional[Callable[..., torch.Tensor]] = None, fused_step: bool = False,
+                 gpu_stage_hop: bool = False):
         self.dit, self.scheduler, self.vae = dit, scheduler, vae
         self.stages = list(stages)
         self.frame_per_unit = frame_per_unit
@@ -53,6 +54,10 @@ class B200PyramidSampler:
         # S:278-286); the result is rounded to the latent dtype once.  Opt-in: it rounds less than the reference's bf16 chain
         # (bf16 CFG combine, bf16 dsigma*v), so outputs differ from the reference at bf16 resolution.
         self.fused_step = fused_step
+        # gpu_stage_hop: the stage transition (nearest x2 up-sample, block noise, renoise; P:729-743) as ONE kernel with the
+        # normals drawn on the device (pf_stage_hop) instead of CPU randn + Cholesky matmul + H2D copy + 3 torch ops.  Opt-in:
+        # same distribution, different RNG stream than the reference (parity tests inject the noise instead).
+        self.gpu_stage_hop = gpu_stage_hop
         # latent normalisation constants (P:160-176)
         if model_name == "pyramid_flux":
             self.vae_shift_factor, self.vae_scale_factor = -0.04, 1 / 1.8726
@@ -84,15 +89,22 @@ class B200PyramidSampler:
             if i_s > 0:
                 height *= 2
                 width *= 2
-                latents = _resize_frames(latents, (height, width), "nearest")
                 ori_sigma = 1 - self.scheduler.ori_start_sigmas[i_s]
                 gamma = self.scheduler.config.gamma
                 alpha = 1 / (math.sqrt(1 + (1 / gamma)) * (1 - ori_sigma) + ori_sigma)
                 beta = alpha * (1 - ori_sigma) / math.sqrt(gamma)
-                bs, ch, temp, height, width = latents.shape
-                fn = self.block_noise_fn or (lambda *a: block_noise(*a, gamma))
-                noise = fn(bs, ch, temp, height, width).to(device=device, dtype=dtype)
-                latents = alpha * latents + beta * noise
+                if self.gpu_stage_hop and self.block_noise_fn is None and latents.is_cuda:
+                    from . import ops
+                    bs, ch, temp = latents.shape[:3]
+                    z = torch.randn(bs, ch, temp, height, width, device=latents.device, dtype=torch.float32,
+                                    generator=getattr(self, "device_generator", None))
+                    latents = ops.stage_hop(latents.contiguous(), z, alpha, beta, gamma)
+                else:
+                    latents = _resize_frames(latents, (height, width), "nearest")
+                    bs, ch, temp, height, width = latents.shape
+                    fn = self.block_noise_fn or (lambda *a: block_noise(*a, gamma))
+                    noise = fn(bs, ch, temp, height, width).to(device=device, dtype=dtype)
+                    latents = alpha * latents + beta * noise
             for t in timesteps:
                 x_in = torch.cat([latents] * 2) if do_cfg else latents
                 timestep = t.expand(x_in.shape[0]).to(x_in.dtype)          # rounded to the latent dtype (bf16), P:750

@@ -299,3 +299,29 @@ def test_step_context_record_and_replay():
     torch.cuda.synchronize()
     assert torch.equal(x, x_rep) and torch.equal(att, att_rep)
     _lib.check(lib.pf_ctx_destroy(ctx), "pf_ctx_destroy")
+
+
+def test_stage_hop_kernel():
+    """pf_stage_hop == alpha * nearest_x2(x) + beta * (L z per 2x2 block) computed in torch on the same normals (P:729-743,
+    P:697-703), and the block covariance of the generated noise is (1+gamma) I - gamma 11^T."""
+    from einops import rearrange
+    from pyramid_flow_b200 import ops
+    torch.manual_seed(4)
+    gamma, alpha, beta = 1.0 / 3.0, 0.74963, 0.43366
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(2, 16, 3, 12, 20, device=DEV).to(dtype)
+        z = torch.randn(2, 16, 3, 24, 40, device=DEV)
+        out = ops.stage_hop(x, z, alpha, beta, gamma)
+        cov = torch.eye(4, dtype=torch.float64) * (1 + gamma) - torch.ones(4, 4, dtype=torch.float64) * gamma
+        L = torch.linalg.cholesky(cov).float().to(DEV)
+        zb = rearrange(z, "b c t (h p) (w q) -> (b c t h w) (p q)", p=2, q=2)
+        nb = rearrange(zb @ L.T, "(b c t h w) (p q) -> b c t (h p) (w q)", b=2, c=16, t=3, h=12, w=20, p=2, q=2)
+        up = torch.nn.functional.interpolate(x.float().flatten(0, 1), scale_factor=(1, 2, 2), mode="nearest").view(2, 16, 3, 24, 40)
+        ref = alpha * up + beta * nb
+        tol = 1e-5 if dtype == torch.float32 else 2e-2
+        assert (out.float() - ref).abs().max().item() < tol
+    xz = torch.zeros(1, 16, 8, 48, 80, device=DEV)
+    n = ops.stage_hop(xz, torch.randn(1, 16, 8, 96, 160, device=DEV), 1.0, 1.0, gamma)
+    blocks = rearrange(n, "b c t (h p) (w q) -> (b c t h w) (p q)", p=2, q=2).double()
+    emp = blocks.T @ blocks / blocks.shape[0]
+    assert (emp.cpu() - cov).abs().max().item() < 0.02
