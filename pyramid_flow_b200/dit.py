@@ -379,25 +379,12 @@ class B200FluxTransformer(torch.nn.Module):
             self._padded = True
 
     def _peer_exchange(self, plan: SeqPlan, hp: int, ldc: int):
-        """The peer arena (sp.PeerExchange), (re)built collectively when a call needs more room than it has.  Every rank sees
-        the same shapes, so every rank takes the same decision."""
+        """The peer arena (sp.PeerExchange) for this call's shapes; see sp.ensure_peer_exchange."""
         from . import sp as SP
         c = self.cfg
         ct, chh, cww = plan.clip_thw[-1]
         vel_bytes = (c.in_channels // 4) * ct * chh * 2 * cww * 2 * 4
-        px = getattr(self, "_px", None)
-        if (px is None or plan.seq > px.max_seq or plan.last_tokens > px.max_last or vel_bytes > px.vel_bytes
-                or px.ldc != ldc):
-            if px is not None:
-                torch.cuda.synchronize()
-                torch.distributed.barrier()
-                self._graphs.clear()            # captured launches point into the old arena
-                px.close()
-            cap = max(plan.seq, getattr(self, "peer_max_seq", 0))
-            last = max(plan.last_tokens, getattr(self, "peer_max_last", 0))
-            px = SP.PeerExchange(self.layout, cap, hp, ldc, c.in_channels, last, max(vel_bytes, getattr(self, "peer_max_vel_bytes", 0)))
-            self._px = px
-        return px
+        return SP.ensure_peer_exchange(self, self.layout, plan.seq, plan.last_tokens, hp, ldc, c.in_channels, vel_bytes)
 
     # -- the step ------------------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -175,20 +175,21 @@ class B200MMDiT(torch.nn.Module):
         self._last_key = (mask, mask._version, shapes, hit)
         return hit
 
-    def _workspace(self, b: int, plan: SeqPlan) -> dict:
-        key = (b, plan.seq, plan.video_len, plan.last_tokens)
+    def _workspace(self, b: int, plan: SeqPlan, sl: Optional[int] = None) -> dict:
+        sl = plan.seq if sl is None else sl
+        key = (b, plan.seq, plan.video_len, plan.last_tokens, sl)
         ws = self._ws.get(key)
         if ws is None:
             if len(self._ws) >= 4:
                 self._ws.clear()
             c = self.cfg
-            d, hn, s, dev = c.inner_dim, c.num_attention_heads, plan.seq, self.device
-            ws = dict(h=torch.empty(b, s, d, device=dev, dtype=torch.float32),
-                      xn=torch.empty(b, s, d, device=dev, dtype=torch.bfloat16),
-                      q=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
-                      k=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
-                      v=torch.empty(b, hn, s, 64, device=dev, dtype=torch.bfloat16),
-                      cat=torch.empty(b, s, 5 * d, device=dev, dtype=torch.bfloat16),
+            d, hn, dev = c.inner_dim, c.num_attention_heads, self.device
+            ws = dict(h=torch.empty(b, sl, d, device=dev, dtype=torch.float32),
+                      xn=torch.empty(b, sl, d, device=dev, dtype=torch.bfloat16),
+                      q=torch.empty(b, hn, sl, 64, device=dev, dtype=torch.bfloat16),
+                      k=torch.empty(b, hn, sl, 64, device=dev, dtype=torch.bfloat16),
+                      v=torch.empty(b, hn, sl, 64, device=dev, dtype=torch.bfloat16),
+                      cat=torch.empty(b, sl, 5 * d, device=dev, dtype=torch.bfloat16),
                       tok=torch.empty(b, plan.video_len, 4 * c.in_channels, device=dev, dtype=torch.bfloat16),
                       mod=torch.empty(b, self.n_mod, device=dev, dtype=torch.float32),
                       temb=torch.empty(b, d, device=dev, dtype=torch.float32),
@@ -196,6 +197,17 @@ class B200MMDiT(torch.nn.Module):
                       head=torch.empty(b, plan.last_tokens, 4 * c.in_channels, device=dev, dtype=torch.float32))
             self._ws[key] = ws
         return ws
+
+    # -- parallel layout (CFG x sequence parallel over NVLink peer memory, sp.py) -----------------------------------------
+    def set_parallel_layout(self, layout) -> None:
+        """Attach a `sp.ParallelLayout`: the CFG pair is split first, then the joint sequence is cut into `sp` chunks; q/k/v and
+        the attention output cross NVLink as remote stores fused into the QKV-GEMM / attention epilogues (csrc/pf_peer.cu), as
+        in B200FluxTransformer.  The reference runs this model with sp 2 or 4 (scripts/inference_multigpu.sh:9); 24 heads
+        divide by both, so no head padding is needed."""
+        assert self.cfg.num_attention_heads % max(1, layout.sp) == 0, "heads must divide by the SP degree"
+        self.layout = layout
+        self._px = None
+        self._ws.clear()
 
     @torch.no_grad()
     def forward(self, sample, timestep_ratio=None, encoder_hidden_states=None, encoder_attention_mask=None,
@@ -205,43 +217,73 @@ class B200MMDiT(torch.nn.Module):
         clips = sample[0] if isinstance(sample[0], (list, tuple)) else [sample[0]]
         c = self.cfg
         d, hn = c.inner_dim, c.num_attention_heads
-        b = clips[-1].shape[0]
+        bg = clips[-1].shape[0]
         plan, pos = self.plan_for([cl.shape for cl in clips], encoder_attention_mask)
         self.last_plan = plan
-        ws = self._workspace(b, plan)
         t_len, s, lv = plan.text_len, plan.seq, plan.video_len
+        lay = getattr(self, "layout", None)
+        par = lay is not None and lay.enabled
+        if par:
+            from . import sp as SP
+            assert bg == lay.cfg_ways, "CFG-parallel layout expects the [uncond ; cond] batch"
+            b, b0, nsp = 1, lay.cfg_rank, lay.sp
+            c0, c1 = SP.chunk_bounds(s, nsp, lay.sp_rank)
+        else:
+            b, b0, nsp, c0, c1 = bg, 0, 1, 0, s
+        sl = c1 - c0
+        ws = self._workspace(b, plan, sl)
         h, xn, q, k, v, cat, mod = ws["h"], ws["xn"], ws["q"], ws["k"], ws["v"], ws["cat"], ws["mod"]
         nm = self.n_mod
+        ldc = 5 * d
+        px = None
+        if par:
+            ct_, ch_, cw_ = plan.clip_thw[-1]
+            px = SP.ensure_peer_exchange(self, lay, s, plan.last_tokens, hn, ldc, 4 * c.in_channels,
+                                         c.in_channels * ct_ * ch_ * 2 * cw_ * 2 * 4)
+            if nsp > 1:
+                cat = px.cat(sl)
+                qkv_x = px.qkv(s)
+        rope = plan.rope[c0:c1]
+        tb, te = max(0, c0), min(t_len, c1)
+        vb, ve = max(t_len, c0), min(s, c1)
+        ranges = ((tb - c0, max(0, te - tb)), (vb - c0, max(0, ve - vb)))        # (text, video) rows of my chunk
 
-        t32 = timestep_ratio.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        t32 = timestep_ratio.detach().to(device=self.device, dtype=torch.float32)[b0:b0 + b].contiguous()
         tproj = ops.timestep_embedding(t32, 256, round_bf16=False)
         ops.small_linear(tproj, self.w_t1, self.b_t1, ws["tmp"], act_out=1)
         ops.small_linear(ws["tmp"], self.w_t2, self.b_t2, ws["temb"])
-        pooled = pooled_projections.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        pooled = pooled_projections.detach().to(device=self.device, dtype=torch.float32)[b0:b0 + b].contiguous()
         ops.small_linear(pooled, self.w_p1, self.b_p1, ws["tmp"], act_out=1)
         ops.small_linear(ws["tmp"], self.w_p2, self.b_p2, ws["temb"], accumulate=True)
         ops.small_linear(ws["temb"], self.w_mod, self.b_mod, mod, act_in=1)
 
-        enc = encoder_hidden_states.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
-        ops.gemm(enc, self.w_ctx, self.b_ctx, PF_EPI_STORE_F32, batches=b, rows_per_batch=t_len, row_begin=0,
-                 row_count=t_len, out=h, ldo=d, out_batch_rows=s, out_row_begin=0)
-        tok0 = 0
-        for cl, (ct, chh, cww) in zip(clips, plan.clip_thw):
-            cl = cl.detach()
-            if cl.dtype not in (torch.float32, torch.bfloat16):
-                cl = cl.float()
-            ops.patchify(cl.contiguous(), ws["tok"], lv, tok0)
-            tok0 += ct * chh * cww
-        # the sincos table is placed in the stream first (device copy), the patch-embed GEMM accumulates onto it
-        h[:, t_len:].copy_(pos[None].expand(b, -1, -1))
-        ops.gemm(ws["tok"], self.w_x, self.b_x, PF_EPI_GATE_RESID, batches=b, rows_per_batch=lv, row_begin=0, row_count=lv,
-                 out=h, ldo=d, out_batch_rows=s, out_row_begin=t_len, gate=self.ones_gate, gate_batch_stride=0)
+        if ranges[0][1] > 0:
+            enc = encoder_hidden_states.detach().to(device=self.device, dtype=torch.bfloat16)[b0:b0 + b].contiguous()
+            ops.gemm(enc, self.w_ctx, self.b_ctx, PF_EPI_STORE_F32, batches=b, rows_per_batch=t_len, row_begin=tb,
+                     row_count=te - tb, out=h, ldo=d, out_batch_rows=sl, out_row_begin=tb - c0)
+        if ranges[1][1] > 0:
+            tok0 = 0
+            for cl, (ct, chh, cww) in zip(clips, plan.clip_thw):
+                cl = cl.detach()[b0:b0 + b]
+                if cl.dtype not in (torch.float32, torch.bfloat16):
+                    cl = cl.float()
+                ops.patchify(cl.contiguous(), ws["tok"], lv, tok0)
+                tok0 += ct * chh * cww
+            # the sincos table is placed in the stream first (device copy), the patch-embed GEMM accumulates onto it
+            h[:, vb - c0:ve - c0].copy_(pos[None, vb - t_len:ve - t_len].expand(b, -1, -1))
+            ops.gemm(ws["tok"], self.w_x, self.b_x, PF_EPI_GATE_RESID, batches=b, rows_per_batch=lv, row_begin=vb - t_len,
+                     row_count=ve - vb, out=h, ldo=d, out_batch_rows=sl, out_row_begin=vb - c0, gate=self.ones_gate,
+                     gate_batch_stride=0)
 
         def lnmod(off_shift, off_scale, r0, rc):
-            ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=s, row_begin=r0,
-                            row_count=rc)
+            if rc > 0:
+                ops.ln_modulate(h, xn, mod[:, off_shift:], mod[:, off_scale:], nm, batches=b, rows_per_batch=sl, row_begin=r0,
+                                row_count=rc)
 
-        ranges = ((0, t_len), (t_len, lv))
+        peer_qkv = None
+        if px is not None and nsp > 1:
+            peer_qkv = dict(peer_ptrs=[pp + px.off_qkv for pp in px.sp_buf.ptrs], peer_heads=hn // nsp, peer_seq=s, peer_row0=c0)
+        seg, tim, sched, sched2 = plan.seg[b0:b0 + b], plan.time[b0:b0 + b], plan.sched[b0:b0 + b], plan.sched2[b0:b0 + b]
         scale = 1.0 / math.sqrt(64)
         for i, w in enumerate(self.blocks):
             last = i == c.num_layers - 1
@@ -250,37 +292,62 @@ class B200MMDiT(torch.nn.Module):
             offs = (oc, ov)
             # text: AdaLayerNormZero (shift, scale, ...) or, in the last block, AdaLayerNormContinuous (scale, shift)
             if last:
-                lnmod(oc + d, oc, 0, t_len)
+                lnmod(oc + d, oc, *ranges[0])
             else:
-                lnmod(oc, oc + d, 0, t_len)
-            lnmod(ov, ov + d, t_len, lv)
+                lnmod(oc, oc + d, *ranges[0])
+            lnmod(ov, ov + d, *ranges[1])
             for j, (r0, rc) in enumerate(ranges):
-                ops.gemm(xn, (w["w_cqkv"], w["w_qkv"])[j], (w["b_cqkv"], w["b_qkv"])[j], PF_EPI_QKV_ROPE, batches=b,
-                         rows_per_batch=s, row_begin=r0, row_count=rc, q_out=q, k_out=k, v_out=v, rope=plan.rope,
-                         q_norm_w=(w["cnq"], w["nq"])[j], k_norm_w=(w["cnk"], w["nk"])[j], norm_eps=1e-5, heads=hn,
-                         head_dim=64, seq_len=s)
-            ops.attn_fwd(q, k, v, cat, plan.seg, plan.time, plan.sched, scale, pair_sched=plan.sched2)
+                if rc > 0:
+                    ops.gemm(xn, (w["w_cqkv"], w["w_qkv"])[j], (w["b_cqkv"], w["b_qkv"])[j], PF_EPI_QKV_ROPE, batches=b,
+                             rows_per_batch=sl, row_begin=r0, row_count=rc, q_out=q, k_out=k, v_out=v, rope=rope,
+                             q_norm_w=(w["cnq"], w["nq"])[j], k_norm_w=(w["cnk"], w["nk"])[j], norm_eps=1e-5, heads=hn,
+                             head_dim=64, seq_len=sl, peer=peer_qkv)
+            if nsp == 1:
+                ops.attn_fwd(q, k, v, cat, seg, tim, sched, scale, pair_sched=sched2)
+            else:
+                px.barrier_sp()                    # every rank's QKV epilogue has stored into every rank's gathered buffer
+                ops.attn_fwd(qkv_x[0][None], qkv_x[1][None], qkv_x[2][None], None, seg, tim, sched, scale, pair_sched=sched2,
+                             ldo=ldc, peer=dict(peer_ptrs=[pp + px.off_cat for pp in px.sp_buf.ptrs], peer_chunk_rows=sl,
+                                                peer_col_begin=lay.sp_rank * (hn // nsp) * 64))
+                px.barrier_sp()                    # ... and every rank's attention epilogue into every rank's `cat`
             for j, (r0, rc) in enumerate(ranges):
-                if j == 0 and last:
+                if rc == 0 or (j == 0 and last):
                     continue   # context_pre_only: the text stream ends here (MB:659-660)
                 wo, bo = ((w.get("w_co"), w["w_o"])[j], (w.get("b_co"), w["b_o"])[j])
                 wf1, bf1 = ((w.get("w_cf1"), w["w_f1"])[j], (w.get("b_cf1"), w["b_f1"])[j])
                 wf2, bf2 = ((w.get("w_cf2"), w["w_f2"])[j], (w.get("b_cf2"), w["b_f2"])[j])
-                ops.gemm(cat[:, :, :d], wo, bo, PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
+                ops.gemm(cat[:, :, :d], wo, bo, PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc,
                          out=h, ldo=d, gate=mod[:, offs[j] + 2 * d:], gate_batch_stride=nm)
                 lnmod(offs[j] + 3 * d, offs[j] + 4 * d, r0, rc)
-                ops.gemm(xn, wf1, bf1, PF_EPI_GELU_BF16, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc, out=cat,
-                         ldo=5 * d, out_col_begin=d)
-                ops.gemm(cat[:, :, d:], wf2, bf2, PF_EPI_GATE_RESID, batches=b, rows_per_batch=s, row_begin=r0, row_count=rc,
+                ops.gemm(xn, wf1, bf1, PF_EPI_GELU_BF16, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc, out=cat,
+                         ldo=ldc, out_col_begin=d)
+                ops.gemm(cat[:, :, d:], wf2, bf2, PF_EPI_GATE_RESID, batches=b, rows_per_batch=sl, row_begin=r0, row_count=rc,
                          out=h, ldo=d, gate=mod[:, offs[j] + 5 * d:], gate_batch_stride=nm)
 
         n_last = plan.last_tokens
         o = self.mod_off["norm_out"]
-        lnmod(o + d, o, s - n_last, n_last)
-        ops.gemm(xn, self.w_out, self.b_out, PF_EPI_STORE_F32, batches=b, rows_per_batch=s, row_begin=s - n_last,
-                 row_count=n_last, out=ws["head"], ldo=4 * c.in_channels, out_batch_rows=n_last, out_row_begin=0)
+        g0, g1 = max(s - n_last, c0), c1                 # my part of the last n_last tokens
+        head = ws["head"]
+        peer_head = px is not None and nsp > 1
+        if peer_head:
+            head = px.head(n_last)
+        if g1 > g0:
+            lnmod(o + d, o, g0 - c0, g1 - g0)
+            ops.gemm(xn, self.w_out, self.b_out, PF_EPI_STORE_F32, batches=b, rows_per_batch=sl, row_begin=g0 - c0,
+                     row_count=g1 - g0, out=head, ldo=4 * c.in_channels, out_batch_rows=n_last, out_row_begin=g0 - (s - n_last))
+            if peer_head:
+                r0h = g0 - (s - n_last)
+                px.bcast(px.sp_buf, head[0, r0h:r0h + (g1 - g0)], px.off_head + r0h * 4 * c.in_channels * 4)
+        if peer_head:
+            px.barrier_sp()
         ct, chh, cww = plan.clip_thw[-1]
         odt = clips[-1].dtype if clips[-1].dtype in (torch.float32, torch.bfloat16) else torch.float32
         out = torch.empty(b, c.in_channels, ct, chh * 2, cww * 2, device=self.device, dtype=odt)
-        ops.unpatchify(ws["head"], n_last, 0, out)
+        ops.unpatchify(head, n_last, 0, out)
+        if par:
+            vel = px.vel((bg, *out.shape[1:]), odt)
+            if lay.sp_rank == 0:
+                px.bcast(px.world_buf, out.view(-1), px.w_off_vel + lay.cfg_rank * px.vel_bytes)
+            px.barrier_world()
+            out = vel.clone()
         return [out]

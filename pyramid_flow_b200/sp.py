@@ -270,3 +270,24 @@ class PeerExchange:
         nb = src.numel() * src.element_size()
         assert src.is_contiguous() and nb % 16 == 0 and dst_offset % 16 == 0
         _lib.check(_lib.load().pf_peer_bcast(C.byref(g), src.data_ptr(), nb, dst_offset, _lib.stream_ptr()), "pf_peer_bcast")
+
+
+def ensure_peer_exchange(owner, lay: ParallelLayout, seq: int, last_tokens: int, hp: int, ldc: int, head_cols: int,
+                         vel_bytes: int) -> PeerExchange:
+    """The peer arena of `owner` (a B200FluxTransformer / B200MMDiT), (re)built collectively when a call needs more room than
+    it has.  Every rank sees the same shapes, so every rank takes the same decision.  `owner.peer_max_seq / peer_max_last /
+    peer_max_vel_bytes` pre-size it (one allocation for a whole sampler run)."""
+    px = getattr(owner, "_px", None)
+    if (px is None or seq > px.max_seq or last_tokens > px.max_last or vel_bytes > px.vel_bytes or px.ldc != ldc
+            or px.head_cols != head_cols):
+        if px is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            if hasattr(owner, "_graphs"):
+                owner._graphs.clear()           # captured launches point into the old arena
+            px.close()
+        px = PeerExchange(lay, max(seq, getattr(owner, "peer_max_seq", 0)), hp, ldc, head_cols,
+                          max(last_tokens, getattr(owner, "peer_max_last", 0)),
+                          max(vel_bytes, getattr(owner, "peer_max_vel_bytes", 0)))
+        owner._px = px
+    return px

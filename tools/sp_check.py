@@ -61,4 +61,33 @@ for name, kw, clip_shapes, tlen in [
                   f"max|parallel - single| per rank = {['%.2e' % e for e in errs]}  |ref| mean {ref.abs().mean().item():.3f}", flush=True)
         assert worst < 2e-2, worst
     model.use_cuda_graph = False
+# ---- SD3 MMDiT (24 heads; the reference runs it with sp 2 or 4)
+from oracle import mmdit_oracle as MO
+from pyramid_flow_b200.mmdit import B200MMDiT, MMDiTConfigB200
+if 24 % lay.sp == 0:
+    kw = dict(num_layers=3, pos_embed_max_size=96, sample_size=64)
+    mcfg = MO.MMDiTConfig(**kw)
+    params = MO.synthetic_mmdit_params(mcfg, seed=2)
+    g = torch.Generator().manual_seed(6)
+    clips = [torch.randn(s_, generator=g).bfloat16().to(dev) for s_ in [(2, 16, 2, 12, 20), (2, 16, 1, 24, 40), (2, 16, 1, 48, 80)]]
+    enc = (torch.randn(2, 128, 4096, generator=g) * 0.2).bfloat16().to(dev)
+    mask = torch.ones(2, 128, dtype=torch.long)
+    mask[0, 50:] = 0
+    mask = mask.to(dev)
+    pooled = torch.randn(2, 2048, generator=g).to(dev)
+    t = torch.tensor([500.0, 500.0], device=dev)
+    model = B200MMDiT(MMDiTConfigB200(**{k_: v_ for k_, v_ in kw.items() if k_ != "sample_size"}), params, device=dev)
+    call = dict(sample=[clips], timestep_ratio=t, encoder_hidden_states=enc, encoder_attention_mask=mask, pooled_projections=pooled)
+    ref = model(**call)[0].float()
+    if model.last_plan.seq % lay.sp == 0:
+        model.set_parallel_layout(lay)
+        out = model(**call)[0].float()
+        torch.cuda.synchronize()
+        err = (out - ref).abs().max().item()
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        if rank == 0:
+            print(f"[sp_check] SD3 MMDiT (3 blocks): world {world} = cfg {lay.cfg_ways} x sp {lay.sp}, S={model.last_plan.seq}: "
+                  f"max|parallel - single| per rank = {['%.2e' % e for e in errs]}  |ref| mean {ref.abs().mean().item():.3f}", flush=True)
+        assert err < 2e-2, err
 dist.destroy_process_group()
