@@ -133,3 +133,34 @@ def test_c_abi_rejects_bad_arguments_with_a_message():
     g.batches, g.rows_per_batch, g.row_count, g.n, g.k, g.lda, g.ldo = 1, 128, 128, 64, 64, 64, 64
     g.epilogue = 17
     assert lib.pf_gemm_bf16(C.byref(g), None) < 0 and "epilogue" in err()
+
+
+def test_pair_schedule_is_the_union_of_the_two_tile_rows():
+    """pf_attn_build_pair_schedule (host code of the two-q-tile attention kernel): pair p = q tiles (q_tiles-2-2p, q_tiles-1-2p);
+    its row is the sorted union of the two tiles' kv lists; per-tile flags reproduce each tile's own list and mask bits; a
+    missing lower tile (odd q_tiles) contributes nothing."""
+    import torch
+    from pyramid_flow_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for seq, lens in [(77, [77]), (128 + 60 * 5, [128 + 60] + [60] * 4), (128 + 200 + 1000 + 1700, [328, 1000, 1700]),
+                      (77 + 240 * 9 + 13, [77 + 240] + [240] * 8 + [13])]:
+        tim = torch.cat([torch.full((n,), i) for i, n in enumerate(lens)]).int()[None].repeat(2, 1)
+        seg = torch.ones(2, seq, dtype=torch.int32)
+        seg[1, 10:int(torch.randint(20, 60, (1,), generator=g))] = 0
+        sched, pairs = ops.attn_build_schedule(seg, tim)
+        ps = ops.attn_build_pair_schedule(sched, seq)
+        qt = (seq + 127) // 128
+        assert ps.shape == (2, (qt + 1) // 2, sched.shape[-1])
+        for b in range(2):
+            for p in range((qt + 1) // 2):
+                hi, lo = qt - 1 - 2 * p, qt - 2 - 2 * p
+                n = int(ps[b, p, 0])
+                ent = ps[b, p, 1:1 + n].tolist()
+                kts = [e >> 4 for e in ent]
+                assert kts == sorted(set(kts)), "union must be strictly increasing"
+                assert all((e & 0xF) != 0 for e in ent), "every entry is needed by at least one tile"
+                for x, t in ((0, lo), (1, hi)):
+                    own = [((e >> 4) << 1) | (((e >> (2 * x)) & 2) >> 1) for e in ent if (e >> (2 * x)) & 1]
+                    want = [] if t < 0 else sched[b, t, 1:1 + int(sched[b, t, 0])].tolist()
+                    assert own == want, (seq, b, p, x)
+                assert bool((ps[b, p, 1 + n:] == 0).all())
