@@ -503,7 +503,8 @@ class B200CausalVAE(torch.nn.Module):
                                 send_next=rank + 1 < world and ranges[rank + 1][1] > ranges[rank + 1][0] and b > a,
                                 ring_send=more and rank == world - 1, ring_recv=more and rank == 0)
             mine = self._decode_chunk(z[:, :, a:b].contiguous(), k == 0 and rank == 0) if b > a else None
-            counts = [8 * (e - s0) - (7 if (k == 0 and r == 0) else 0) if e > s0 else 0 for r, (s0, e) in enumerate(ranges)]
+            tf = 2 ** sum(1 for u in self.cfg.temporal_up_sample if u)      # temporal up-sampling factor of this decoder (8 by default)
+            counts = [tf * (e - s0) - ((tf - 1) if (k == 0 and r == 0) else 0) if e > s0 else 0 for r, (s0, e) in enumerate(ranges)]
             if mine is not None:
                 assert mine.shape[0] == counts[rank] and tuple(mine.shape[1:]) == tail_shape, (mine.shape, counts, rank)
             pad = torch.zeros(max(counts), *tail_shape, device=self.device, dtype=torch.float32)
