@@ -20,9 +20,11 @@ if which == "attn":
     v = torch.randn(B, H, S, 64, device=dev).bfloat16()
     out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
     sched, pairs = ops.attn_build_schedule(seg, tim)
+    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
+    variant = int(sys.argv[3], 0) if len(sys.argv) > 3 else 0        # pf_attn_desc.variant (0 = default, 3 = one-tile, 0x1k = pair kernel)
     for _ in range(reps):
-        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125)
+        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant=variant, pair_sched=ps)
 elif which == "conv":
     # the widest full-resolution resnet conv of the VAE decode: 128 -> 128, 3x3x3, one 768x1280 frame chunk
     from pyramid_flow_b200.vae import B200CausalVAE, _Conv
