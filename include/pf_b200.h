@@ -273,6 +273,10 @@ PF_API int pf_softmax_rows(void* s_bf16, int64_t rows, int32_t cols, int64_t ld,
 PF_API int pf_pack_latent(const void* z, int32_t z_is_f32, int32_t b, int32_t c, int32_t t, int32_t h, int32_t w,
                           void* y_bf16, int32_t cpad, int32_t y_t_total, int32_t y_t_offset, const float* frame_scale,
                           const float* frame_shift, void* stream);
+/* Cross-fade of neighbouring decoded tiles (blend_v / blend_h, V:397-407), tensors viewed as fp32 [outer, L, inner] with L the
+ * blended axis: b[o, y, i] = a[o, la - extent + y, i] * (1 - y/extent) + b[o, y, i] * (y/extent) for y < extent (in place). */
+PF_API int pf_blend_tiles(const float* a, float* b, int64_t outer, int32_t la, int32_t lb, int64_t inner, int32_t extent,
+                          void* stream);
 
 /* ------------------------------------------------------------------ debug probe (used only by tests/tools)
  * One CTA, one 128 x N x K tcgen05.mma chain with host-chosen descriptor bits, so descriptor encodings can be

@@ -18,7 +18,7 @@ SYMBOLS = [
     "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step", "pf_stage_hop",
-    "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent",
+    "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent", "pf_blend_tiles",
     "pf_ctx_create", "pf_ctx_destroy", "pf_ctx_record_begin", "pf_ctx_record_end", "pf_ctx_replay", "pf_dit_step_flux",
     "pf_dit_step_mmdit", "pf_vae_decode_chunk",
     "pf_peer_alloc", "pf_peer_free", "pf_peer_export", "pf_peer_open", "pf_peer_close", "pf_peer_barrier", "pf_peer_bcast",
@@ -138,6 +138,7 @@ def load() -> C.CDLL:
     lib.pf_cfg_euler_step.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.pf_stage_hop.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float,
                                  C.c_float, C.POINTER(C.c_float), C.c_void_p]
+    lib.pf_blend_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]
     lib.pf_debug_umma.argtypes = [C.POINTER(UmmaProbe), C.c_void_p]
     lib.pf_debug_attn_trace.argtypes = [C.c_void_p]
     lib.pf_debug_attn_cta_trace.argtypes = [C.c_void_p, C.c_int64]

@@ -166,6 +166,22 @@ __global__ void pack_latent_kernel(const T* __restrict__ z, int b, int c, int t,
   y[((((static_cast<size_t>(bb) * y_t_total + tt + y_t_offset) * h + hh) * w + ww)) * cpad + cc] = __float2bfloat16(v);
 }
 
+// Cross-fade of two neighbouring decoded tiles (blend_v / blend_h, V:397-407): tensors viewed as [outer, L, inner] with L the
+// blended axis; b[o, y, i] = a[o, La - extent + y, i] * (1 - y / extent) + b[o, y, i] * (y / extent) for y < extent.
+__global__ void blend_tiles_kernel(const float* __restrict__ a, float* __restrict__ b, long long outer, int la, int lb,
+                                   long long inner, int extent) {
+  const long long total = outer * extent * inner;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long i = idx % inner;
+  const int y = static_cast<int>((idx / inner) % extent);
+  const long long o = idx / (inner * extent);
+  const float w = static_cast<float>(y) / static_cast<float>(extent);
+  const float av = a[(o * la + (la - extent + y)) * inner + i];
+  float* bp = b + (o * lb + y) * inner + i;
+  *bp = av * (1.f - w) + *bp * w;
+}
+
 }  // namespace pf
 
 extern "C" {
@@ -235,6 +251,16 @@ int pf_pack_latent(const void* z, int32_t z_is_f32, int32_t b, int32_t c, int32_
                                                                   static_cast<__nv_bfloat16*>(y), cpad, y_t_total,
                                                                   y_t_offset, frame_scale, frame_shift);
   return check_launch("pf_pack_latent");
+}
+
+
+int pf_blend_tiles(const float* a, float* b, int64_t outer, int32_t la, int32_t lb, int64_t inner, int32_t extent, void* stream) {
+  using namespace pf;
+  PF_REQUIRE(a && b && outer > 0 && inner > 0 && extent > 0 && extent <= la && extent <= lb, "pf_blend_tiles: bad arguments");
+  const long long total = outer * extent * inner;
+  blend_tiles_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, outer, la, lb,
+                                                                                                              inner, extent);
+  return check_launch("pf_blend_tiles");
 }
 
 }  // extern "C"

@@ -616,17 +616,19 @@ class B200CausalVAE(torch.nn.Module):
 
 
 def _blend(a: torch.Tensor, b: torch.Tensor, extent: int, dim: int) -> torch.Tensor:
-    """blend_v / blend_h (V:397-407) vectorised: b[..., y, ...] = a[..., -extent+y, ...]*(1-y/extent) + b*(y/extent)."""
+    """blend_v / blend_h (V:397-407): b[..., y, ...] = a[..., -extent+y, ...]*(1-y/extent) + b*(y/extent), one kernel
+    (pf_blend_tiles) on the contiguous fp32 tiles, in place on b."""
     extent = min(a.shape[dim], b.shape[dim], extent)
     if extent <= 0:
         return b
-    wgt = (torch.arange(extent, device=b.device, dtype=b.dtype) / extent)
-    shape = [1] * b.ndim
-    shape[dim] = extent
-    wgt = wgt.view(shape)
-    sl_b = [slice(None)] * b.ndim
-    sl_b[dim] = slice(0, extent)
-    sl_a = [slice(None)] * a.ndim
-    sl_a[dim] = slice(a.shape[dim] - extent, a.shape[dim])
-    b[tuple(sl_b)] = a[tuple(sl_a)] * (1 - wgt) + b[tuple(sl_b)] * wgt
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.float32
+    assert a.shape[:dim] == b.shape[:dim] and a.shape[dim + 1:] == b.shape[dim + 1:], "tiles must agree off the blended axis"
+    outer = 1
+    for n in b.shape[:dim]:
+        outer *= int(n)
+    inner = 1
+    for n in b.shape[dim + 1:]:
+        inner *= int(n)
+    _lib.check(_lib.load().pf_blend_tiles(a.data_ptr(), b.data_ptr(), outer, a.shape[dim], b.shape[dim], inner, extent,
+                                          _lib.stream_ptr()), "pf_blend_tiles")
     return b
