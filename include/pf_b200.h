@@ -33,6 +33,18 @@ PF_API int pf_device_check(void);
  * that no later launch initialises anything host-side (required before capturing launches into a CUDA graph; also what makes
  * a second GPU driven from the same process work).  Idempotent, thread-safe. */
 PF_API int pf_warmup(void);
+/* Library options: data-path choices that do not change results (same arithmetic, same bits) but are A/B-measured. */
+enum {
+  PF_OPT_GEMM_STAGED_RESID = 0, /* GATE_RESID epilogue: residual read-modify-write transposed through shared memory */
+  PF_OPT_GEMM_WAVE_TILING = 1,  /* wave-quantisation-aware tile width for GEMMs with few rows */
+  PF_OPT_ATTN_PAIR_KERNEL = 2,  /* variant 0 of pf_attn_fwd_masked = the two-q-tile kernel (needs pair_sched) */
+  PF_OPT_COUNT = 3
+};
+#define PF_OPT_DEFAULT_GEMM_STAGED_RESID 0
+#define PF_OPT_DEFAULT_GEMM_WAVE_TILING 0
+#define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 0
+PF_API int pf_set_option(int key, int value);
+PF_API int pf_get_option(int key);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 PF_API int64_t pf_launch_count(void);
 

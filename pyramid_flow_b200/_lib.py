@@ -13,7 +13,7 @@ LIB_PATH = _HERE / "lib" / "libpf_b200.so"
 
 # every symbol include/pf_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
-    "pf_last_error", "pf_version", "pf_device_check", "pf_warmup", "pf_launch_count",
+    "pf_last_error", "pf_version", "pf_device_check", "pf_warmup", "pf_set_option", "pf_get_option", "pf_launch_count",
     "pf_gemm_bf16",
     "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
@@ -27,6 +27,7 @@ SYMBOLS = [
     "pf_debug_attn_cta_trace",
 ]
 
+PF_OPT_GEMM_STAGED_RESID, PF_OPT_GEMM_WAVE_TILING, PF_OPT_ATTN_PAIR_KERNEL = range(3)
 PF_EPI_STORE_BF16, PF_EPI_GELU_BF16, PF_EPI_STORE_F32, PF_EPI_GATE_RESID, PF_EPI_QKV_ROPE, PF_EPI_QKV_GELU = range(6)
 
 
@@ -173,6 +174,14 @@ def require_device() -> None:
 def stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def set_option(key: int, value: int) -> None:
+    check(load().pf_set_option(int(key), int(value)), "pf_set_option")
+
+
+def get_option(key: int) -> int:
+    return int(load().pf_get_option(int(key)))
 
 
 def launch_count() -> int:

@@ -102,6 +102,20 @@ int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
   return 0;
 }
 
+// Library options (pf_set_option): new data paths stay opt-in until a hardware run has validated them; the defaults below are
+// the validated choices.
+static std::atomic<int> g_options[PF_OPT_COUNT] = {};
+static std::once_flag g_options_once;
+static void options_init() {
+  g_options[PF_OPT_GEMM_STAGED_RESID].store(PF_OPT_DEFAULT_GEMM_STAGED_RESID);
+  g_options[PF_OPT_GEMM_WAVE_TILING].store(PF_OPT_DEFAULT_GEMM_WAVE_TILING);
+  g_options[PF_OPT_ATTN_PAIR_KERNEL].store(PF_OPT_DEFAULT_ATTN_PAIR_KERNEL);
+}
+int get_option(int key) {
+  std::call_once(g_options_once, options_init);
+  return (key >= 0 && key < PF_OPT_COUNT) ? g_options[key].load(std::memory_order_relaxed) : 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -210,6 +224,17 @@ int pf_ctx_replay(pf_ctx* c, void* stream) {
 int pf_dit_step_flux(pf_ctx* c, void* stream) { return pf_ctx_replay(c, stream); }
 int pf_dit_step_mmdit(pf_ctx* c, void* stream) { return pf_ctx_replay(c, stream); }
 int pf_vae_decode_chunk(pf_ctx* c, void* stream) { return pf_ctx_replay(c, stream); }
+
+int pf_set_option(int key, int value) {
+  std::call_once(pf::g_options_once, pf::options_init);
+  if (key < 0 || key >= PF_OPT_COUNT) {
+    pf::set_error("pf_set_option: unknown key %d", key);
+    return -1;
+  }
+  pf::g_options[key].store(value);
+  return 0;
+}
+int pf_get_option(int key) { return pf::get_option(key); }
 
 int pf_warmup(void) {
   int rc = pf::warmup_gemm();

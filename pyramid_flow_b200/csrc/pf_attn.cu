@@ -481,7 +481,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 int warmup_attn2();
 int attn2_launch(const pf_attn_desc* d, int poly, cudaStream_t stream);
 constexpr int ATT2_DEFAULT_POLY = 1;   // exponentials on the FMA pipe: 2 of every 8 (tuned on B200)
-constexpr bool ATT2_IS_DEFAULT = false;  // flipped once the two-q-tile kernel is validated on hardware (tests pin both kernels)
 
 int warmup_attn() {
   int rc = warmup_attn2();
@@ -563,7 +562,7 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   // variant: 0 = default (two-q-tile kernel when a pair schedule is given, else the one-tile kernel); 0x10 | k = two-q-tile
   // kernel with k of every 4 exponential pairs on the FMA pipe (k = 0..3); 1 / 2 / 3 = one-tile kernel (polynomial mix / clock
   // trace / plain)
-  const bool use_pair = (d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr && (ATT2_IS_DEFAULT || d->peer_count > 1));
+  const bool use_pair = (d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
   PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
   if (use_pair) {
     PF_REQUIRE(d->pair_sched != nullptr, "pf_attn_fwd_masked: variant 0x%x needs pair_sched", d->variant);

@@ -33,6 +33,7 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
                       const uint32_t* elem_strides = nullptr /* traversal stride per dim (strided convs); NULL = 1 */);
 
 int num_sms();
+int get_option(int key);   // pf_set_option values (include/pf_b200.h PF_OPT_*)
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a process
 // that drives several GPUs must set it on each (thread-safe; ~20 ns on the fast path).
 int ensure_dyn_smem(const void* kernel, int bytes, const char* what);

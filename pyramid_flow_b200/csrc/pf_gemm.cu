@@ -42,6 +42,7 @@ struct GemmArgs {
   // sequence parallel: q/k/v heads go straight into the owning rank's [3][peer_heads][peer_seq][64] buffer (pf_b200.h)
   __nv_bfloat16* peer_qkv[PF_MAX_PEERS];
   int peer_count, peer_heads, peer_seq, peer_row0;
+  int epi_staged;   // GATE_RESID: transposed read-modify-write through shared memory (pf_set_option(PF_OPT_GEMM_STAGED_RESID))
 };
 
 constexpr int BM = 128;
@@ -213,6 +214,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
                                                  g.out_col_begin + n0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) d4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        }
+      } else if (EPI == PF_EPI_GATE_RESID && !g.epi_staged) {
+        // round-1 form: each thread read-modify-writes its own row (32 rows x 16 bytes per warp instruction)
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + out_row * g.ldo +
+                                                 g.out_col_begin + n0);
+          const float4* g4 = reinterpret_cast<const float4*>(g.gate + b * g.gate_batch_stride + n0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 rr = d4[i];
+            const float4 gg = __ldg(g4 + i);
+            rr.x += gg.x * x[4 * i + 0];
+            rr.y += gg.y * x[4 * i + 1];
+            rr.z += gg.z * x[4 * i + 2];
+            rr.w += gg.w * x[4 * i + 3];
+            d4[i] = rr;
+          }
         }
       } else if (EPI == PF_EPI_GATE_RESID) {
         const int lane = threadIdx.x & 31;
@@ -710,6 +728,7 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   g.head_dim = d->head_dim;
   g.seq_len = d->seq_len;
   g.n_split = d->n_split;
+  g.epi_staged = get_option(PF_OPT_GEMM_STAGED_RESID);
   g.peer_count = d->peer_count;
   g.peer_heads = d->peer_heads;
   g.peer_seq = d->peer_seq;
@@ -737,7 +756,7 @@ extern "C" int pf_gemm_bf16(const pf_gemm_desc* d, void* stream_) {
   // persistent grid mostly idle (M=3872, N=1920: 112 tile pairs on 74 SM pairs = 2 waves for 1.5 waves of work, plus a
   // 128-wide tail launch).  A narrower tiling changes neither the K order nor the bits, so pick the one whose wave count x
   // tile cost is smallest (tile efficiencies measured on B200: 256 -> 1.0, 192 -> 0.97, 128 -> 0.90).
-  if (epi != PF_EPI_QKV_GELU && d->kernel_variant == 0) {
+  if (epi != PF_EPI_QKV_GELU && d->kernel_variant == 0 && get_option(PF_OPT_GEMM_WAVE_TILING)) {
     int sms = num_sms();
     if (sms <= 0) sms = 148;
     auto part_cost = [&](int tile_n, int ncols) -> double {

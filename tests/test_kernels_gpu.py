@@ -325,3 +325,48 @@ def test_stage_hop_kernel():
     blocks = rearrange(n, "b c t (h p) (w q) -> (b c t h w) (p q)", p=2, q=2).double()
     emp = blocks.T @ blocks / blocks.shape[0]
     assert (emp.cpu() - cov).abs().max().item() < 0.02
+
+
+def test_gemm_library_options_do_not_change_bits():
+    """pf_set_option data-path choices (GATE_RESID read-modify-write staged through shared memory; wave-quantisation-aware tile
+    width) compute the same sums in the same order: outputs are bit-identical to the default path, for row ranges, ragged M
+    and the sequence-parallel chunk shape (M=3872, N=1920) whose tiling actually changes."""
+    from pyramid_flow_b200 import _lib, ops
+    from pyramid_flow_b200._lib import (PF_EPI_GATE_RESID, PF_EPI_GELU_BF16, PF_EPI_STORE_BF16, PF_OPT_GEMM_STAGED_RESID,
+                                        PF_OPT_GEMM_WAVE_TILING)
+    torch.manual_seed(7)
+    saved = (_lib.get_option(PF_OPT_GEMM_STAGED_RESID), _lib.get_option(PF_OPT_GEMM_WAVE_TILING))
+
+    def run_all():
+        outs = []
+        for (B, S, K, N, r0) in [(2, 300, 384, 384, 40), (1, 3872, 1920, 1920, 0), (2, 777, 512, 1920, 5), (1, 128, 1920, 1920, 0)]:
+            g = torch.Generator(device=DEV).manual_seed(B * 1000 + S)
+            x = (torch.randn(B, S, K, device=DEV, generator=g) * 0.5).bfloat16()
+            w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).bfloat16()
+            bias = torch.randn(N, device=DEV, generator=g) * 0.1
+            resid = torch.randn(B, S, N, device=DEV, generator=g)
+            gate = torch.randn(B, N, device=DEV, generator=g)
+            ops.gemm(x, w, bias, PF_EPI_GATE_RESID, batches=B, rows_per_batch=S, row_begin=r0, row_count=S - r0, out=resid,
+                     gate=gate, gate_batch_stride=N)
+            y = torch.zeros(B, S, N, device=DEV, dtype=torch.bfloat16)
+            ops.gemm(x, w, bias, PF_EPI_GELU_BF16, batches=B, rows_per_batch=S, row_begin=r0, row_count=S - r0, out=y)
+            torch.cuda.synchronize()
+            outs += [resid, y]
+            if S == 300:     # and against fp32 math once
+                want = F.gelu(x[:, r0:].float() @ w.float().t() + bias, approximate="tanh")
+                assert _rel(y[:, r0:], want) < 8e-3
+        return outs
+
+    try:
+        _lib.set_option(PF_OPT_GEMM_STAGED_RESID, 0)
+        _lib.set_option(PF_OPT_GEMM_WAVE_TILING, 0)
+        base = run_all()
+        for staged, wave in ((1, 0), (0, 1), (1, 1)):
+            _lib.set_option(PF_OPT_GEMM_STAGED_RESID, staged)
+            _lib.set_option(PF_OPT_GEMM_WAVE_TILING, wave)
+            got = run_all()
+            for a, b in zip(base, got):
+                assert torch.equal(a, b), (staged, wave)
+    finally:
+        _lib.set_option(PF_OPT_GEMM_STAGED_RESID, saved[0])
+        _lib.set_option(PF_OPT_GEMM_WAVE_TILING, saved[1])

@@ -457,8 +457,31 @@ def group_gemm_epi_perf():
         try:
             ms = _time_cuda(fn)
             print(f"[gemm_epi_perf] m={m} n={n} k={k} {name}: {ms:.3f} ms = {fl/ms:.0f} TF/s", flush=True)
+            if epi == 3:      # the staged (transposed) read-modify-write, pf_set_option(PF_OPT_GEMM_STAGED_RESID)
+                from pyramid_flow_b200 import _lib
+                old = _lib.get_option(_lib.PF_OPT_GEMM_STAGED_RESID)
+                _lib.set_option(_lib.PF_OPT_GEMM_STAGED_RESID, 1 - old)
+                ms2 = _time_cuda(fn)
+                _lib.set_option(_lib.PF_OPT_GEMM_STAGED_RESID, old)
+                print(f"[gemm_epi_perf] m={m} n={n} k={k} {name} with staged={1 - old}: {ms2:.3f} ms = {fl/ms2:.0f} TF/s", flush=True)
         except Exception as e:  # noqa: BLE001
             print(f"[gemm_epi_perf] {name}: EXC {e}", flush=True)
+    # the sequence-parallel chunk shape (8 GPUs): wave-quantisation-aware tile width on/off, K = 1920 / 7680 / 9600
+    from pyramid_flow_b200 import _lib
+    for kk in (1920, 7680, 9600):
+        mm, nn = 3872, 1920
+        xs = (torch.randn(mm, kk, device=dev) * 0.5).bfloat16()
+        ws = (torch.randn(nn, kk, device=dev) * 0.05).bfloat16()
+        hh = torch.zeros(1, mm, nn, device=dev, dtype=torch.float32)
+        gg = torch.randn(1, nn, device=dev) * 0.1
+        f2 = lambda: ops.gemm(xs, ws, None, 3, rows_per_batch=mm, out=hh, gate=gg, gate_batch_stride=nn, batches=1)
+        res = {}
+        for wave in (0, 1):
+            _lib.set_option(_lib.PF_OPT_GEMM_WAVE_TILING, wave)
+            res[wave] = _time_cuda(f2, iters=20)
+        _lib.set_option(_lib.PF_OPT_GEMM_WAVE_TILING, 0)
+        fl2 = 2.0 * mm * nn * kk / 1e9
+        print(f"[gemm_epi_perf] m={mm} n={nn} k={kk} gate_resid: default tiling {res[0]:.3f} ms = {fl2/res[0]:.0f} TF/s | wave-aware {res[1]:.3f} ms = {fl2/res[1]:.0f} TF/s", flush=True)
 
 
 def group_gemm_qkv_perf():
