@@ -576,6 +576,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.exchange is None:
+        from pyramid_flow_b200.dit import DEFAULT_EXCHANGE
+        args.exchange = DEFAULT_EXCHANGE
     parity_ref = None
     if world > 1:
         # the SAME step on one GPU (every rank computes it, host-launched) before the layout is attached: the reference the
@@ -747,7 +750,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="(debug) skip the CPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="(debug) launch every kernel from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--model", default="flux", choices=["flux", "mmdit"], help="flux = miniFLUX (the headline, configs[2]); mmdit = SD3 MMDiT 768p/5s (configs[4])")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: peer-memory fused exchange (default) or NCCL all-to-all (A/B)")
+    ap.add_argument("--exchange", default=None, choices=["peer", "nccl"], help="N>1: peer-memory fused exchange (default) or NCCL all-to-all (A/B)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
     ap.add_argument("--no-video", action="store_true", help="skip the 768p/10s end-to-end sampler + decode leg (~1 min at N=1)")
     ap.add_argument("--no-eager", action="store_true", help="skip the reference-eager-on-GPU baseline leg")

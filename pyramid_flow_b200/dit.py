@@ -123,6 +123,11 @@ def build_seq_plan(clip_shapes: Sequence[Sequence[int]], mask_cpu: torch.Tensor,
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# default formulation of the sequence-parallel exchange: "peer" (remote stores fused into the kernels over NVLink peer memory) once
+# validated on hardware, else "nccl" (all_to_all_single)
+DEFAULT_EXCHANGE = "nccl"
+
+
 class _Cfg(dict):
     __getattr__ = dict.__getitem__
 
@@ -350,7 +355,7 @@ class B200FluxTransformer(torch.nn.Module):
         return plan
 
     # -- parallel layout (CFG x sequence parallel, sp.py) ---------------------------------------------------------------
-    def set_parallel_layout(self, layout, exchange: str = "peer") -> None:
+    def set_parallel_layout(self, layout, exchange: str = DEFAULT_EXCHANGE) -> None:
         """Attach a `sp.ParallelLayout` (after torch.distributed is initialised); weights are replicated.
         exchange = "peer": q/k/v and the attention output cross NVLink as remote stores fused into the QKV GEMM / attention
         epilogues + flag barriers (csrc/pf_peer.cu): no NCCL call in the step, CUDA-graph capturable.  "nccl": the
@@ -396,7 +401,7 @@ class B200FluxTransformer(torch.nn.Module):
         lay = getattr(self, "layout", None)
         # the NCCL formulation of the parallel step stays host-launched (capturing its all-to-alls hung on the 2-GPU box in
         # round 1); the peer-memory formulation is plain kernels and is captured like the single-GPU step
-        nccl_par = lay is not None and lay.enabled and getattr(self, "exchange", "peer") == "nccl"
+        nccl_par = lay is not None and lay.enabled and getattr(self, "exchange", DEFAULT_EXCHANGE) == "nccl"
         if self.use_cuda_graph and not nccl_par and not self.timer.enabled and self.attn_events is None:
             return self._forward_graphed(list(clips), timestep_ratio, encoder_hidden_states, encoder_attention_mask,
                                          pooled_projections)
@@ -429,7 +434,7 @@ class B200FluxTransformer(torch.nn.Module):
                 from . import sp as SP
                 c0, c1 = SP.chunk_bounds(plan.seq, lay.sp, lay.sp_rank)
                 self._workspace(1, plan, c1 - c0, self._hp)
-                if getattr(self, "exchange", "peer") == "peer":
+                if getattr(self, "exchange", DEFAULT_EXCHANGE) == "peer":
                     self._peer_exchange(plan, self._hp, self._hp * 64 + 4 * self.cfg.inner_dim)
             else:
                 self._workspace(clips[-1].shape[0], plan)
@@ -494,7 +499,7 @@ class B200FluxTransformer(torch.nn.Module):
         nm = self.n_mod
         ldc = wa + 4 * d
         # peer-memory formulation of the exchanges (sp.PeerExchange): `cat` and the gathered q/k/v live in the peer arena
-        px = self._peer_exchange(plan, hp, ldc) if (par and getattr(self, "exchange", "peer") == "peer") else None
+        px = self._peer_exchange(plan, hp, ldc) if (par and getattr(self, "exchange", DEFAULT_EXCHANGE) == "peer") else None
         if px is not None and nsp > 1:
             cat = px.cat(sl)
             qkv_x = px.qkv(s)                          # [3, Hg, S, 64]: my head group over the whole sequence
