@@ -1,5 +1,5 @@
 """Stage the reference's Python packages for the GPU box: /root/reference/{pyramid_dit,video_vae,diffusion_schedulers,
-trainer_misc} -> baseline/_ref/ (git-ignored, NOT gpurun-ignored: it travels with the snapshot like the built .so files).
+trainer_misc} (+ the top-level utils.py they import) -> baseline/_ref/ (git-ignored, NOT gpurun-ignored: it travels with the snapshot like the built .so files).
 
 TEST / BASELINE INFRASTRUCTURE.  The GPU box has no /root/reference; the drop-in test (tests/test_dropin_gpu.py) and
 bench.py's `gpu_eager_baseline` leg import the UNMODIFIED reference from this copy through oracle/pin/ref_shim.py.  Nothing is
@@ -18,6 +18,7 @@ ROOT = Path(__file__).resolve().parents[2]
 SRC = Path("/root/reference")
 DST = ROOT / "baseline" / "_ref"
 PACKAGES = ("pyramid_dit", "video_vae", "diffusion_schedulers", "trainer_misc")
+TOP_FILES = ("utils.py",)          # video_vae/modeling_causal_conv.py:11 imports the context-parallel helpers from it
 
 
 def stage(verbose: bool = True) -> bool:
@@ -35,6 +36,10 @@ def stage(verbose: bool = True) -> bool:
             if not out.exists() or not filecmp.cmp(f, out, shallow=False):
                 shutil.copyfile(f, out)
             n += 1
+    for name in TOP_FILES:
+        if not (DST / name).exists() or not filecmp.cmp(SRC / name, DST / name, shallow=False):
+            shutil.copyfile(SRC / name, DST / name)
+        n += 1
     (DST / "STAGED_FROM").write_text(f"{SRC} (unmodified copy of {', '.join(PACKAGES)}; {n} files)\n")
     if verbose:
         print(f"[stage_reference] {n} files -> {DST}")

@@ -188,13 +188,14 @@ def test_attention_adversarial_score_jumps():
             assert own == sched[0, t, 1:1 + int(sched[0, t, 0])].tolist()
     sg, tm = seg.to(DEV), tim.to(DEV)
     ref, _ = _attn_ref(q, k, v, sg, tm)
-    for variant in ATTN_VARIANTS:
+    # the one-tile kernel (variant 3) exponentiates against a max that is one tile stale and is NOT safe on such inputs (it
+    # is kept for A/B timing only); the two-q-tile kernel has an exact per-row max and must be exact here
+    for variant in [v_ for v_ in ATTN_VARIANTS if v_ & 0x10]:
         out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
         ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=psched.to(DEV))
         torch.cuda.synchronize()
         assert bool(torch.isfinite(out.float()).all()), variant
-        if variant != 3:      # the one-tile kernel's reference max is one tile stale: it saturates (finite) on such jumps
-            assert (out.float() - ref).abs().max().item() < 3e-2, variant
+        assert (out.float() - ref).abs().max().item() < 3e-2, variant
 
 
 def test_elementwise_kernels():
