@@ -479,7 +479,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 int warmup_attn2();
-int attn2_launch(const pf_attn_desc* d, int poly, cudaStream_t stream);
+int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t stream);
 constexpr int ATT2_DEFAULT_POLY = 1;   // exponentials on the FMA pipe: 2 of every 8 (tuned on B200)
 
 int warmup_attn() {
@@ -562,13 +562,15 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   // variant: 0 = default (two-q-tile kernel when a pair schedule is given, else the one-tile kernel); 0x10 | k = two-q-tile
   // kernel with k of every 4 exponential pairs on the FMA pipe (k = 0..3); 1 / 2 / 3 = one-tile kernel (polynomial mix / clock
   // trace / plain)
+  PF_REQUIRE((d->variant & ~0x33) == 0, "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
   const bool use_pair = (d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
   PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
   if (use_pair) {
     PF_REQUIRE(d->pair_sched != nullptr, "pf_attn_fwd_masked: variant 0x%x needs pair_sched", d->variant);
-    const int poly = (d->variant & 0x10) ? (d->variant & 0xf) : ATT2_DEFAULT_POLY;
-    PF_REQUIRE(poly >= 0 && poly <= 3, "pf_attn_fwd_masked: bad polynomial share %d", poly);
-    return attn2_launch(d, poly, stream);
+    // 0x10 | k: k of every 4 exponential pairs on the FMA pipe; | 0x20: WITHOUT the ping-pong token (A/B)
+    const int poly = (d->variant & 0x10) ? (d->variant & 0x3) : ATT2_DEFAULT_POLY;
+    const int pingpong = (d->variant & 0x20) ? 0 : 1;
+    return attn2_launch(d, poly, pingpong, stream);
   }
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};

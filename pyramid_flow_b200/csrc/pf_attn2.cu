@@ -77,6 +77,15 @@ __device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// named barriers 1 / 2 = the "XU token" of softmax warpgroup 0 / 1 (ping-pong, see the kernel comment)
+__device__ __forceinline__ void a2_token_wait(int id) {
+  if (id == 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+__device__ __forceinline__ void a2_token_pass(int id) {
+  if (id == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
+  else asm volatile("bar.arrive 2, 256;" ::: "memory");
+}
 __device__ __forceinline__ float a2_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -146,7 +155,7 @@ __device__ __forceinline__ void a2_exp32(const uint32_t (&v)[32], uint32_t (&pk)
   }
 }
 
-template <int POLY>
+template <int POLY, int PINGPONG>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Attn2Args a) {
@@ -296,6 +305,13 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       float m_run = -INFINITY;   // reference max (raw score units) the accumulators are scaled by; -inf: nothing finite yet
       uint64_t l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);
       int entry = sched[1];
+      // Ping-pong: the exponential phase (the XU-bound part) of the two warpgroups is strictly alternated with a token passed
+      // through named barriers.  Left alone the two q tiles fall into lockstep (both S tiles become ready together), contend
+      // for the XU during their exps and leave it idle while both load / reduce / store: measured XU pipe 59 % busy, the same
+      // as the one-tile kernel (profiles/r02_attn2_lockstep_ncu.txt).  With the token one warpgroup's TMEM loads, max and P
+      // store run under the other's exponentials.
+      const bool pingpong = PINGPONG && act_lo;
+      if (pingpong && X == 1) a2_token_pass(1);
 
       for (int j = 0; j < n_kv; ++j) {
         const int kt = entry >> 4;
@@ -368,6 +384,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
 
         // ---- first half of the row
+        if (pingpong) a2_token_wait(1 + X);
         uint32_t pk0[16], pk1[16];
         if (POLY > 0 && !masked) {
           a2_exp32<POLY>(v0, pk0, c2, nm2, l01, l23);
@@ -402,6 +419,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           a2_exp32<0>(v2, pk0, c2, nm2, l01, l23);
           a2_exp32<0>(v3, pk1, c2, nm2, l01, l23);
         }
+        if (pingpong && !(X == 1 && j == n_kv - 1)) a2_token_pass(2 - X);   // the other warpgroup's exponentials may start
         tmem_st16(t_p + 32, pk0);
         tmem_st16(t_p + 48, pk1);
         tmem_st_wait();
@@ -453,24 +471,25 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
 }
 
-template <int POLY>
+template <int POLY, int PINGPONG>
 static int attn2_launch_t(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream) {
-  auto kern = attn2_fwd_kernel<POLY>;
+  auto kern = attn2_fwd_kernel<POLY, PINGPONG>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), A2_SMEM_BYTES, "attn2_fwd_kernel")) return rc;
   kern<<<grid, A2_THREADS, A2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked(pair kernel)");
 }
 
 int warmup_attn2() {
-  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0>), A2_SMEM_BYTES, "attn2_fwd_kernel<0>");
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<1>), A2_SMEM_BYTES, "attn2_fwd_kernel<1>");
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<2>), A2_SMEM_BYTES, "attn2_fwd_kernel<2>");
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<3>), A2_SMEM_BYTES, "attn2_fwd_kernel<3>");
+  int rc = 0;
+#define PF_WARM2(P, Q) if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<P, Q>), A2_SMEM_BYTES, "attn2_fwd_kernel")
+  PF_WARM2(0, 0); PF_WARM2(1, 0); PF_WARM2(2, 0); PF_WARM2(3, 0);
+  PF_WARM2(0, 1); PF_WARM2(1, 1); PF_WARM2(2, 1); PF_WARM2(3, 1);
+#undef PF_WARM2
   return rc;
 }
 
 // called by pf_attn_fwd_masked (pf_attn.cu) after argument validation; poly = exponentials per 8 on the FMA pipe / 2
-int attn2_launch(const pf_attn_desc* d, int poly, cudaStream_t stream) {
+int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t stream) {
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};
   for (int i = 0; i < 3; ++i) {
@@ -515,11 +534,15 @@ int attn2_launch(const pf_attn_desc* d, int poly, cudaStream_t stream) {
   // pair p covers tiles q_tiles-2-2p and q_tiles-1-2p: launch the pairs whose upper tile is >= q_tile_begin
   const int pairs = (a.q_tiles - a.q_tile_begin + 1) / 2;
   dim3 grid(pairs, d->heads, d->batch);
-  switch (poly) {
-    case 0: return attn2_launch_t<0>(tm, a, grid, stream);
-    case 1: return attn2_launch_t<1>(tm, a, grid, stream);
-    case 2: return attn2_launch_t<2>(tm, a, grid, stream);
-    case 3: return attn2_launch_t<3>(tm, a, grid, stream);
+  switch (poly * 2 + (pingpong ? 1 : 0)) {
+    case 0: return attn2_launch_t<0, 0>(tm, a, grid, stream);
+    case 1: return attn2_launch_t<0, 1>(tm, a, grid, stream);
+    case 2: return attn2_launch_t<1, 0>(tm, a, grid, stream);
+    case 3: return attn2_launch_t<1, 1>(tm, a, grid, stream);
+    case 4: return attn2_launch_t<2, 0>(tm, a, grid, stream);
+    case 5: return attn2_launch_t<2, 1>(tm, a, grid, stream);
+    case 6: return attn2_launch_t<3, 0>(tm, a, grid, stream);
+    case 7: return attn2_launch_t<3, 1>(tm, a, grid, stream);
   }
   set_error("pf_attn_fwd_masked: bad poly %d", poly);
   return -1;

@@ -95,8 +95,9 @@ def test_gemm_epilogues_row_ranges():
     assert _rel(cat[..., D:], F.gelu(x.float() @ wm.float().t() + bm, approximate="tanh")) < 8e-3
 
 
-# pf_attn_desc.variant: 3 = one-q-tile kernel, 0x10 | k = two-q-tile kernel with k of every 4 exponential pairs on the FMA pipe
-ATTN_VARIANTS = [3, 0x10, 0x11, 0x12, 0x13, 0]
+# pf_attn_desc.variant: 3 = one-q-tile kernel, 0x10 | k = two-q-tile kernel with k of every 4 exponential pairs on the FMA pipe,
+# | 0x20 = without the ping-pong token between its two softmax warpgroups
+ATTN_VARIANTS = [3, 0x10, 0x11, 0x12, 0x13, 0x30, 0x31, 0]
 
 
 def _attn_ref(q, k, v, sg, tm):
@@ -317,7 +318,7 @@ def test_stage_hop_kernel():
         L = torch.linalg.cholesky(cov).float().to(DEV)
         zb = rearrange(z, "b c t (h p) (w q) -> (b c t h w) (p q)", p=2, q=2)
         nb = rearrange(zb @ L.T, "(b c t h w) (p q) -> b c t (h p) (w q)", b=2, c=16, t=3, h=12, w=20, p=2, q=2)
-        up = torch.nn.functional.interpolate(x.float().flatten(0, 1), scale_factor=(1, 2, 2), mode="nearest").view(2, 16, 3, 24, 40)
+        up = torch.nn.functional.interpolate(x.float(), scale_factor=(1, 2, 2), mode="nearest")
         ref = alpha * up + beta * nb
         tol = 1e-5 if dtype == torch.float32 else 2e-2
         assert (out.float() - ref).abs().max().item() < tol
