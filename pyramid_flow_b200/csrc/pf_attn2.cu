@@ -51,6 +51,7 @@ struct Attn2Args {
   // sequence parallel: output rows go straight into the owning rank's buffer (pf_b200.h)
   __nv_bfloat16* peer_out[PF_MAX_PEERS];
   int peer_count, peer_chunk_rows, peer_col_begin;
+  uint32_t zero;   // always 0, opaque to ptxas: lets the exponential loop express "wait for a later MUFU" as a data dependency
 };
 
 // ---- packed fp32x2 helpers (sm_100: FFMA2 / FADD2) -------------------------------------------------------------------
@@ -117,6 +118,80 @@ __device__ __forceinline__ void a2_mask32(uint32_t (&v)[32], uint32_t bits) {
 // POLY of every 4 pairs take the FMA-pipe path: x = n + f (round to nearest, f in [-0.5, 0.5]), 2^f by a cubic (rel. error
 // 6e-4, bf16 P carries 4e-3), n added into the exponent field (LEA).  x <= 8 by construction (lazy-rescale invariant) and is
 // clamped at -126 from below; masked tiles (scores of -inf) always take the MUFU path.
+// volatile forms: ptxas keeps volatile asm statements in program order, which is how the exponential loop below pins the
+// distance between a MUFU and its consumers
+__device__ __forceinline__ float a2_ex2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t f2_add_ordered(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_ordered(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// Same result as two a2_exp32 calls on (va, vb), software-pipelined by hand: the row sum / bf16 pack of pair i is issued
+// A2_EXP_LAG pairs (2 x A2_EXP_LAG MUFU.EX2 = 16 x A2_EXP_LAG XU clocks) after its exponentials.  Left to ptxas the consumers sat
+// two MUFUs behind their producers; a warp then stalls on the MUFU latency at every pair, the XU queue drains, and one warp
+// keeps the XU pipe only ~50 % busy (tools/probes/tmem_probe.cu: 7.9 ex2/clk/SM with one such warp per SMSP, 11.3 with two;
+// attn2 in lockstep: XU 59 %, 0.34 IPC per SMSP, profiles/r02_attn2_lockstep_ncu.txt).  The polynomial pairs' FMA-pipe work
+// is not pinned and fills issue slots between MUFUs.
+constexpr int A2_EXP_LAG = 5;
+template <int POLY>
+__device__ __forceinline__ void a2_exp64(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t (&pka)[16],
+                                         uint32_t (&pkb)[16], uint64_t c2, uint64_t nm2, uint64_t& l01, uint64_t& l23,
+                                         uint32_t zero) {
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f);   // 1.5 * 2^23
+  const uint64_t k3 = f2_pack(0.0555041086648216f, 0.0555041086648216f);
+  const uint64_t k2 = f2_pack(0.2402264923172690f, 0.2402264923172690f);
+  const uint64_t k1 = f2_pack(0.6931471805599453f, 0.6931471805599453f);
+  const uint64_t one = f2_pack(1.f, 1.f);
+  float p[64];
+#pragma unroll
+  for (int i = 0; i < 32 + A2_EXP_LAG; ++i) {
+    if (i < 32) {
+      const uint32_t s0 = i < 16 ? va[2 * i] : vb[2 * i - 32], s1 = i < 16 ? va[2 * i + 1] : vb[2 * i - 31];
+      const uint64_t x = f2_fma(f2_pack(__uint_as_float(s0), __uint_as_float(s1)), c2, nm2);
+      float x0, x1;
+      f2_unpack(x, x0, x1);
+      if ((i & 3) < POLY) {
+        const uint64_t xc = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+        const uint64_t t = f2_add(xc, magic);
+        const uint64_t f = f2_sub(xc, f2_sub(t, magic));
+        uint64_t q = f2_fma(f, k3, k2);
+        q = f2_fma(q, f, k1);
+        q = f2_fma(q, f, one);
+        float q0, q1, t0, t1;
+        f2_unpack(q, q0, q1);
+        f2_unpack(t, t0, t1);
+        p[2 * i] = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+        p[2 * i + 1] = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+      } else {
+        p[2 * i] = a2_ex2(x0);
+        p[2 * i + 1] = a2_ex2(x1);
+      }
+    }
+    if (i >= A2_EXP_LAG) {
+      const int k = i - A2_EXP_LAG;
+      float a = p[2 * k];
+      // ptxas schedules by data dependencies only (volatile asm does not pin SASS order): OR-ing in `later & 0` makes pair k's
+      // consumers depend on the MUFU of pair k + LAG, so they are placed LAG pairs behind and the XU queue stays full
+      if (A2_EXP_LAG > 0 && k + A2_EXP_LAG < 32 && ((k + A2_EXP_LAG) & 3) >= POLY)
+        a = __uint_as_float(__float_as_uint(a) | (__float_as_uint(p[2 * (k + A2_EXP_LAG) + 1]) & zero));
+      if (k & 1) l23 = f2_add(l23, f2_pack(a, p[2 * k + 1]));
+      else l01 = f2_add(l01, f2_pack(a, p[2 * k + 1]));
+      if (k < 16) pka[k] = pack_bf16x2(a, p[2 * k + 1]);
+      else pkb[k - 16] = pack_bf16x2(a, p[2 * k + 1]);
+    }
+  }
+}
+
 template <int POLY>
 __device__ __forceinline__ void a2_exp32(const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t c2, uint64_t nm2, uint64_t& l01,
                                          uint64_t& l23) {
@@ -386,13 +461,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         // ---- first half of the row
         if (pingpong) a2_token_wait(1 + X);
         uint32_t pk0[16], pk1[16];
-        if (POLY > 0 && !masked) {
-          a2_exp32<POLY>(v0, pk0, c2, nm2, l01, l23);
-          a2_exp32<POLY>(v1, pk1, c2, nm2, l01, l23);
-        } else {
-          a2_exp32<0>(v0, pk0, c2, nm2, l01, l23);
-          a2_exp32<0>(v1, pk1, c2, nm2, l01, l23);
-        }
+        if (POLY > 0 && !masked) a2_exp64<POLY>(v0, v1, pk0, pk1, c2, nm2, l01, l23, a.zero);
+        else a2_exp64<0>(v0, v1, pk0, pk1, c2, nm2, l01, l23, a.zero);
         // ---- P(j-1) consumed and O(j-1) produced before P is overwritten / O is rescaled
         if (j > 0) {
           if (!pv_ok) mbar_wait(&bar_pv_done[X], (j - 1) & 1);
@@ -412,13 +482,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_st16(t_p, pk0);
         tmem_st16(t_p + 16, pk1);
         // ---- second half
-        if (POLY > 0 && !masked) {
-          a2_exp32<POLY>(v2, pk0, c2, nm2, l01, l23);
-          a2_exp32<POLY>(v3, pk1, c2, nm2, l01, l23);
-        } else {
-          a2_exp32<0>(v2, pk0, c2, nm2, l01, l23);
-          a2_exp32<0>(v3, pk1, c2, nm2, l01, l23);
-        }
+        if (POLY > 0 && !masked) a2_exp64<POLY>(v2, v3, pk0, pk1, c2, nm2, l01, l23, a.zero);
+        else a2_exp64<0>(v2, v3, pk0, pk1, c2, nm2, l01, l23, a.zero);
         if (pingpong && !(X == 1 && j == n_kv - 1)) a2_token_pass(2 - X);   // the other warpgroup's exponentials may start
         tmem_st16(t_p + 32, pk0);
         tmem_st16(t_p + 48, pk1);
@@ -514,6 +579,7 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t str
   a.time = d->time;
   a.psched = d->pair_sched;
   a.sched_stride = d->sched_stride;
+  a.zero = 0u;
   a.peer_count = d->peer_count;
   a.peer_chunk_rows = d->peer_chunk_rows;
   a.peer_col_begin = d->peer_col_begin;

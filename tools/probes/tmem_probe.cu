@@ -98,6 +98,77 @@ __global__ void __launch_bounds__(512, 1) probe(unsigned long long* out, int ite
   }
 }
 
+// Consumer-lag experiment: 128 exponentials per thread per iteration; the row-sum / pack of pair k is forced (by a data
+// dependency through an opaque zero) to wait for the MUFU results of pair k + LAG.  LAG = 0 is "consume at once".
+template <int LAG>
+__global__ void __launch_bounds__(512, 1) lag_probe(unsigned long long* out, int iters, int nwarps, float c, float m, uint32_t zero) {
+  const int warp = threadIdx.x >> 5;
+  float v[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) v[i] = 0.001f * (threadIdx.x + i);
+  uint64_t l01 = pk(0.f, 0.f), l23 = pk(0.f, 0.f);
+  uint32_t acc = 0;
+  const uint64_t c2 = pk(c, c), m2 = pk(-m, -m);
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  if (warp < nwarps) {
+    for (int it = 0; it < iters; ++it) {
+      float p[128];
+#pragma unroll
+      for (int i = 0; i < 64 + LAG; ++i) {
+        if (i < 64) {
+          uint64_t x;
+          asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(pk(v[2 * i], v[2 * i + 1])), "l"(c2), "l"(m2));
+          float x0, x1;
+          upk(x, x0, x1);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[2 * i]) : "f"(x0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[2 * i + 1]) : "f"(x1));
+        }
+        if (i >= LAG) {
+          const int k = i - LAG;
+          float a = p[2 * k], b = p[2 * k + 1];
+          if (LAG > 0 && k + LAG < 64) a = __uint_as_float(__float_as_uint(a) | (__float_as_uint(p[2 * (k + LAG) + 1]) & zero));
+          uint64_t s;
+          asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(k & 1 ? l23 : l01), "l"(pk(a, b)));
+          if (k & 1) l23 = s; else l01 = s;
+          uint32_t pkd;
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pkd) : "f"(b), "f"(a));
+          acc ^= pkd;
+          v[2 * k] = a * 0.25f;
+          v[2 * k + 1] = b * 0.25f;
+        }
+      }
+    }
+  }
+  const unsigned long long t1 = clock64();
+  __syncthreads();
+  float s0, s1, s2, s3;
+  upk(l01, s0, s1);
+  upk(l23, s2, s3);
+  float s = s0 + s1 + s2 + s3;
+  for (int i = 0; i < 128; ++i) s += v[i];
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  if (s == 12345.678f || acc == 0x12345678u) out[1] = (unsigned long long)s;
+}
+
+template <int LAG>
+void run_lag(int nwarps) {
+  unsigned long long* out;
+  cudaMalloc(&out, 16);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int iters = 2000;
+  lag_probe<LAG><<<sms, 512>>>(out, 50, nwarps, 1.0f, 0.5f, 0u);
+  lag_probe<LAG><<<sms, 512>>>(out, iters, nwarps, 1.0f, 0.5f, 0u);
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long h[2] = {0, 0};
+  cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+  const double clk = double(h[0]) / iters;
+  printf("[tmem_probe] softmax stream, consumer lag %2d pairs, %2d warps: %8.1f clk per 128 exps/thread | ex2 %5.2f /clk/SM (%s)\n", LAG,
+         nwarps, clk, 4096.0 * nwarps / clk, cudaGetErrorString(e));
+  cudaFree(out);
+}
+
 template <int MODE>
 void run(const char* name, int nwarps) {
   unsigned long long* out;
@@ -124,5 +195,12 @@ int main() {
   for (int w : {1, 4, 8, 16}) run<1>("LDTM 4 x x32 only", w);
   for (int w : {4, 8, 16}) run<2>("softmax stream only", w);
   for (int w : {4, 8, 16}) run<3>("LDTM + softmax stream", w);
+  for (int w : {4, 8}) {
+    run_lag<0>(w);
+    run_lag<2>(w);
+    run_lag<4>(w);
+    run_lag<6>(w);
+    run_lag<10>(w);
+  }
   return 0;
 }
