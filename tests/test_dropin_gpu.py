@@ -88,10 +88,14 @@ def test_unmodified_generate_with_swapped_dit(ref, golden_dir):
         assert lat.shape == g["latents"].shape
         outs[name] = lat.float().cpu()
     gold = g["latents"]
-    r_ref, r_ours, r_pair = _rel_mse(outs["reference"], gold), _rel_mse(outs["b200"], gold), _rel_mse(outs["b200"], outs["reference"])
-    print(f"generate() final latents, relative MSE vs the CPU fp32 golden: reference-on-GPU (bf16 autocast) {r_ref:.3e}, "
-          f"B200 drop-in {r_ours:.3e}; drop-in vs reference-on-GPU {r_pair:.3e}; |latent| mean {gold.abs().mean():.3f}")
-    assert r_ours < 2e-3 and r_ours <= 1.5 * r_ref + 2e-4, "the drop-in must be as close to the fp32 loop as the reference's own bf16 run"
+    r_pair = _rel_mse(outs["b200"], outs["reference"])
+    r_ref, r_ours = _rel_mse(outs["reference"], gold), _rel_mse(outs["b200"], gold)
+    print(f"generate() final latents: drop-in vs the reference's own modules on the same GPU (both bf16): relative MSE {r_pair:.3e}; "
+          f"|latent| mean {outs['reference'].abs().mean():.3f}.  (vs the CPU fp32 golden: reference {r_ref:.3e}, drop-in {r_ours:.3e} -- "
+          f"not comparable: on the GPU the pipeline draws its start noise in bf16, a different random stream than the fp32 CPU run)")
+    # measured 2.96e-4 on B200 (round 2): 6 Euler steps of bf16 latents through two different bf16 implementations of the DiT
+    assert r_pair < 1e-3 and outs["reference"].abs().mean().item() > 1.0
+    assert abs(r_ours - r_ref) < 0.05 * r_ref + 1e-3, "both runs must sit at the same distance from the fp32 CPU run"
 
 
 def test_unmodified_generate_i2v_and_decode_latent_with_swapped_vae(ref, golden_dir):
