@@ -13,8 +13,10 @@ pytestmark = pytest.mark.gpu
 # Measured on B200 (round 2, gpurun_out/r2_tests1.log): 8+16 blocks @ S=15488: max-abs 1.159e-2, mse 5.80e-6 (2+2 blocks at the
 # same size: 9.84e-3 / 4.37e-6 -- the fp32 residual stream keeps the growth over 24 blocks at ~18 %); MMDiT 24 blocks:
 # 1.129e-2 / 6.10e-6 (3 blocks: 8.6e-3 / 4.0e-6).  Thresholds = measured x 1.3.
-TOL_FULL_MAX_ABS = 1.5e-2
-TOL_FULL_MSE = 7.6e-6
+TOL_FULL_MAX_ABS = 1.5e-2       # fp32 velocity store: measured 1.159e-2
+TOL_FULL_MSE = 7.6e-6           #                       measured 5.80e-6
+TOL_FULL_BF16_MAX_ABS = 2.5e-2  # bf16 velocity store (what the pipeline receives): measured 1.898e-2 -- |v| reaches 5.6 here, where
+TOL_FULL_BF16_MSE = 1.22e-5     # half a bf16 ulp is 1.6e-2; measured mse 9.36e-6
 TOL_MMDIT24_MAX_ABS = 1.47e-2
 TOL_MMDIT24_MSE = 8.0e-6
 
@@ -70,8 +72,9 @@ def test_full_depth_full_size_flux_step_matches_oracle():
     print(f"FULL DEPTH 8+16 @ S=15488: bf16-out max_abs {err:.3e} mse {mse:.3e} | fp32-out max_abs {err32:.3e} mse {mse32:.3e} "
           f"| |v| mean {ref.abs().mean():.3f} max {ref.abs().max():.2f}")
     assert ref.abs().mean().item() > 0.1, "degenerate oracle output"
-    assert err < TOL_FULL_MAX_ABS and mse < TOL_FULL_MSE
-    assert err32 <= err + 4e-3 and mse32 <= mse * 1.05      # the bf16 store can only add up to half an ulp
+    assert err32 < TOL_FULL_MAX_ABS and mse32 < TOL_FULL_MSE
+    assert err < TOL_FULL_BF16_MAX_ABS and mse < TOL_FULL_BF16_MSE
+    assert mse32 <= mse      # the bf16 store can only add error
 
 
 def test_24_block_mmdit_step_matches_oracle():
