@@ -40,8 +40,8 @@ enum {
   PF_OPT_ATTN_PAIR_KERNEL = 2,  /* variant 0 of pf_attn_fwd_masked = the two-q-tile kernel (needs pair_sched) */
   PF_OPT_COUNT = 3
 };
-#define PF_OPT_DEFAULT_GEMM_STAGED_RESID 0
-#define PF_OPT_DEFAULT_GEMM_WAVE_TILING 0
+#define PF_OPT_DEFAULT_GEMM_STAGED_RESID 1
+#define PF_OPT_DEFAULT_GEMM_WAVE_TILING 1
 #define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 0
 PF_API int pf_set_option(int key, int value);
 PF_API int pf_get_option(int key);
