@@ -316,7 +316,7 @@ PF_API int pf_debug_umma(const pf_umma_probe* p, void* stream);
  * and the MMA issuer, first 48 kv tiles), filled by pf_attn_fwd_masked launches with variant bit 1 (value 2) set.
  * NULL disables.  Test/profiling aid only (tools/gpu_check.py attn_trace). */
 PF_API int pf_debug_attn_trace(void* device_buf);
-/* Per-CTA records of the same trace variant: `device_buf` = capacity x 4 uint64 (clock64 at CTA entry, at exit, number of
+/* Per-CTA records of the same trace variant: `device_buf` = capacity x 8 uint64 (clock64 at CTA entry, at exit, number of
  * kv tiles, SM id), indexed by the linear block index.  NULL disables. */
 PF_API int pf_debug_attn_cta_trace(void* device_buf, int64_t capacity);
 

@@ -155,6 +155,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __shared__ uint32_t tmem_slot;
   __shared__ float xch[2][2][ATT_BM];  // [tile parity][column half][row]: partial row max published to the paired warp
   __shared__ float lxch[2][ATT_BM];    // [column half][row]: partial row sums (epilogue)
+  __shared__ unsigned long long cta_stamp[4];   // trace variant: after alloc+sync, first S seen, softmax loop end, last PV issued
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +203,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (TRACE) {
+    if (threadIdx.x == 0) cta_stamp[0] = clock64();
+  }
 
   if (warp == W_TMA) {
     if (elect_one()) {
@@ -276,6 +280,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         umma_commit(&v_empty[vs]);
         umma_commit(&bar_pv_done);
         trace_stamp<TRACE>(tr_cta, 2, j, 4);
+        if (TRACE) {
+          if (j == n_kv - 1) cta_stamp[3] = clock64();
+        }
         if (++vs == ATT_VSTAGES) {
           vs = 0;
           vph ^= 1;
@@ -344,6 +351,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (!s_ok) mbar_wait(&bar_s_full, j & 1);
       tc_fence_after();
       trace_stamp<TRACE>(tr_me, half, j, 0);
+      if (TRACE) {
+        if (j == 0 && threadIdx.x == 0) cta_stamp[1] = clock64();
+      }
 
       // ---- this thread's 64 scores stay in registers for both the max and the exp
       uint32_t va[32], vb[32];
@@ -430,6 +440,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       trace_stamp<TRACE>(tr_me, half, j, 6);
     }
 
+    if (TRACE) {
+      if (threadIdx.x == 0) cta_stamp[2] = clock64();
+    }
     // ---- epilogue: combine the two halves' row sums, O / l -> bf16 -> out[b, qpos, h*64 + half*32 .. +32]
     const float l_part = (l4[0] + l4[1]) + (l4[2] + l4[3]);
     lxch[half][row] = l_part;
@@ -468,17 +481,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (idx < g_attn_cta_trace_cap) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        unsigned long long* r = g_attn_cta_trace + idx * 4;
+        unsigned long long* r = g_attn_cta_trace + idx * 8;
         r[0] = cta_t0;
         r[1] = clock64();
         r[2] = static_cast<unsigned long long>(n_kv);
         r[3] = smid;
+        r[4] = cta_stamp[0];
+        r[5] = cta_stamp[1];
+        r[6] = cta_stamp[2];
+        r[7] = cta_stamp[3];
       }
     }
   }
 }
 
 int warmup_attn2();
+void attn2_set_trace(unsigned long long* p, long long cap);
 int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t stream);
 constexpr int ATT2_DEFAULT_POLY = 1;   // exponentials on the FMA pipe: 2 of every 8 (tuned on B200)
 
@@ -611,6 +629,7 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
 extern "C" int pf_debug_attn_cta_trace(void* device_buf, int64_t capacity) {
   unsigned long long* p = static_cast<unsigned long long*>(device_buf);
   long long cap = device_buf ? capacity : 0;
+  pf::attn2_set_trace(p, cap);
   cudaError_t e = cudaMemcpyToSymbol(pf::g_attn_cta_trace, &p, sizeof(p));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(pf::g_attn_cta_trace_cap, &cap, sizeof(cap));
   if (e != cudaSuccess) {

@@ -51,6 +51,8 @@ struct Attn2Args {
   // sequence parallel: output rows go straight into the owning rank's buffer (pf_b200.h)
   __nv_bfloat16* peer_out[PF_MAX_PEERS];
   int peer_count, peer_chunk_rows, peer_col_begin;
+  unsigned long long* trace;   // debug: per-CTA phase stamps (pf_debug_attn_cta_trace), NULL = off
+  long long trace_cap;
   uint32_t zero;   // always 0, opaque to ptxas: lets the exponential loop express "wait for a later MUFU" as a data dependency
 };
 
@@ -142,7 +144,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_ordered(float lo, float hi) {
 // keeps the XU pipe only ~50 % busy (tools/probes/tmem_probe.cu: 7.9 ex2/clk/SM with one such warp per SMSP, 11.3 with two;
 // attn2 in lockstep: XU 59 %, 0.34 IPC per SMSP, profiles/r02_attn2_lockstep_ncu.txt).  The polynomial pairs' FMA-pipe work
 // is not pinned and fills issue slots between MUFUs.
-constexpr int A2_EXP_LAG = 5;
+constexpr int A2_EXP_LAG = 0;   // measured: no gain from a forced lag (tools/probes/tmem_probe.cu: a warp's MUFU rate is capped at one per 16 clk whatever the consumer distance)
 template <int POLY>
 __device__ __forceinline__ void a2_exp64(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t (&pka)[16],
                                          uint32_t (&pkb)[16], uint64_t c2, uint64_t nm2, uint64_t& l01, uint64_t& l23,
@@ -243,6 +245,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ __align__(8) uint64_t bar_q[2], bar_s_full[2], bar_s_free[2], bar_p_full[2], bar_pv_done[2];
   __shared__ __align__(8) uint64_t k_full[A2_KSTAGES], k_empty[A2_KSTAGES], v_full[A2_VSTAGES], v_empty[A2_VSTAGES];
   __shared__ uint32_t tmem_slot;
+  __shared__ unsigned long long cta_stamp[4];
+  const unsigned long long cta_t0 = a.trace ? clock64() : 0ull;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -288,6 +292,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (a.trace && threadIdx.x == 128) cta_stamp[0] = clock64();
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A2_REGS_OTHER));
@@ -418,6 +423,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (j > 0) pv_ok = mbar_test(&bar_pv_done[X], (j - 1) & 1);    // probed early, consumed before the P store
         mbar_wait(&bar_s_full[X], j & 1);
         tc_fence_after();
+        if (a.trace && j == 0 && threadIdx.x == 128) cta_stamp[1] = clock64();
 
         // ---- the row's 128 scores: TMEM -> registers, then the tensor pipe may overwrite S with S(j+1)
         uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -492,6 +498,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_arrive(&bar_p_full[X]);
       }
 
+      if (a.trace && threadIdx.x == 128) cta_stamp[2] = clock64();
       // ---- epilogue: O / l -> bf16 -> out[b, qpos, h*64 .. +64]
       float s0, s1, s2, s3;
       f2_unpack(l01, s0, s1);
@@ -534,6 +541,29 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, A2_TMEM_COLS);
   }
+  if (a.trace && threadIdx.x == 128) {       // thread 128 = first thread of the upper tile's warpgroup (always active)
+    const long long idx = (static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (idx < a.trace_cap) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* r = a.trace + idx * 8;
+      r[0] = cta_t0;
+      r[1] = clock64();
+      r[2] = static_cast<unsigned long long>(n_kv);
+      r[3] = smid;
+      r[4] = cta_stamp[0];
+      r[5] = cta_stamp[1];
+      r[6] = cta_stamp[2];
+      r[7] = 0;
+    }
+  }
+}
+
+static unsigned long long* g_a2_trace = nullptr;
+static long long g_a2_trace_cap = 0;
+void attn2_set_trace(unsigned long long* p, long long cap) {
+  g_a2_trace = p;
+  g_a2_trace_cap = cap;
 }
 
 template <int POLY, int PINGPONG>
@@ -580,6 +610,8 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t str
   a.psched = d->pair_sched;
   a.sched_stride = d->sched_stride;
   a.zero = 0u;
+  a.trace = g_a2_trace;
+  a.trace_cap = g_a2_trace_cap;
   a.peer_count = d->peer_count;
   a.peer_chunk_rows = d->peer_chunk_rows;
   a.peer_col_begin = d->peer_col_begin;

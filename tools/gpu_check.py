@@ -524,8 +524,12 @@ def group_attn_trace():
     N, SL = 48, 8
     buf = torch.zeros(3 * N * SL, dtype=torch.int64, device=dev)
     _lib.check(_lib.load().pf_debug_attn_trace(buf.data_ptr()), "trace")
+    variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x30 / 0x10 = two-q-tile kernel
+    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    if variant & 0x10:
+        n_cta = ((((S + 127) // 128) + 1) // 2) * H * B
     for _ in range(2):
-        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, 2)
+        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps)
     torch.cuda.synchronize()
     _lib.check(_lib.load().pf_debug_attn_trace(None), "trace")
     t = buf.cpu().view(3, N, SL)
@@ -568,14 +572,28 @@ def group_attn_cta_trace():
     sched, pairs = ops.attn_build_schedule(seg, tim)
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
     n_cta = ((S + 127) // 128) * H * B
-    buf = torch.zeros(n_cta * 4, dtype=torch.int64, device=dev)
+    buf = torch.zeros(n_cta * 8, dtype=torch.int64, device=dev)
     lib = _lib.load()
     _lib.check(lib.pf_debug_attn_cta_trace(buf.data_ptr(), n_cta), "cta trace")
+    variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x30 / 0x10 = two-q-tile kernel
+    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    if variant & 0x10:
+        n_cta = ((((S + 127) // 128) + 1) // 2) * H * B
     for _ in range(2):
-        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, 2)
+        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps)
     torch.cuda.synchronize()
     _lib.check(lib.pf_debug_attn_cta_trace(None, 0), "cta trace")
-    r = buf.cpu().view(n_cta, 4).double()
+    r = buf.cpu()[:n_cta * 8].view(n_cta, 8).double()
+    ph = lambda a_, b_: float((r[:, b_] - r[:, a_]).mean())
+    print(f"[attn_cta_trace] mean phases per CTA (clk): entry -> alloc+sync done {ph(0, 4):.0f} | -> first S tile seen {ph(4, 5):.0f} | "
+          f"softmax loop {ph(5, 6):.0f} ({float(((r[:, 6] - r[:, 5]) / r[:, 2]).mean()):.0f} per kv tile) | loop end -> exit {ph(6, 1):.0f} | "
+          f"last PV issued -> exit {ph(7, 1):.0f}")
+    for lo, hi in [(1, 8), (8, 32), (32, 64), (64, 200)]:
+        m_ = (r[:, 2] >= lo) & (r[:, 2] < hi)
+        if m_.any():
+            rr = r[m_]
+            print(f"[attn_cta_trace]   kv tiles in [{lo}, {hi}): entry->sync {float((rr[:, 4] - rr[:, 0]).mean()):.0f}, sync->first S {float((rr[:, 5] - rr[:, 4]).mean()):.0f}, "
+                  f"loop per tile {float(((rr[:, 6] - rr[:, 5]) / rr[:, 2]).mean()):.0f}, loop end->exit {float((rr[:, 1] - rr[:, 6]).mean()):.0f}")
     dur, nkv, sm = r[:, 1] - r[:, 0], r[:, 2], r[:, 3].long()
     A = torch.stack([torch.ones_like(nkv), nkv], 1)
     sol = torch.linalg.lstsq(A, dur[:, None]).solution.flatten()
