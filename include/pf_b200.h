@@ -170,6 +170,8 @@ typedef struct pf_attn_desc {
                               * needs the current clip's rows only (history outputs are discarded, reference F:380). */
   const int32_t* pair_sched; /* device; built by pf_attn_build_pair_schedule from tile_sched, same sched_stride.  When set (and
                               * variant does not ask for the one-tile kernel) the launch uses the two-q-tiles-per-CTA kernel. */
+  const int32_t* pair_mask_index; /* device; from pf_attn_build_pair_masks (required with pair_sched) */
+  const void* pair_mask_bits;     /* device; [blocks, 128, 4] uint32 */
   /* sequence parallelism (peer_count > 1, batch 1, two-q-tile kernel): row q of this rank's head group is stored into rank
    * (q / peer_chunk_rows)'s buffer peer_out[...] at row q % peer_chunk_rows, columns peer_col_begin + h*64 (row stride ldo);
    * `out` is ignored. */
@@ -189,6 +191,13 @@ PF_API int pf_attn_build_schedule(const int32_t* seg_host, const int32_t* time_h
  * element mask (a tile without bit0 is computed fully masked).  `out` holds batch * ceil(q_tiles/2) rows of sched_stride. */
 PF_API int pf_attn_build_pair_schedule(const int32_t* tile_sched_host, int32_t batch, int32_t seq, int32_t sched_stride,
                                        int32_t* out);
+/* Host helper: the element masks of the two-q-tile kernel.  For every (pair entry, tile X) whose flags say "partial" it
+ * assigns a block index (mask_index[batch, n_pairs, 2 * sched_stride], entry e / tile X at [2 e + X], -1 otherwise) and, when
+ * mask_bits != NULL, fills block = 128 rows x 4 uint32: bit i of word w of row r = q row r of the tile may attend kv column
+ * 32 w + i of the kv tile.  Returns the number of blocks needed (call once with mask_bits = NULL to size the buffer). */
+PF_API int64_t pf_attn_build_pair_masks(const int32_t* seg_host, const int32_t* time_host, const int32_t* pair_sched_host,
+                                        int32_t batch, int32_t seq, int32_t sched_stride, int32_t* mask_index,
+                                        uint32_t* mask_bits, int64_t capacity_blocks);
 PF_API int pf_attn_fwd_masked(const pf_attn_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm + AdaLN modulate pre-pass (HBM-bound)

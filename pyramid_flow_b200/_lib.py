@@ -15,7 +15,7 @@ LIB_PATH = _HERE / "lib" / "libpf_b200.so"
 SYMBOLS = [
     "pf_last_error", "pf_version", "pf_device_check", "pf_warmup", "pf_set_option", "pf_get_option", "pf_launch_count",
     "pf_gemm_bf16",
-    "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_fwd_masked",
+    "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_build_pair_masks", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step", "pf_stage_hop",
     "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent", "pf_blend_tiles",
@@ -58,6 +58,7 @@ class AttnDesc(C.Structure):
         ("seg", C.c_void_p), ("time", C.c_void_p), ("tile_sched", C.c_void_p),
         ("sched_stride", C.c_int32), ("variant", C.c_int32), ("q_row_begin", C.c_int32),
         ("pair_sched", C.c_void_p),
+        ("pair_mask_index", C.c_void_p), ("pair_mask_bits", C.c_void_p),
         ("peer_out", C.c_void_p * 8),
         ("peer_count", C.c_int32), ("peer_chunk_rows", C.c_int32), ("peer_col_begin", C.c_int32),
     ]
@@ -115,6 +116,9 @@ def load() -> C.CDLL:
     lib.pf_attn_fwd_masked.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     lib.pf_attn_build_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.pf_attn_build_pair_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.pf_attn_build_pair_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_int64]
+    lib.pf_attn_build_pair_masks.restype = C.c_int64
     lib.pf_ctx_create.argtypes = [C.POINTER(C.c_void_p)]
     for name in ("pf_ctx_destroy", "pf_ctx_record_end"):
         getattr(lib, name).argtypes = [C.c_void_p]

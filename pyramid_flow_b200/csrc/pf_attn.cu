@@ -584,7 +584,8 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   const bool use_pair = (d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
   PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
   if (use_pair) {
-    PF_REQUIRE(d->pair_sched != nullptr, "pf_attn_fwd_masked: variant 0x%x needs pair_sched", d->variant);
+    PF_REQUIRE(d->pair_sched != nullptr && d->pair_mask_index != nullptr && d->pair_mask_bits != nullptr,
+               "pf_attn_fwd_masked: variant 0x%x needs pair_sched, pair_mask_index and pair_mask_bits", d->variant);
     // 0x10 | k: k of every 4 exponential pairs on the FMA pipe; | 0x20: WITHOUT the ping-pong token (A/B)
     const int poly = (d->variant & 0x10) ? (d->variant & 0x3) : ATT2_DEFAULT_POLY;
     const int pingpong = (d->variant & 0x20) ? 0 : 1;

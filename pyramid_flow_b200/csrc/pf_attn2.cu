@@ -48,6 +48,8 @@ struct Attn2Args {
   const int* time;
   const int* psched;
   int sched_stride;
+  const int* pmask_idx;        // [batch, n_pairs, 2 * sched_stride]: block of (entry, tile X) in pmask_bits, -1 = none
+  const uint4* pmask_bits;     // [blocks, 128 rows]: 128 allow bits of the row over the kv tile (bit i of word w = column 32 w + i)
   // sequence parallel: output rows go straight into the owning rank's buffer (pf_b200.h)
   __nv_bfloat16* peer_out[PF_MAX_PEERS];
   int peer_count, peer_chunk_rows, peer_col_begin;
@@ -385,6 +387,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       float m_run = -INFINITY;   // reference max (raw score units) the accumulators are scaled by; -inf: nothing finite yet
       uint64_t l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);
       int entry = sched[1];
+      const int* mask_idx = a.pmask_idx + (static_cast<size_t>(b) * a.n_pairs + pair) * 2 * a.sched_stride;
       // Ping-pong: the exponential phase (the XU-bound part) of the two warpgroups is strictly alternated with a token passed
       // through named barriers.  Left alone the two q tiles fall into lockstep (both S tiles become ready together), contend
       // for the XU during their exps and leave it idle while both load / reduce / store: measured XU pipe 59 % busy, the same
@@ -399,25 +402,18 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const bool own = (fl & 1) != 0;
         const bool masked = !own || (fl & 2) != 0;
         if (j + 1 < n_kv) entry = __ldg(sched + 2 + j);
+        // element mask of a partial tile: 128 allow bits per q row, precomputed on the host (pf_attn_build_pair_masks) --
+        // one 16-byte load per thread, issued here so its latency hides under the wait for S.  (Building the bits from the
+        // seg/time arrays in the kernel cost ~20k clk per partial tile = 20-35 % of the whole kernel:
+        // profiles/r02_attn_cta_phases.txt.)
         uint32_t allow0 = 0u, allow1 = 0u, allow2 = 0u, allow3 = 0u;
         if (own && masked) {
-          const int* sg = a.seg + static_cast<size_t>(b) * a.seq;
-          const int* tm = a.time + static_cast<size_t>(b) * a.seq;
-          auto bits_of = [&](int w) {
-            uint32_t bits = 0;
-#pragma unroll 4
-            for (int i = 0; i < 32; ++i) {
-              const int kv = kt * A2_BN + w * 32 + i;
-              bool ok = false;
-              if (kv < a.seq) ok = (__ldg(sg + kv) == seg_q) && (__ldg(tm + kv) <= time_q);
-              bits |= (ok ? 1u : 0u) << i;
-            }
-            return bits;
-          };
-          allow0 = bits_of(0);
-          allow1 = bits_of(1);
-          allow2 = bits_of(2);
-          allow3 = bits_of(3);
+          const int blk = __ldg(mask_idx + 2 * j + X);
+          const uint4 w = __ldg(a.pmask_bits + static_cast<size_t>(blk) * A2_BM + row);
+          allow0 = w.x;
+          allow1 = w.y;
+          allow2 = w.z;
+          allow3 = w.w;
         }
         bool pv_ok = true;
         if (j > 0) pv_ok = mbar_test(&bar_pv_done[X], (j - 1) & 1);    // probed early, consumed before the P store
@@ -609,6 +605,8 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t str
   a.time = d->time;
   a.psched = d->pair_sched;
   a.sched_stride = d->sched_stride;
+  a.pmask_idx = d->pair_mask_index;
+  a.pmask_bits = static_cast<const uint4*>(d->pair_mask_bits);
   a.zero = 0u;
   a.trace = g_a2_trace;
   a.trace_cap = g_a2_trace_cap;
@@ -678,4 +676,52 @@ extern "C" int pf_attn_build_pair_schedule(const int32_t* tile_sched, int32_t ba
     }
   }
   return 0;
+}
+
+extern "C" int64_t pf_attn_build_pair_masks(const int32_t* seg, const int32_t* time, const int32_t* pair_sched, int32_t batch,
+                                            int32_t seq, int32_t sched_stride, int32_t* mask_index, uint32_t* mask_bits,
+                                            int64_t capacity_blocks) {
+  using namespace pf;
+  if (!seg || !time || !pair_sched || !mask_index || batch <= 0 || seq <= 0) {
+    set_error("pf_attn_build_pair_masks: bad arguments");
+    return -1;
+  }
+  const int q_tiles = (seq + 127) / 128;
+  const int n_pairs = (q_tiles + 1) / 2;
+  int64_t blocks = 0;
+  for (int b = 0; b < batch; ++b) {
+    const int32_t* sg = seg + static_cast<size_t>(b) * seq;
+    const int32_t* tm = time + static_cast<size_t>(b) * seq;
+    for (int p = 0; p < n_pairs; ++p) {
+      const int32_t* row = pair_sched + (static_cast<size_t>(b) * n_pairs + p) * sched_stride;
+      int32_t* mi = mask_index + (static_cast<size_t>(b) * n_pairs + p) * 2 * sched_stride;
+      for (int i = 0; i < 2 * sched_stride; ++i) mi[i] = -1;
+      const int hi = q_tiles - 1 - 2 * p;
+      for (int e = 0; e < row[0]; ++e) {
+        const int ent = row[1 + e], kt = ent >> 4;
+        for (int x = 0; x < 2; ++x) {
+          const int fl = (ent >> (2 * x)) & 3;
+          if (fl != 3) continue;                       // needs bits only when the tile owns the entry AND is partial
+          const int qt = x ? hi : hi - 1;
+          if (mask_bits != nullptr && blocks < capacity_blocks) {
+            uint32_t* blk = mask_bits + static_cast<size_t>(blocks) * 128 * 4;
+            for (int r = 0; r < 128; ++r) {
+              const int q = qt * 128 + r;
+              uint32_t w[4] = {0u, 0u, 0u, 0u};
+              if (q < seq) {
+                for (int c = 0; c < 128; ++c) {
+                  const int kv = kt * 128 + c;
+                  if (kv < seq && sg[kv] == sg[q] && tm[kv] <= tm[q]) w[c >> 5] |= 1u << (c & 31);
+                }
+              }
+              for (int k = 0; k < 4; ++k) blk[r * 4 + k] = w[k];
+            }
+          }
+          mi[2 * e + x] = static_cast<int32_t>(blocks);
+          ++blocks;
+        }
+      }
+    }
+  }
+  return blocks;
 }

@@ -100,7 +100,7 @@ class SeqPlan:
     seg: torch.Tensor         # device int32 [B, S]
     time: torch.Tensor        # device int32 [B, S]
     sched: torch.Tensor       # device int32 [B, q_tiles, stride]
-    sched2: torch.Tensor      # device int32 [B, ceil(q_tiles/2), stride]: pair schedule of the two-q-tile attention kernel
+    sched2: object            # ops.PairSchedule on the device: pair schedule + row masks of the two-q-tile attention kernel
     allowed_pairs: int        # sum over batch of allowed (q, kv) pairs (attention FLOP accounting)
 
 
@@ -116,7 +116,7 @@ def build_seq_plan(clip_shapes: Sequence[Sequence[int]], mask_cpu: torch.Tensor,
     seg[:, :text_len][mask_cpu == 0] = 0
     time = ids[:, 0].to(torch.int32)[None].repeat(b, 1).contiguous()
     sched, pairs = ops.attn_build_schedule(seg, time)
-    sched2 = ops.attn_build_pair_schedule(sched, seq)
+    sched2 = ops.attn_build_pair_schedule(sched, seq, seg, time)
     t, h, w = clip_thw[-1]
     return SeqPlan(text_len, video_len, seq, t * h * w, clip_thw, rope.to(device), seg.to(device), time.to(device),
                    sched.to(device), sched2.to(device), int(pairs.sum()))

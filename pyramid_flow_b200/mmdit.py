@@ -169,7 +169,7 @@ class B200MMDiT(torch.nn.Module):
             dev = self.device
             t, h, w = thw[-1]
             plan = SeqPlan(t_len, video_len, seq, t * h * w, thw, build_rope_table(tid[:, None], (64,)).to(dev), seg.to(dev),
-                           time.to(dev), sched.to(dev), ops.attn_build_pair_schedule(sched, seq).to(dev), int(pairs.sum()))
+                           time.to(dev), sched.to(dev), ops.attn_build_pair_schedule(sched, seq, seg, time).to(dev), int(pairs.sum()))
             hit = (plan, torch.cat(pos, 0).to(dev).contiguous())
             self._plans[key] = hit
         self._last_key = (mask, mask._version, shapes, hit)

@@ -162,20 +162,46 @@ def attn_build_schedule(seg: torch.Tensor, time: torch.Tensor):
     return sched, pairs
 
 
-def attn_build_pair_schedule(sched: torch.Tensor, seq: int) -> torch.Tensor:
-    """Tile schedule (int32 CPU [batch, q_tiles, stride]) -> pair schedule [batch, ceil(q_tiles/2), stride] of the two-q-tile
-    kernel (pf_attn_build_pair_schedule)."""
+class PairSchedule:
+    """Schedule of the two-q-tile attention kernel: `sched` int32 [batch, n_pairs, stride] (pf_attn_build_pair_schedule),
+    `mask_index` int32 [batch, n_pairs, 2 * stride] and `mask_bits` int32 [blocks, 128, 4] (pf_attn_build_pair_masks)."""
+
+    def __init__(self, sched: torch.Tensor, mask_index: torch.Tensor, mask_bits: torch.Tensor):
+        self.sched, self.mask_index, self.mask_bits = sched, mask_index, mask_bits
+
+    def to(self, device) -> "PairSchedule":
+        return PairSchedule(self.sched.to(device), self.mask_index.to(device), self.mask_bits.to(device))
+
+    def __getitem__(self, idx) -> "PairSchedule":          # batch slice (block indices are global: the bit pool is shared)
+        assert isinstance(idx, slice)
+        return PairSchedule(self.sched[idx], self.mask_index[idx], self.mask_bits)
+
+
+def attn_build_pair_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, time: torch.Tensor) -> PairSchedule:
+    """Tile schedule (int32 CPU [batch, q_tiles, stride]) + the seg/time ids -> PairSchedule (CPU tensors) of the two-q-tile
+    kernel: merged kv lists of adjacent q tiles and the precomputed 128-bit row masks of their partial tiles."""
     sched = sched.to(torch.int32).contiguous().cpu()
+    seg = seg.to(torch.int32).contiguous().cpu()
+    time = time.to(torch.int32).contiguous().cpu()
     batch, qt, stride = sched.shape
-    out = torch.zeros(batch, (qt + 1) // 2, stride, dtype=torch.int32)
-    _lib.check(_lib.load().pf_attn_build_pair_schedule(sched.data_ptr(), batch, seq, stride, out.data_ptr()),
-               "pf_attn_build_pair_schedule")
-    return out
+    n_pairs = (qt + 1) // 2
+    lib = _lib.load()
+    ps = torch.zeros(batch, n_pairs, stride, dtype=torch.int32)
+    _lib.check(lib.pf_attn_build_pair_schedule(sched.data_ptr(), batch, seq, stride, ps.data_ptr()), "pf_attn_build_pair_schedule")
+    midx = torch.full((batch, n_pairs, 2 * stride), -1, dtype=torch.int32)
+    n = lib.pf_attn_build_pair_masks(seg.data_ptr(), time.data_ptr(), ps.data_ptr(), batch, seq, stride, midx.data_ptr(), None, 0)
+    if n < 0:
+        _lib.check(int(n), "pf_attn_build_pair_masks")
+    bits = torch.zeros(max(1, int(n)), 128, 4, dtype=torch.int32)
+    n2 = lib.pf_attn_build_pair_masks(seg.data_ptr(), time.data_ptr(), ps.data_ptr(), batch, seq, stride, midx.data_ptr(),
+                                      bits.data_ptr(), int(n))
+    assert n2 == n
+    return PairSchedule(ps, midx, bits)
 
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, seg: torch.Tensor,
              time: torch.Tensor, sched: torch.Tensor, scale: float, variant: int = 0, q_row_begin: int = 0,
-             pair_sched: Optional[torch.Tensor] = None, ldo: Optional[int] = None, peer: Optional[dict] = None) -> None:
+             pair_sched: Optional[PairSchedule] = None, ldo: Optional[int] = None, peer: Optional[dict] = None) -> None:
     """q,k,v bf16 [B,H,S,64]; out bf16 [B,S,*] (row stride = out.stride(1)); seg/time/sched int32 on device.
     Only q rows >= q_row_begin (multiple of 128) are computed; other rows of `out` are left untouched."""
     assert q.dtype == torch.bfloat16 and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
@@ -198,8 +224,11 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
     d.variant = variant
     d.q_row_begin = q_row_begin
     if pair_sched is not None:
-        assert pair_sched.dtype == torch.int32 and pair_sched.shape[-1] == sched.shape[-1]
-        d.pair_sched = pair_sched.data_ptr()
+        assert pair_sched.sched.dtype == torch.int32 and pair_sched.sched.shape[-1] == sched.shape[-1]
+        assert pair_sched.sched.is_contiguous() and pair_sched.mask_index.is_contiguous() and pair_sched.mask_bits.is_contiguous()
+        d.pair_sched = pair_sched.sched.data_ptr()
+        d.pair_mask_index = pair_sched.mask_index.data_ptr()
+        d.pair_mask_bits = pair_sched.mask_bits.data_ptr()
     _lib.check(_lib.load().pf_attn_fwd_masked(C.byref(d), _lib.stream_ptr()), "pf_attn_fwd_masked")
 
 

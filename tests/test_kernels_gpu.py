@@ -114,7 +114,7 @@ def _attn_case(B, H, S, seg, tim, scale_q=1.0):
     k = torch.randn(B, H, S, 64, device=DEV).bfloat16()
     v = torch.randn(B, H, S, 64, device=DEV).bfloat16()
     sched, pairs = ops.attn_build_schedule(seg, tim)
-    psched = ops.attn_build_pair_schedule(sched, S).to(DEV)
+    psched = ops.attn_build_pair_schedule(sched, S, seg, tim).to(DEV)
     sg, tm = seg.to(DEV).int(), tim.to(DEV).int()
     ref, mask = _attn_ref(q, k, v, sg, tm)
     assert int(pairs.sum()) == int(mask.sum())
@@ -174,7 +174,8 @@ def test_attention_adversarial_score_jumps():
     seg = torch.ones(B, S, dtype=torch.int32)
     tim = (torch.arange(S) // 256).int()[None]
     sched, _ = ops.attn_build_schedule(seg, tim)
-    psched = ops.attn_build_pair_schedule(sched, S)
+    pso = ops.attn_build_pair_schedule(sched, S, seg, tim)
+    psched = pso.sched
     # pair rows: union of the two tiles' lists, flags consistent with the tile rows
     qt = S // 128
     for p in range((qt + 1) // 2):
@@ -193,7 +194,7 @@ def test_attention_adversarial_score_jumps():
     # is kept for A/B timing only); the two-q-tile kernel has an exact per-row max and must be exact here
     for variant in [v_ for v_ in ATTN_VARIANTS if v_ & 0x10]:
         out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
-        ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=psched.to(DEV))
+        ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=pso.to(DEV))
         torch.cuda.synchronize()
         assert bool(torch.isfinite(out.float()).all()), variant
         assert (out.float() - ref).abs().max().item() < 3e-2, variant
@@ -262,7 +263,7 @@ def test_step_context_record_and_replay():
     seg = torch.ones(B, S, dtype=torch.int32)
     tim = (torch.arange(S) // 128).int()[None]
     sched, _ = ops.attn_build_schedule(seg, tim)
-    ps = ops.attn_build_pair_schedule(sched, S).to(DEV)
+    ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(DEV)
     sg, tm, sc = seg.to(DEV), tim.to(DEV), sched.to(DEV)
 
     def sequence():

@@ -148,7 +148,8 @@ def test_pair_schedule_is_the_union_of_the_two_tile_rows():
         seg = torch.ones(2, seq, dtype=torch.int32)
         seg[1, 10:int(torch.randint(20, 60, (1,), generator=g))] = 0
         sched, pairs = ops.attn_build_schedule(seg, tim)
-        ps = ops.attn_build_pair_schedule(sched, seq)
+        pso = ops.attn_build_pair_schedule(sched, seq, seg, tim)
+        ps = pso.sched
         qt = (seq + 127) // 128
         assert ps.shape == (2, (qt + 1) // 2, sched.shape[-1])
         for b in range(2):
@@ -164,3 +165,19 @@ def test_pair_schedule_is_the_union_of_the_two_tile_rows():
                     want = [] if t < 0 else sched[b, t, 1:1 + int(sched[b, t, 0])].tolist()
                     assert own == want, (seq, b, p, x)
                 assert bool((ps[b, p, 1 + n:] == 0).all())
+                # row masks of the partial tiles == the dense mask definition (F:318-350), bit i of word w = kv column 32 w + i
+                for e_i, e in enumerate(ent):
+                    for x, t in ((0, lo), (1, hi)):
+                        blk = int(pso.mask_index[b, p, 2 * e_i + x])
+                        if ((e >> (2 * x)) & 3) != 3:
+                            assert blk == -1
+                            continue
+                        words = pso.mask_bits[blk].to(torch.int64) & 0xFFFFFFFF            # [128, 4]
+                        bits = ((words[:, :, None] >> torch.arange(32)[None, None, :]) & 1).reshape(128, 128).bool()
+                        q = torch.arange(t * 128, t * 128 + 128)
+                        kv = torch.arange((e >> 4) * 128, (e >> 4) * 128 + 128)
+                        qv, kvv = q < seq, kv < seq
+                        qc, kc = q.clamp(max=seq - 1), kv.clamp(max=seq - 1)
+                        dense = (seg[b][qc][:, None] == seg[b][kc][None, :]) & (tim[b][qc][:, None] >= tim[b][kc][None, :])
+                        dense &= qv[:, None] & kvv[None, :]
+                        assert torch.equal(bits, dense), (seq, b, p, e_i, x)

@@ -424,7 +424,7 @@ def group_attn_perf():
     sched, pairs = ops.attn_build_schedule(seg, tim)
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
     flops = 4.0 * 64 * H * float(pairs.sum())
-    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     ref = None
     for variant in (3, 0x30, 0x31, 0x10, 0x11, 0x12, 0x13):
         out.zero_()
@@ -525,7 +525,7 @@ def group_attn_trace():
     buf = torch.zeros(3 * N * SL, dtype=torch.int64, device=dev)
     _lib.check(_lib.load().pf_debug_attn_trace(buf.data_ptr()), "trace")
     variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x30 / 0x10 = two-q-tile kernel
-    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     if variant & 0x10:
         n_cta = ((((S + 127) // 128) + 1) // 2) * H * B
     for _ in range(2):
@@ -576,7 +576,7 @@ def group_attn_cta_trace():
     lib = _lib.load()
     _lib.check(lib.pf_debug_attn_cta_trace(buf.data_ptr(), n_cta), "cta trace")
     variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x30 / 0x10 = two-q-tile kernel
-    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     if variant & 0x10:
         n_cta = ((((S + 127) // 128) + 1) // 2) * H * B
     for _ in range(2):

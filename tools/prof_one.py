@@ -20,7 +20,7 @@ if which == "attn":
     v = torch.randn(B, H, S, 64, device=dev).bfloat16()
     out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
     sched, pairs = ops.attn_build_schedule(seg, tim)
-    ps = ops.attn_build_pair_schedule(sched, S).to(dev)
+    ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
     variant = int(sys.argv[3], 0) if len(sys.argv) > 3 else 0        # pf_attn_desc.variant (0 = default, 3 = one-tile, 0x1k = pair kernel)
     for _ in range(reps):
