@@ -42,7 +42,7 @@ enum {
 };
 #define PF_OPT_DEFAULT_GEMM_STAGED_RESID 1
 #define PF_OPT_DEFAULT_GEMM_WAVE_TILING 1
-#define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 0
+#define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 1
 PF_API int pf_set_option(int key, int value);
 PF_API int pf_get_option(int key);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */

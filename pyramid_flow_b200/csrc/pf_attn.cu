@@ -498,7 +498,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 int warmup_attn2();
 void attn2_set_trace(unsigned long long* p, long long cap);
 int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t stream);
-constexpr int ATT2_DEFAULT_POLY = 1;   // exponentials on the FMA pipe: 2 of every 8 (tuned on B200)
+constexpr int ATT2_DEFAULT_POLY = 0;       // measured on B200: a warp's MUFU.EX2 costs it 16 clk and the 9-instruction
+constexpr int ATT2_DEFAULT_PINGPONG = 0;   // polynomial pair costs the same; strict alternation of the warpgroups loses 6 %
 
 int warmup_attn() {
   int rc = warmup_attn2();
@@ -588,7 +589,7 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
                "pf_attn_fwd_masked: variant 0x%x needs pair_sched, pair_mask_index and pair_mask_bits", d->variant);
     // 0x10 | k: k of every 4 exponential pairs on the FMA pipe; | 0x20: WITHOUT the ping-pong token (A/B)
     const int poly = (d->variant & 0x10) ? (d->variant & 0x3) : ATT2_DEFAULT_POLY;
-    const int pingpong = (d->variant & 0x20) ? 0 : 1;
+    const int pingpong = (d->variant & 0x10) ? ((d->variant & 0x20) ? 0 : 1) : ATT2_DEFAULT_PINGPONG;
     return attn2_launch(d, poly, pingpong, stream);
   }
   CUtensorMap tm[3];

@@ -169,6 +169,82 @@ void run_lag(int nwarps) {
   cudaFree(out);
 }
 
+// Packed exponentials: PACKED = 0: two ex2.approx.ftz.f32 per pair; 1: one ex2.approx.ftz.bf16x2 per pair (input packed by a
+// cvt.rn.bf16x2.f32, output is already the packed bf16 P; the row sum unpacks it); 2: one ex2.approx.f16x2 per pair.
+template <int PACKED>
+__global__ void __launch_bounds__(512, 1) packed_probe(unsigned long long* out, int iters, int nwarps, float c, float m) {
+  const int warp = threadIdx.x >> 5;
+  float v[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) v[i] = 0.001f * (threadIdx.x + i);
+  uint64_t l01 = pk(0.f, 0.f), l23 = pk(0.f, 0.f);
+  uint32_t acc = 0;
+  const uint64_t c2 = pk(c, c), m2 = pk(-m, -m);
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  if (warp < nwarps) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        uint64_t x;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(pk(v[2 * i], v[2 * i + 1])), "l"(c2), "l"(m2));
+        float x0, x1, p0, p1;
+        upk(x, x0, x1);
+        uint32_t pkd;
+        if (PACKED == 0) {
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pkd) : "f"(p1), "f"(p0));
+        } else if (PACKED == 1) {
+          uint32_t xin;
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xin) : "f"(x1), "f"(x0));
+          asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(pkd) : "r"(xin));
+          p0 = __uint_as_float(pkd << 16);
+          p1 = __uint_as_float(pkd & 0xffff0000u);
+        } else {
+          uint32_t xin;
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xin) : "f"(x1), "f"(x0));
+          asm("ex2.approx.f16x2 %0, %1;" : "=r"(pkd) : "r"(xin));
+          asm("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}" : "=f"(p0), "=f"(p1) : "r"(pkd));
+        }
+        uint64_t s;
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(i & 1 ? l23 : l01), "l"(pk(p0, p1)));
+        if (i & 1) l23 = s; else l01 = s;
+        acc ^= pkd;
+        v[2 * i] = p0 * 0.25f;
+        v[2 * i + 1] = p1 * 0.25f;
+      }
+    }
+  }
+  const unsigned long long t1 = clock64();
+  __syncthreads();
+  float s0, s1, s2, s3;
+  upk(l01, s0, s1);
+  upk(l23, s2, s3);
+  float s = s0 + s1 + s2 + s3;
+  for (int i = 0; i < 128; ++i) s += v[i];
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  if (s == 12345.678f || acc == 0x12345678u) out[1] = (unsigned long long)s;
+}
+
+template <int PACKED>
+void run_packed(const char* name, int nwarps) {
+  unsigned long long* out;
+  cudaMalloc(&out, 16);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int iters = 2000;
+  packed_probe<PACKED><<<sms, 512>>>(out, 50, nwarps, 1.0f, 0.5f);
+  packed_probe<PACKED><<<sms, 512>>>(out, iters, nwarps, 1.0f, 0.5f);
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long h[2] = {0, 0};
+  cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+  const double clk = double(h[0]) / iters;
+  printf("[tmem_probe] packed-exp %-22s %2d warps: %8.1f clk per 128 exps/thread | exps %5.2f /clk/SM (%s)\n", name, nwarps, clk,
+         4096.0 * nwarps / clk, cudaGetErrorString(e));
+  cudaFree(out);
+}
+
 template <int MODE>
 void run(const char* name, int nwarps) {
   unsigned long long* out;
@@ -195,6 +271,11 @@ int main() {
   for (int w : {1, 4, 8, 16}) run<1>("LDTM 4 x x32 only", w);
   for (int w : {4, 8, 16}) run<2>("softmax stream only", w);
   for (int w : {4, 8, 16}) run<3>("LDTM + softmax stream", w);
+  for (int w : {4, 8, 16}) {
+    run_packed<0>("2 x ex2.f32", w);
+    run_packed<1>("1 x ex2.bf16x2", w);
+    run_packed<2>("1 x ex2.f16x2", w);
+  }
   for (int w : {4, 8}) {
     run_lag<0>(w);
     run_lag<2>(w);
