@@ -497,9 +497,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 int warmup_attn2();
 void attn2_set_trace(unsigned long long* p, long long cap);
-int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, cudaStream_t stream);
+int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, cudaStream_t stream);
 constexpr int ATT2_DEFAULT_POLY = 0;       // measured on B200: a warp's MUFU.EX2 costs it 16 clk and the 9-instruction
-constexpr int ATT2_DEFAULT_PINGPONG = 0;   // polynomial pair costs the same; strict alternation of the warpgroups loses 6 %
+constexpr int ATT2_DEFAULT_PINGPONG = 0;
+constexpr int ATT2_DEFAULT_SPLIT_ROWS = 0;   // polynomial pair costs the same; strict alternation of the warpgroups loses 6 %
 
 int warmup_attn() {
   int rc = warmup_attn2();
@@ -581,8 +582,8 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   // variant: 0 = default (two-q-tile kernel when a pair schedule is given, else the one-tile kernel); 0x10 | k = two-q-tile
   // kernel with k of every 4 exponential pairs on the FMA pipe (k = 0..3); 1 / 2 / 3 = one-tile kernel (polynomial mix / clock
   // trace / plain)
-  PF_REQUIRE((d->variant & ~0x33) == 0, "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
-  const bool use_pair = (d->variant & 0x10) || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
+  PF_REQUIRE((d->variant & ~0x73) == 0, "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
+  const bool use_pair = (d->variant & 0x50) || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
   PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
   if (use_pair) {
     PF_REQUIRE(d->pair_sched != nullptr && d->pair_mask_index != nullptr && d->pair_mask_bits != nullptr,
@@ -590,7 +591,9 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
     // 0x10 | k: k of every 4 exponential pairs on the FMA pipe; | 0x20: WITHOUT the ping-pong token (A/B)
     const int poly = (d->variant & 0x10) ? (d->variant & 0x3) : ATT2_DEFAULT_POLY;
     const int pingpong = (d->variant & 0x10) ? ((d->variant & 0x20) ? 0 : 1) : ATT2_DEFAULT_PINGPONG;
-    return attn2_launch(d, poly, pingpong, stream);
+    // 0x40: two threads per row (pf_attn3.cu)
+    const int split = (d->variant & 0x40) ? 1 : ((d->variant & 0x10) ? 0 : ATT2_DEFAULT_SPLIT_ROWS);
+    return attn2_launch(d, poly, pingpong, split, stream);
   }
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};
