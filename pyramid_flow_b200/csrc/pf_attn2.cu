@@ -362,6 +362,8 @@ static int attn2_launch_t(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, 
   return check_launch("pf_attn_fwd_masked(pair kernel)");
 }
 
+int warmup_attn3();
+
 int warmup_attn2() {
   int rc = 0;
 #define PF_WARM2(P, Q) if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<P, Q>), A2_SMEM_BYTES, "attn2_fwd_kernel")
@@ -374,7 +376,6 @@ int warmup_attn2() {
 
 // called by pf_attn_fwd_masked (pf_attn.cu) after argument validation; poly = exponentials per 8 on the FMA pipe / 2
 int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream);
-int warmup_attn3();
 
 // split_rows: 1 = pf_attn3.cu (two threads per row, 16 softmax warps), 0 = the kernel above
 int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, cudaStream_t stream) {
