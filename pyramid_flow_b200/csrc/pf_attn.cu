@@ -590,7 +590,7 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
                "pf_attn_fwd_masked: variant 0x%x needs pair_sched, pair_mask_index and pair_mask_bits", d->variant);
     // 0x10 | k: k of every 4 exponential pairs on the FMA pipe; | 0x20: WITHOUT the ping-pong token (A/B)
     const int poly = (d->variant & 0x10) ? (d->variant & 0x3) : ATT2_DEFAULT_POLY;
-    const int pingpong = (d->variant & 0x10) ? ((d->variant & 0x20) ? 0 : 1) : ATT2_DEFAULT_PINGPONG;
+    const int pingpong = (d->variant & 0x50) ? ((d->variant & 0x20) ? 0 : 1) : ATT2_DEFAULT_PINGPONG;
     // 0x40: two threads per row (pf_attn3.cu)
     const int split = (d->variant & 0x40) ? 1 : ((d->variant & 0x10) ? 0 : ATT2_DEFAULT_SPLIT_ROWS);
     return attn2_launch(d, poly, pingpong, split, stream);

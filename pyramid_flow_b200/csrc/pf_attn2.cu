@@ -375,7 +375,7 @@ int warmup_attn2() {
 }
 
 // called by pf_attn_fwd_masked (pf_attn.cu) after argument validation; poly = exponentials per 8 on the FMA pipe / 2
-int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream);
+int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, int pingpong, cudaStream_t stream);
 
 // split_rows: 1 = pf_attn3.cu (two threads per row, 16 softmax warps), 0 = the kernel above
 int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, cudaStream_t stream) {
@@ -428,7 +428,7 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, 
   // pair p covers tiles q_tiles-2-2p and q_tiles-1-2p: launch the pairs whose upper tile is >= q_tile_begin
   const int pairs = (a.q_tiles - a.q_tile_begin + 1) / 2;
   dim3 grid(pairs, d->heads, d->batch);
-  if (split_rows) return attn3_launch_raw(tm, a, grid, stream);
+  if (split_rows) return attn3_launch_raw(tm, a, grid, pingpong, stream);
   switch (poly * 2 + (pingpong ? 1 : 0)) {
     case 0: return attn2_launch_t<0, 0>(tm, a, grid, stream);
     case 1: return attn2_launch_t<0, 1>(tm, a, grid, stream);

@@ -37,6 +37,17 @@ __device__ __forceinline__ void a3_pair_sync(int id) {
   }
 }
 
+// named barriers 9 / 10 = the XU token of q tile A / B (512 = the 256 waiting threads + the 256 passing ones)
+__device__ __forceinline__ void a3_token_wait(int x) {
+  if (x == 0) asm volatile("bar.sync 9, 512;" ::: "memory");
+  else asm volatile("bar.sync 10, 512;" ::: "memory");
+}
+__device__ __forceinline__ void a3_token_pass(int x) {
+  if (x == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");
+  else asm volatile("bar.arrive 10, 512;" ::: "memory");
+}
+
+template <int PINGPONG>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn3_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Attn2Args a) {
@@ -187,6 +198,13 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       uint64_t l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);
       int entry = sched[1];
       const int* mask_idx = a.pmask_idx + (static_cast<size_t>(b) * a.n_pairs + pair) * 2 * a.sched_stride;
+      // Ping-pong between the two q tiles: left alone, all 16 softmax warps run in lockstep (both S tiles become ready
+      // together): 4 warps per SMSP share the XU during their exponentials (2048 clk) and leave it idle while all of them
+      // load / reduce / exchange / store (~850 clk) -- measured 2950 clk per pair of tiles, the same as pf_attn2.  With the
+      // token, tile A's two warps per SMSP exponentiate (2 x 64 MUFU.EX2 at the per-warp rate of one per 16 clk = the XU's
+      // full rate) while tile B's warps do everything else, and vice versa.
+      const bool pingpong = PINGPONG && act_lo;
+      if (pingpong && X == 1) a3_token_pass(0);
 
       for (int j = 0; j < n_kv; ++j) {
         const int fl = (entry >> (2 * X)) & 3;
@@ -242,8 +260,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           l23 = f2_pack(a0 * alpha, a1 * alpha);
         }
         uint32_t pk0[16], pk1[16];
+        if (pingpong) a3_token_wait(X);
         a2_exp32<0>(va, pk0, c2, nm2, l01, l23);
         a2_exp32<0>(vb, pk1, c2, nm2, l01, l23);
+        if (pingpong && !(X == 1 && j == n_kv - 1)) a3_token_pass(X ^ 1);
         if (j > 0) {
           if (!pv_ok) mbar_wait(&bar_pv_done[X], (j - 1) & 1);
           tc_fence_after();
@@ -311,12 +331,15 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 int warmup_attn3() {
-  return ensure_dyn_smem(reinterpret_cast<const void*>(attn3_fwd_kernel), A2_SMEM_BYTES, "attn3_fwd_kernel");
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn3_fwd_kernel<0>), A2_SMEM_BYTES, "attn3_fwd_kernel<0>");
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn3_fwd_kernel<1>), A2_SMEM_BYTES, "attn3_fwd_kernel<1>");
+  return rc;
 }
 
-int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream) {
+int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, int pingpong, cudaStream_t stream) {
   if (int rc = warmup_attn3()) return rc;
-  attn3_fwd_kernel<<<grid, A3_THREADS, A2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  if (pingpong) attn3_fwd_kernel<1><<<grid, A3_THREADS, A2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
+  else attn3_fwd_kernel<0><<<grid, A3_THREADS, A2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked(pair kernel, split rows)");
 }
 

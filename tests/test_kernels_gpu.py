@@ -97,7 +97,7 @@ def test_gemm_epilogues_row_ranges():
 
 # pf_attn_desc.variant: 3 = one-q-tile kernel, 0x10 | k = two-q-tile kernel with k of every 4 exponential pairs on the FMA pipe,
 # | 0x20 = without the ping-pong token between its two softmax warpgroups; 0x40 = two-q-tile kernel with two threads per row
-ATTN_VARIANTS = [3, 0x10, 0x11, 0x12, 0x13, 0x30, 0x31, 0x40, 0]
+ATTN_VARIANTS = [3, 0x10, 0x11, 0x12, 0x13, 0x30, 0x31, 0x40, 0x60, 0]
 
 
 def _attn_ref(q, k, v, sg, tm):
