@@ -215,14 +215,10 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
         // ---- the row's 128 scores: TMEM -> registers, then the tensor pipe may overwrite S with S(j+1)
         uint32_t v0[32], v1[32], v2[32], v3[32];
-        if (PINGPONG) {          // (A/B) the four x32 loads of the first version
-          tmem_ld32(t_s, v0);
-          tmem_ld32(t_s + 32, v1);
-          tmem_ld32(t_s + 64, v2);
-          tmem_ld32(t_s + 96, v3);
-        } else {
-          tmem_ld128(t_s, v0, v1, v2, v3);
-        }
+        tmem_ld32(t_s, v0);      // (one x128 load instead of four x32 measured the same: 2.97 vs 2.93 ms)
+        tmem_ld32(t_s + 32, v1);
+        tmem_ld32(t_s + 64, v2);
+        tmem_ld32(t_s + 96, v3);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bar_s_free[X]);

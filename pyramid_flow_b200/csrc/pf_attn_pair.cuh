@@ -156,10 +156,7 @@ __device__ __forceinline__ void a2_exp64(const uint32_t (&va)[32], const uint32_
       const uint64_t x = f2_fma(f2_pack(__uint_as_float(s0), __uint_as_float(s1)), c2, nm2);
       float x0, x1;
       f2_unpack(x, x0, x1);
-      if (POLY == 3) {          // TIMING EXPERIMENT ONLY (variant 0x33): no exponential at all -> the floor of everything else
-        p[2 * i] = x0;
-        p[2 * i + 1] = x1;
-      } else if ((i & 3) < POLY) {
+      if ((i & 3) < POLY) {
         const uint64_t xc = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
         const uint64_t t = f2_add(xc, magic);
         const uint64_t f = f2_sub(xc, f2_sub(t, magic));
@@ -203,9 +200,7 @@ __device__ __forceinline__ void a2_exp32(const uint32_t (&v)[32], uint32_t (&pk)
   for (int i = 0; i < 16; ++i) {
     uint64_t x = f2_fma(f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), c2, nm2);
     float p0, p1;
-    if (POLY == 3) {            // TIMING EXPERIMENT ONLY (variant 0x33): no exponential at all -> the floor of everything else
-      f2_unpack(x, p0, p1);
-    } else if ((i & 3) < POLY) {
+    if ((i & 3) < POLY) {
       float x0, x1;
       f2_unpack(x, x0, x1);
       x = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));

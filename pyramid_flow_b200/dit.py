@@ -125,7 +125,7 @@ def build_seq_plan(clip_shapes: Sequence[Sequence[int]], mask_cpu: torch.Tensor,
 # ----------------------------------------------------------------------------------------------------------------------
 # default formulation of the sequence-parallel exchange: "peer" (remote stores fused into the kernels over NVLink peer memory) once
 # validated on hardware, else "nccl" (all_to_all_single)
-DEFAULT_EXCHANGE = "nccl"
+DEFAULT_EXCHANGE = "peer"
 
 
 class _Cfg(dict):

@@ -426,7 +426,7 @@ def group_attn_perf():
     flops = 4.0 * 64 * H * float(pairs.sum())
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     ref = None
-    for variant in (3, 0x30, 0x33):
+    for variant in (3, 0, 0x30, 0x31, 0x10, 0x60, 0x40):
         out.zero_()
         ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps), iters=8, warm=2)
         if ref is None:
