@@ -31,7 +31,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-ATTN_TRAFFIC_BYTES = None   # filled from the committed ncu capture of the attention kernel (profiles/r02_attn2_ncu.txt)
+ATTN_TRAFFIC_BYTES = 459.96e6   # profiles/r02_attn2_ncu.txt: dram__bytes_read 357.70 MB + dram__bytes_write 102.26 MB per launch
 METRIC = "dit_step_latent_tokens_per_sec"
 UNIT = "tokens/s"
 WORKLOAD = ("miniFLUX 768p/10s (BASELINE configs[2]) — one DiT forward at unit 30 / stage 2: CFG batch 2, "
