@@ -541,6 +541,10 @@ def run_ours(args):
     model = B200FluxTransformer(cfg, sd, device=dev)
     del sd
     torch.cuda.empty_cache()
+    if args.attn_variant is not None:
+        model.attn_variant = args.attn_variant
+    if args.attn_phase is not None:
+        _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, args.attn_phase)
     lay = None
     b = 2
     g = torch.Generator().manual_seed(100)
@@ -751,6 +755,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="(debug) launch every kernel from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--model", default="flux", choices=["flux", "mmdit"], help="flux = miniFLUX (the headline, configs[2]); mmdit = SD3 MMDiT 768p/5s (configs[4])")
     ap.add_argument("--exchange", default=None, choices=["peer", "nccl"], help="N>1: peer-memory fused exchange (default) or NCCL all-to-all (A/B)")
+    ap.add_argument("--attn-variant", type=lambda x: int(x, 0), default=None, help="(debug) pf_attn_desc.variant of the DiT's attention launches")
+    ap.add_argument("--attn-phase", type=int, default=None, help="(debug) pf_set_option(PF_OPT_ATTN_TILE_PHASE, clocks)")
     ap.add_argument("--no-vae", action="store_true", help="skip the VAE decode leg")
     ap.add_argument("--no-video", action="store_true", help="skip the 768p/10s end-to-end sampler + decode leg (~1 min at N=1)")
     ap.add_argument("--no-eager", action="store_true", help="skip the reference-eager-on-GPU baseline leg")

@@ -38,11 +38,14 @@ enum {
   PF_OPT_GEMM_STAGED_RESID = 0, /* GATE_RESID epilogue: residual read-modify-write transposed through shared memory */
   PF_OPT_GEMM_WAVE_TILING = 1,  /* wave-quantisation-aware tile width for GEMMs with few rows */
   PF_OPT_ATTN_PAIR_KERNEL = 2,  /* variant 0 of pf_attn_fwd_masked = the two-q-tile kernel (needs pair_sched) */
-  PF_OPT_COUNT = 3
+  PF_OPT_ATTN_TILE_PHASE = 3,   /* two-q-tile attention kernel: SM clocks the second q tile's softmax warps are held back once per
+                                 * CTA so the two tiles run out of phase (0 = start together) */
+  PF_OPT_COUNT = 4
 };
 #define PF_OPT_DEFAULT_GEMM_STAGED_RESID 1
 #define PF_OPT_DEFAULT_GEMM_WAVE_TILING 1
 #define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 1
+#define PF_OPT_DEFAULT_ATTN_TILE_PHASE 0
 PF_API int pf_set_option(int key, int value);
 PF_API int pf_get_option(int key);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */

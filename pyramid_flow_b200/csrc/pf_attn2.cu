@@ -26,7 +26,8 @@
 
 namespace pf {
 
-template <int POLY, int PINGPONG>
+// LEAN bit 0: branch-free lazy-rescale test; bit 1: the barrier round trips of a tile overlap its TMEM traffic (LEAN blocks below)
+template <int POLY, int PINGPONG, int LEAN = 0, int TL = 0>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Attn2Args a) {
@@ -136,14 +137,22 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           umma_commit(&bar_s_full[X]);
           if (++ks == A2_KSTAGES) { ks = 0; kph ^= 1; }
         };
+        const bool tl_on = TL && a.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        auto tl = [&](int j, int slot) {
+          if (TL && tl_on && j < 64) a.timeline[((2 + X) * 64 + j) * 12 + slot] = clock64();
+        };
         issue_qk();
         for (int j = 0; j < n_kv; ++j) {
           if (j + 1 < n_kv) {
             mbar_wait(&bar_s_free[X], j & 1);   // S(j) lives in the softmax threads' registers
+            tl(j, 0);
             issue_qk();                         // S(j+1) runs on the tensor pipe under softmax(j)
+            tl(j, 1);
           }
           mbar_wait(&bar_p_full[X], j & 1);
+          tl(j, 2);
           mbar_wait(&v_full[vs], vph);
+          tl(j, 3);
           tc_fence_after();
           // V tile [128 kv x 64 hd], 128-byte rows: MN-major, 8-row k groups 1024 B apart, 16 kv rows (2048 B) per MMA
           const uint32_t sv = smem_u32(smem_v + vs * A2_TILE_BYTES);
@@ -154,6 +163,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
           umma_commit(&v_empty[vs]);
           umma_commit(&bar_pv_done[X]);
+          tl(j, 4);
           if (++vs == A2_VSTAGES) { vs = 0; vph ^= 1; }
         }
       }
@@ -187,8 +197,24 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // store run under the other's exponentials.
       const bool pingpong = PINGPONG && act_lo;
       if (pingpong && X == 1) a2_token_pass(1);
+      bool sfull_ok = false;                                  // LEAN: S(j) already seen complete by the probe of iteration j-1
+      const bool tl_on = TL && a.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && quarter == 0 && lane == 0;
+      auto tl = [&](int j, int slot) {   // TL = 1 only: per-iteration clock stamps of CTA (0, 0, 0) (tools/gpu_check.py attn4_timeline)
+        if (TL && tl_on && j < 64) a.timeline[(X * 64 + j) * 12 + slot] = clock64();
+      };
+      if (X == 1 && act_lo && a.b_delay > 0) {
+        // De-phase the two q tiles once per CTA.  Nothing couples the two softmax warpgroups but the K/V ring, so they start
+        // together and STAY together: both exponentiate (sharing the XU), then both load / reduce / store with the XU idle.
+        // Started part of a tile apart they stay apart just the same, and one tile's TMEM loads, max and P stores then run
+        // under the other tile's MUFU stream (measured: PF_OPT_ATTN_TILE_PHASE in tools/gpu_check.py attn_phase_sweep).
+        mbar_wait(&bar_s_full[X], 0);
+        const long long t_begin = clock64();
+        while (clock64() - t_begin < a.b_delay) {
+        }
+      }
 
       for (int j = 0; j < n_kv; ++j) {
+        tl(j, 0);
         const int kt = entry >> 4;
         const int fl = (entry >> (2 * X)) & 3;              // bit0: this tile has allowed pairs here, bit1: element mask
         const bool own = (fl & 1) != 0;
@@ -209,8 +235,9 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         bool pv_ok = true;
         if (j > 0) pv_ok = mbar_test(&bar_pv_done[X], (j - 1) & 1);    // probed early, consumed before the P store
-        mbar_wait(&bar_s_full[X], j & 1);
+        if (!(LEAN & 2) || !sfull_ok) mbar_wait(&bar_s_full[X], j & 1);
         tc_fence_after();
+        tl(j, 1);
         if (a.trace && j == 0 && threadIdx.x == 128) cta_stamp[1] = clock64();
 
         // ---- the row's 128 scores: TMEM -> registers, then the tensor pipe may overwrite S with S(j+1)
@@ -219,9 +246,17 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_ld32(t_s + 32, v1);
         tmem_ld32(t_s + 64, v2);
         tmem_ld32(t_s + 96, v3);
+        if ((LEAN & 2) && j > 0) {
+          // P(j-1) went to TMEM at the end of the previous iteration; its completion wait and the p_full arrive sit HERE, under
+          // the latency of the four loads of S(j), instead of in front of them
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bar_p_full[X]);
+        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bar_s_free[X]);
+        tl(j, 2);
         if (masked) {
           a2_mask32(v0, allow0);
           a2_mask32(v1, allow1);
@@ -233,7 +268,16 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         // ---- lazy rescale: move the reference only when the row max grew by more than 2^8 (exponent argument <= 8)
         float alpha = 1.f;
         bool need = false;
-        if (m_tile > m_run) {
+        if (LEAN & 1) {
+          // branch-free (same values bit for bit): four data-dependent branches with their FSETP -> BRA latencies sat between the
+          // row max and the first exponential
+          const bool first = m_run == -INFINITY;
+          const bool grow = m_tile > m_run;
+          need = grow && !first && (m_tile - m_run) * c > 8.f;
+          const float e = a2_ex2(fmaxf((m_run - m_tile) * c, -126.f));
+          alpha = need ? e : 1.f;
+          m_run = (grow && (first || need)) ? m_tile : m_run;
+        } else if (m_tile > m_run) {
           if (m_run == -INFINITY) {
             m_run = m_tile;                      // everything accumulated so far is exactly zero
           } else if ((m_tile - m_run) * c > 8.f) {
@@ -244,7 +288,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
         const uint64_t nm2 = f2_pack(-m_ref, -m_ref);
-        if (need) {
+        if ((LEAN & 1) || need) {
           float a0, a1;
           f2_unpack(l01, a0, a1);
           l01 = f2_pack(a0 * alpha, a1 * alpha);
@@ -252,11 +296,13 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           l23 = f2_pack(a0 * alpha, a1 * alpha);
         }
 
+        tl(j, 3);
         // ---- first half of the row
         if (pingpong) a2_token_wait(1 + X);
         uint32_t pk0[16], pk1[16];
         if (POLY > 0 && !masked) a2_exp64<POLY>(v0, v1, pk0, pk1, c2, nm2, l01, l23, a.zero);
         else a2_exp64<0>(v0, v1, pk0, pk1, c2, nm2, l01, l23, a.zero);
+        tl(j, 4);
         // ---- P(j-1) consumed and O(j-1) produced before P is overwritten / O is rescaled
         if (j > 0) {
           if (!pv_ok) mbar_wait(&bar_pv_done[X], (j - 1) & 1);
@@ -275,15 +321,24 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         tmem_st16(t_p, pk0);
         tmem_st16(t_p + 16, pk1);
+        // LEAN: S(j+1) has been on the tensor pipe since S(j) was released (about 1000 clk ago): probe its barrier now and consume
+        // the predicate at the top of the next iteration, so the mbarrier round trip (100-300 clk through the MIO queue, behind
+        // the MUFU stream) runs under the second half's exponentials instead of with the XU idle
+        if (LEAN & 2) sfull_ok = (j + 1 < n_kv) && mbar_test(&bar_s_full[X], (j + 1) & 1);
+        tl(j, 5);
         // ---- second half
         if (POLY > 0 && !masked) a2_exp64<POLY>(v2, v3, pk0, pk1, c2, nm2, l01, l23, a.zero);
         else a2_exp64<0>(v2, v3, pk0, pk1, c2, nm2, l01, l23, a.zero);
         if (pingpong && !(X == 1 && j == n_kv - 1)) a2_token_pass(2 - X);   // the other warpgroup's exponentials may start
+        tl(j, 6);
         tmem_st16(t_p + 32, pk0);
         tmem_st16(t_p + 48, pk1);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bar_p_full[X]);
+        if (!(LEAN & 2) || j == n_kv - 1) {
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&bar_p_full[X]);
+        }
+        tl(j, 7);
       }
 
       if (a.trace && threadIdx.x == 128) cta_stamp[2] = clock64();
@@ -349,20 +404,25 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 static unsigned long long* g_a2_trace = nullptr;
 static long long g_a2_trace_cap = 0;
+static unsigned long long* g_a2_timeline = nullptr;
+
 void attn2_set_trace(unsigned long long* p, long long cap) {
   g_a2_trace = p;
   g_a2_trace_cap = cap;
 }
+void attn2_set_timeline(unsigned long long* p) { g_a2_timeline = p; }
 
-template <int POLY, int PINGPONG>
+template <int POLY, int PINGPONG, int LEAN = 0, int TL = 0>
 static int attn2_launch_t(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream) {
-  auto kern = attn2_fwd_kernel<POLY, PINGPONG>;
+  auto kern = attn2_fwd_kernel<POLY, PINGPONG, LEAN, TL>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), A2_SMEM_BYTES, "attn2_fwd_kernel")) return rc;
   kern<<<grid, A2_THREADS, A2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked(pair kernel)");
 }
 
 int warmup_attn3();
+int warmup_attn4();
+int warmup_attn5();
 
 int warmup_attn2() {
   int rc = 0;
@@ -370,14 +430,22 @@ int warmup_attn2() {
   PF_WARM2(0, 0); PF_WARM2(1, 0); PF_WARM2(2, 0); PF_WARM2(3, 0);
   PF_WARM2(0, 1); PF_WARM2(1, 1); PF_WARM2(2, 1); PF_WARM2(3, 1);
 #undef PF_WARM2
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0, 0, 1>), A2_SMEM_BYTES, "attn2_fwd_kernel<lean 1>");
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0, 0, 2>), A2_SMEM_BYTES, "attn2_fwd_kernel<lean 2>");
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0, 0, 3>), A2_SMEM_BYTES, "attn2_fwd_kernel<lean 3>");
   if (!rc) rc = warmup_attn3();
+  if (!rc) rc = warmup_attn4();
+  if (!rc) rc = warmup_attn5();
   return rc;
 }
 
 // called by pf_attn_fwd_masked (pf_attn.cu) after argument validation; poly = exponentials per 8 on the FMA pipe / 2
 int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, int pingpong, cudaStream_t stream);
+int attn4_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, int poly8, int pingpong, cudaStream_t stream);
+int attn5_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream);
 
-// split_rows: 1 = pf_attn3.cu (two threads per row, 16 softmax warps), 0 = the kernel above
+// split_rows: 4 = the kernel above with LEAN = 1, 3 = pf_attn5.cu (software-pipelined softmax), 2 = pf_attn4.cu (E/C phases; poly = pairs per 8), 1 = pf_attn3.cu (two threads per row, 16 softmax warps),
+// 0 = the kernel above
 int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, cudaStream_t stream) {
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};
@@ -408,6 +476,8 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, 
   a.zero = 0u;
   a.trace = g_a2_trace;
   a.trace_cap = g_a2_trace_cap;
+  a.timeline = g_a2_timeline;
+  a.b_delay = get_option(PF_OPT_ATTN_TILE_PHASE);
   a.peer_count = d->peer_count;
   a.peer_chunk_rows = d->peer_chunk_rows;
   a.peer_col_begin = d->peer_col_begin;
@@ -428,6 +498,12 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, 
   // pair p covers tiles q_tiles-2-2p and q_tiles-1-2p: launch the pairs whose upper tile is >= q_tile_begin
   const int pairs = (a.q_tiles - a.q_tile_begin + 1) / 2;
   dim3 grid(pairs, d->heads, d->batch);
+  if (split_rows == 3) return attn5_launch_raw(tm, a, grid, stream);
+  if (split_rows == 4) return a.timeline ? attn2_launch_t<0, 0, 3, 1>(tm, a, grid, stream) : attn2_launch_t<0, 0, 3>(tm, a, grid, stream);
+  if (split_rows == 5) return attn2_launch_t<0, 0, 1>(tm, a, grid, stream);
+  if (split_rows == 6) return attn2_launch_t<0, 0, 2>(tm, a, grid, stream);
+  if (a.timeline != nullptr && poly == 0 && !pingpong) return attn2_launch_t<0, 0, 0, 1>(tm, a, grid, stream);   // debug timeline
+  if (split_rows == 2) return attn4_launch_raw(tm, a, grid, poly, pingpong, stream);
   if (split_rows) return attn3_launch_raw(tm, a, grid, pingpong, stream);
   switch (poly * 2 + (pingpong ? 1 : 0)) {
     case 0: return attn2_launch_t<0, 0>(tm, a, grid, stream);

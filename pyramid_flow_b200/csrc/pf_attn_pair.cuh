@@ -35,6 +35,8 @@ struct Attn2Args {
   int peer_count, peer_chunk_rows, peer_col_begin;
   unsigned long long* trace;   // debug: per-CTA phase stamps (pf_debug_attn_cta_trace), NULL = off
   long long trace_cap;
+  int b_delay;                 // clocks q tile B's softmax warps wait once, after their first S tile arrived, before their first exponential (pf_attn2.cu)
+  unsigned long long* timeline;   // debug: per-iteration clock stamps of CTA (0, 0, 0) of the timeline instantiation (pf_debug_attn_trace)
   uint32_t zero;   // always 0, opaque to ptxas: lets the exponential loop express "wait for a later MUFU" as a data dependency
 };
 
