@@ -45,7 +45,7 @@ enum {
 #define PF_OPT_DEFAULT_GEMM_STAGED_RESID 1
 #define PF_OPT_DEFAULT_GEMM_WAVE_TILING 1
 #define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 1
-#define PF_OPT_DEFAULT_ATTN_TILE_PHASE 0
+#define PF_OPT_DEFAULT_ATTN_TILE_PHASE 800   /* measured on B200: 2.84 -> 2.78 ms per launch at the bench shape (tools/gpu_check.py attn_phase_sweep) */
 PF_API int pf_set_option(int key, int value);
 PF_API int pf_get_option(int key);
 /* number of kernels launched by this library since load (bench.py's gpu_launches claim). */
@@ -168,7 +168,7 @@ typedef struct pf_attn_desc {
   const int32_t* time;       /* device [batch, seq] */
   const int32_t* tile_sched; /* device; layout documented at pf_attn_build_schedule */
   int32_t sched_stride;      /* int32 entries per (batch, q_tile) row */
-  int32_t variant;           /* 0 = default; other values select experimental data paths (see pf_attn.cu) */
+  int32_t variant;           /* 0 = default; 0x10 = the two-q-tile kernel; 1 / 2 / 3 = the one-tile kernel (A/B, see pf_attn.cu) */
   int32_t q_row_begin;       /* only q rows >= q_row_begin are computed (multiple of 128; 0 = all).  The last single block
                               * needs the current clip's rows only (history outputs are discarded, reference F:380). */
   const int32_t* pair_sched; /* device; built by pf_attn_build_pair_schedule from tile_sched, same sched_stride.  When set (and
@@ -325,7 +325,9 @@ typedef struct pf_umma_probe {
 PF_API int pf_debug_umma(const pf_umma_probe* p, void* stream);
 
 /* Debug timeline of the attention kernel: `device_buf` = 3 * 48 * 8 uint64 (clock64 stamps of one CTA: two softmax warps
- * and the MMA issuer, first 48 kv tiles), filled by pf_attn_fwd_masked launches with variant bit 1 (value 2) set.
+ * and the MMA issuer, first 48 kv tiles), filled by pf_attn_fwd_masked launches with variant bit 1 (value 2) set.  While a
+ * buffer is set, launches of the two-q-tile kernel use its timeline instantiation and fill 4 x 64 x 12 uint64 instead
+ * (softmax thread 0 of q tile A / B and the two MMA issuers of CTA (0, 0, 0), first 64 kv tiles).
  * NULL disables.  Test/profiling aid only (tools/gpu_check.py attn_trace). */
 PF_API int pf_debug_attn_trace(void* device_buf);
 /* Per-CTA records of the same trace variant: `device_buf` = capacity x 8 uint64 (clock64 at CTA entry, at exit, number of

@@ -499,10 +499,7 @@ int warmup_attn2();
 void attn2_set_trace(unsigned long long* p, long long cap);
 void attn2_set_timeline(unsigned long long* p);
 
-int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, cudaStream_t stream);
-constexpr int ATT2_DEFAULT_POLY = 0;       // measured on B200: a warp's MUFU.EX2 costs it 16 clk and the 9-instruction
-constexpr int ATT2_DEFAULT_PINGPONG = 0;
-constexpr int ATT2_DEFAULT_SPLIT_ROWS = 0;   // polynomial pair costs the same; strict alternation of the warpgroups loses 6 %
+int attn2_launch(const pf_attn_desc* d, cudaStream_t stream);
 
 int warmup_attn() {
   int rc = warmup_attn2();
@@ -581,27 +578,15 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   PF_REQUIRE(d->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pf_attn_fwd_masked: out must be 16-byte aligned");
   PF_REQUIRE(d->peer_count <= 1 || d->pair_sched != nullptr, "pf_attn_fwd_masked: peer stores need the two-q-tile kernel (pair_sched)");
 
-  // variant: 0 = default (two-q-tile kernel when a pair schedule is given, else the one-tile kernel); 0x10 | k = two-q-tile
-  // kernel with k of every 4 exponential pairs on the FMA pipe (k = 0..3); 1 / 2 / 3 = one-tile kernel (polynomial mix / clock
-  // trace / plain)
-  PF_REQUIRE((d->variant & ~0xff) == 0, "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
-  const bool use_pair = (d->variant & 0xd8) || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
+  // variant: 0 = default (the two-q-tile kernel pf_attn2.cu when a pair schedule is given, else the one-tile kernel below);
+  // 0x10 = the two-q-tile kernel, explicitly; 1 / 2 / 3 = the one-tile kernel (polynomial mix / clock trace / plain), kept for A/B
+  PF_REQUIRE(d->variant == 0x10 || (d->variant >= 0 && d->variant <= 3), "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
+  const bool use_pair = d->variant == 0x10 || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
   PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
   if (use_pair) {
     PF_REQUIRE(d->pair_sched != nullptr && d->pair_mask_index != nullptr && d->pair_mask_bits != nullptr,
                "pf_attn_fwd_masked: variant 0x%x needs pair_sched, pair_mask_index and pair_mask_bits", d->variant);
-    // 0x10 | k: k of every 4 exponential pairs on the FMA pipe; | 0x20: WITHOUT the ping-pong token (A/B)
-    // 0x80 | k: the E/C-phase kernel (pf_attn4.cu) with k of every 8 exponential pairs on the FMA pipe (k = 0..4)
-    const int poly = (d->variant & 0x80) ? (d->variant & 0x7) : (d->variant & 0x10) ? (d->variant & 0x3) : ATT2_DEFAULT_POLY;
-    PF_REQUIRE(!(d->variant & 0x80) || poly <= 4, "pf_attn_fwd_masked: variant 0x%x: at most 4 of 8 pairs on the FMA pipe", d->variant);
-    if (d->variant == 0x08) return attn2_launch(d, 0, 0, 3, stream);   // 0x08: software-pipelined softmax (pf_attn5.cu)
-    if (d->variant == 0x0c) return attn2_launch(d, 0, 0, 4, stream);   // 0x0c: pf_attn2.cu with LEAN = 3
-    if (d->variant == 0x0d) return attn2_launch(d, 0, 0, 5, stream);   // 0x0d: LEAN = 1 (branch-free rescale test)
-    if (d->variant == 0x0e) return attn2_launch(d, 0, 0, 6, stream);   // 0x0e: LEAN = 2 (overlapped barrier round trips)
-    const int pingpong = (d->variant & 0xd0) ? ((d->variant & 0x20) ? 0 : 1) : ATT2_DEFAULT_PINGPONG;
-    // 0x40: two threads per row (pf_attn3.cu)
-    const int split = (d->variant & 0x80) ? 2 : (d->variant & 0x40) ? 1 : ((d->variant & 0x10) ? 0 : ATT2_DEFAULT_SPLIT_ROWS);
-    return attn2_launch(d, poly, pingpong, split, stream);
+    return attn2_launch(d, stream);
   }
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};

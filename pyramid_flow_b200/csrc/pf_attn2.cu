@@ -7,17 +7,21 @@
 //   * one CTA per SM owns TWO adjacent 128-row q tiles of one (batch, head) and walks the union of their kv tile lists once:
 //     every K/V tile is loaded from L2 once for 256 q rows (half the L2->smem traffic of the one-tile kernel);
 //   * softmax warpgroup X (warps 4X..4X+3, 128 threads) owns q tile X: ONE THREAD = ONE FULL ROW of 128 scores in registers.
-//     The row max is exact and thread-local: no partner exchange, no shared-memory round trip, no stale reference.  While
-//     warpgroup 0 exponentiates tile A(j), the tensor pipe runs S_B(j) / P_A.V and warpgroup 1 is one half-phase behind;
-//   * the FMA pipe takes a share of the exponentials off the MUFU (XU) pipe, which bounds attention at head_dim 64
-//     (16384 ex2 per 128x128 tile at 16/clk/SM = 1024 clk against 512 clk of MMA): Cody-Waite split + cubic, evaluated with
-//     packed fma.rn.f32x2 / add.f32x2 (SASS FFMA2 / FADD2) so the emulation is not issue-bound; the scale-and-subtract and the
-//     row sums are packed too;
+//     The row max is exact and thread-local: no partner exchange, no shared-memory round trip, no stale reference;
+//   * scale-and-subtract and the row sums are packed (fma.rn.f32x2 / add.rn.f32x2 = SASS FFMA2 / FADD2); every exponential is a
+//     MUFU.EX2 -- the XU pipe bounds attention at head_dim 64 (16384 ex2 per 128x128 tile at 16/clk/SM = 1024 clk against
+//     512 clk of MMA);
 //   * O is rescaled in TMEM by the owning thread only when the row max moved by more than 2^8 since the last rescale (the
-//     exponent argument is therefore always <= 8: no overflow for any input);
+//     exponent argument is therefore always <= 8: no overflow for any input); the test is branch-free;
+//   * the second q tile's softmax warps start `b_delay` clocks late, once per CTA (PF_OPT_ATTN_TILE_PHASE): nothing couples
+//     the two warpgroups but the K/V ring, so started together they STAY together -- both exponentiate (sharing the XU), then
+//     both load / reduce / store with the XU idle; started out of phase they stay out of phase, and one tile's TMEM loads, row
+//     max and P stores run under the other tile's MUFU stream;
 //   * warp 8/9 = MMA issuers of tile A/B (one elected lane each), warp 10 = TMA producer (Q once, K through a 4-stage and V
 //     through a 3-stage mbarrier ring shared by both tiles), warp 11 allocates TMEM; setmaxnreg moves registers from
 //     warps 8-11 (40) to the softmax warpgroups (232).
+// What was tried on top and measured slower or equal on B200 is listed in DESIGN.md §3b (polynomial exponentials on the FMA
+// pipe, a strict ping-pong token between the tiles, two threads per row, an exponential-only phase, a software-pipelined loop).
 // TMEM (512 columns): tile X at column 256 X: S fp32 [0,128) | O fp32 [128,192) | P bf16x2 [192,256).
 #include <algorithm>
 #include <vector>
@@ -26,8 +30,9 @@
 
 namespace pf {
 
-// LEAN bit 0: branch-free lazy-rescale test; bit 1: the barrier round trips of a tile overlap its TMEM traffic (LEAN blocks below)
-template <int POLY, int PINGPONG, int LEAN = 0, int TL = 0>
+// TL = 1: timeline instantiation (per-iteration clock64 stamps of CTA (0, 0, 0): softmax thread 0 of each q tile and the two MMA
+// issuers, tools/gpu_check.py attn_timeline); the TL = 0 kernel carries none of it
+template <int TL>
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Attn2Args a) {
@@ -190,16 +195,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       uint64_t l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);
       int entry = sched[1];
       const int* mask_idx = a.pmask_idx + (static_cast<size_t>(b) * a.n_pairs + pair) * 2 * a.sched_stride;
-      // Ping-pong: the exponential phase (the XU-bound part) of the two warpgroups is strictly alternated with a token passed
-      // through named barriers.  Left alone the two q tiles fall into lockstep (both S tiles become ready together), contend
-      // for the XU during their exps and leave it idle while both load / reduce / store: measured XU pipe 59 % busy, the same
-      // as the one-tile kernel (profiles/r02_attn2_lockstep_ncu.txt).  With the token one warpgroup's TMEM loads, max and P
-      // store run under the other's exponentials.
-      const bool pingpong = PINGPONG && act_lo;
-      if (pingpong && X == 1) a2_token_pass(1);
-      bool sfull_ok = false;                                  // LEAN: S(j) already seen complete by the probe of iteration j-1
       const bool tl_on = TL && a.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && quarter == 0 && lane == 0;
-      auto tl = [&](int j, int slot) {   // TL = 1 only: per-iteration clock stamps of CTA (0, 0, 0) (tools/gpu_check.py attn4_timeline)
+      auto tl = [&](int j, int slot) {   // TL = 1 only: per-iteration clock stamps of CTA (0, 0, 0) (tools/gpu_check.py attn_timeline)
         if (TL && tl_on && j < 64) a.timeline[(X * 64 + j) * 12 + slot] = clock64();
       };
       if (X == 1 && act_lo && a.b_delay > 0) {
@@ -235,7 +232,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         bool pv_ok = true;
         if (j > 0) pv_ok = mbar_test(&bar_pv_done[X], (j - 1) & 1);    // probed early, consumed before the P store
-        if (!(LEAN & 2) || !sfull_ok) mbar_wait(&bar_s_full[X], j & 1);
+        mbar_wait(&bar_s_full[X], j & 1);
         tc_fence_after();
         tl(j, 1);
         if (a.trace && j == 0 && threadIdx.x == 128) cta_stamp[1] = clock64();
@@ -246,13 +243,6 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_ld32(t_s + 32, v1);
         tmem_ld32(t_s + 64, v2);
         tmem_ld32(t_s + 96, v3);
-        if ((LEAN & 2) && j > 0) {
-          // P(j-1) went to TMEM at the end of the previous iteration; its completion wait and the p_full arrive sit HERE, under
-          // the latency of the four loads of S(j), instead of in front of them
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bar_p_full[X]);
-        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bar_s_free[X]);
@@ -266,29 +256,16 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const float m_tile = fmaxf(fmaxf(a2_max32(v0), a2_max32(v1)), fmaxf(a2_max32(v2), a2_max32(v3)));
 
         // ---- lazy rescale: move the reference only when the row max grew by more than 2^8 (exponent argument <= 8)
-        float alpha = 1.f;
-        bool need = false;
-        if (LEAN & 1) {
-          // branch-free (same values bit for bit): four data-dependent branches with their FSETP -> BRA latencies sat between the
-          // row max and the first exponential
-          const bool first = m_run == -INFINITY;
-          const bool grow = m_tile > m_run;
-          need = grow && !first && (m_tile - m_run) * c > 8.f;
-          const float e = a2_ex2(fmaxf((m_run - m_tile) * c, -126.f));
-          alpha = need ? e : 1.f;
-          m_run = (grow && (first || need)) ? m_tile : m_run;
-        } else if (m_tile > m_run) {
-          if (m_run == -INFINITY) {
-            m_run = m_tile;                      // everything accumulated so far is exactly zero
-          } else if ((m_tile - m_run) * c > 8.f) {
-            need = true;
-            alpha = a2_ex2(fmaxf((m_run - m_tile) * c, -126.f));
-            m_run = m_tile;
-          }
-        }
+        // (branch-free, same values as the nested ifs it replaces: four data-dependent branches with their FSETP -> BRA latencies
+        // sat between the row max and the first exponential: 2.92 -> 2.84 ms per launch at the bench shape)
+        const bool first = m_run == -INFINITY;                  // everything accumulated so far is exactly zero
+        const bool grow = m_tile > m_run;
+        const bool need = grow && !first && (m_tile - m_run) * c > 8.f;
+        const float alpha = need ? a2_ex2(fmaxf((m_run - m_tile) * c, -126.f)) : 1.f;
+        m_run = (grow && (first || need)) ? m_tile : m_run;
         const float m_ref = (m_run == -INFINITY) ? 0.f : m_run * c;
         const uint64_t nm2 = f2_pack(-m_ref, -m_ref);
-        if ((LEAN & 1) || need) {
+        {
           float a0, a1;
           f2_unpack(l01, a0, a1);
           l01 = f2_pack(a0 * alpha, a1 * alpha);
@@ -298,10 +275,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
         tl(j, 3);
         // ---- first half of the row
-        if (pingpong) a2_token_wait(1 + X);
         uint32_t pk0[16], pk1[16];
-        if (POLY > 0 && !masked) a2_exp64<POLY>(v0, v1, pk0, pk1, c2, nm2, l01, l23, a.zero);
-        else a2_exp64<0>(v0, v1, pk0, pk1, c2, nm2, l01, l23, a.zero);
+        a2_exp64(v0, v1, pk0, pk1, c2, nm2, l01, l23);
         tl(j, 4);
         // ---- P(j-1) consumed and O(j-1) produced before P is overwritten / O is rescaled
         if (j > 0) {
@@ -321,23 +296,15 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         tmem_st16(t_p, pk0);
         tmem_st16(t_p + 16, pk1);
-        // LEAN: S(j+1) has been on the tensor pipe since S(j) was released (about 1000 clk ago): probe its barrier now and consume
-        // the predicate at the top of the next iteration, so the mbarrier round trip (100-300 clk through the MIO queue, behind
-        // the MUFU stream) runs under the second half's exponentials instead of with the XU idle
-        if (LEAN & 2) sfull_ok = (j + 1 < n_kv) && mbar_test(&bar_s_full[X], (j + 1) & 1);
         tl(j, 5);
         // ---- second half
-        if (POLY > 0 && !masked) a2_exp64<POLY>(v2, v3, pk0, pk1, c2, nm2, l01, l23, a.zero);
-        else a2_exp64<0>(v2, v3, pk0, pk1, c2, nm2, l01, l23, a.zero);
-        if (pingpong && !(X == 1 && j == n_kv - 1)) a2_token_pass(2 - X);   // the other warpgroup's exponentials may start
+        a2_exp64(v2, v3, pk0, pk1, c2, nm2, l01, l23);
         tl(j, 6);
         tmem_st16(t_p + 32, pk0);
         tmem_st16(t_p + 48, pk1);
-        if (!(LEAN & 2) || j == n_kv - 1) {
-          tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bar_p_full[X]);
-        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_p_full[X]);
         tl(j, 7);
       }
 
@@ -412,41 +379,22 @@ void attn2_set_trace(unsigned long long* p, long long cap) {
 }
 void attn2_set_timeline(unsigned long long* p) { g_a2_timeline = p; }
 
-template <int POLY, int PINGPONG, int LEAN = 0, int TL = 0>
+template <int TL>
 static int attn2_launch_t(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream) {
-  auto kern = attn2_fwd_kernel<POLY, PINGPONG, LEAN, TL>;
+  auto kern = attn2_fwd_kernel<TL>;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), A2_SMEM_BYTES, "attn2_fwd_kernel")) return rc;
   kern<<<grid, A2_THREADS, A2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], a);
   return check_launch("pf_attn_fwd_masked(pair kernel)");
 }
 
-int warmup_attn3();
-int warmup_attn4();
-int warmup_attn5();
-
 int warmup_attn2() {
-  int rc = 0;
-#define PF_WARM2(P, Q) if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<P, Q>), A2_SMEM_BYTES, "attn2_fwd_kernel")
-  PF_WARM2(0, 0); PF_WARM2(1, 0); PF_WARM2(2, 0); PF_WARM2(3, 0);
-  PF_WARM2(0, 1); PF_WARM2(1, 1); PF_WARM2(2, 1); PF_WARM2(3, 1);
-#undef PF_WARM2
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0, 0, 1>), A2_SMEM_BYTES, "attn2_fwd_kernel<lean 1>");
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0, 0, 2>), A2_SMEM_BYTES, "attn2_fwd_kernel<lean 2>");
-  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0, 0, 3>), A2_SMEM_BYTES, "attn2_fwd_kernel<lean 3>");
-  if (!rc) rc = warmup_attn3();
-  if (!rc) rc = warmup_attn4();
-  if (!rc) rc = warmup_attn5();
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<0>), A2_SMEM_BYTES, "attn2_fwd_kernel<0>");
+  if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn2_fwd_kernel<1>), A2_SMEM_BYTES, "attn2_fwd_kernel<1>");
   return rc;
 }
 
-// called by pf_attn_fwd_masked (pf_attn.cu) after argument validation; poly = exponentials per 8 on the FMA pipe / 2
-int attn3_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, int pingpong, cudaStream_t stream);
-int attn4_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, int poly8, int pingpong, cudaStream_t stream);
-int attn5_launch_raw(const CUtensorMap* tm, const Attn2Args& a, dim3 grid, cudaStream_t stream);
-
-// split_rows: 4 = the kernel above with LEAN = 1, 3 = pf_attn5.cu (software-pipelined softmax), 2 = pf_attn4.cu (E/C phases; poly = pairs per 8), 1 = pf_attn3.cu (two threads per row, 16 softmax warps),
-// 0 = the kernel above
-int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, cudaStream_t stream) {
+// called by pf_attn_fwd_masked (pf_attn.cu) after argument validation
+int attn2_launch(const pf_attn_desc* d, cudaStream_t stream) {
   CUtensorMap tm[3];
   const void* ptrs[3] = {d->q, d->k, d->v};
   for (int i = 0; i < 3; ++i) {
@@ -473,7 +421,6 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, 
   a.sched_stride = d->sched_stride;
   a.pmask_idx = d->pair_mask_index;
   a.pmask_bits = static_cast<const uint4*>(d->pair_mask_bits);
-  a.zero = 0u;
   a.trace = g_a2_trace;
   a.trace_cap = g_a2_trace_cap;
   a.timeline = g_a2_timeline;
@@ -498,25 +445,7 @@ int attn2_launch(const pf_attn_desc* d, int poly, int pingpong, int split_rows, 
   // pair p covers tiles q_tiles-2-2p and q_tiles-1-2p: launch the pairs whose upper tile is >= q_tile_begin
   const int pairs = (a.q_tiles - a.q_tile_begin + 1) / 2;
   dim3 grid(pairs, d->heads, d->batch);
-  if (split_rows == 3) return attn5_launch_raw(tm, a, grid, stream);
-  if (split_rows == 4) return a.timeline ? attn2_launch_t<0, 0, 3, 1>(tm, a, grid, stream) : attn2_launch_t<0, 0, 3>(tm, a, grid, stream);
-  if (split_rows == 5) return attn2_launch_t<0, 0, 1>(tm, a, grid, stream);
-  if (split_rows == 6) return attn2_launch_t<0, 0, 2>(tm, a, grid, stream);
-  if (a.timeline != nullptr && poly == 0 && !pingpong) return attn2_launch_t<0, 0, 0, 1>(tm, a, grid, stream);   // debug timeline
-  if (split_rows == 2) return attn4_launch_raw(tm, a, grid, poly, pingpong, stream);
-  if (split_rows) return attn3_launch_raw(tm, a, grid, pingpong, stream);
-  switch (poly * 2 + (pingpong ? 1 : 0)) {
-    case 0: return attn2_launch_t<0, 0>(tm, a, grid, stream);
-    case 1: return attn2_launch_t<0, 1>(tm, a, grid, stream);
-    case 2: return attn2_launch_t<1, 0>(tm, a, grid, stream);
-    case 3: return attn2_launch_t<1, 1>(tm, a, grid, stream);
-    case 4: return attn2_launch_t<2, 0>(tm, a, grid, stream);
-    case 5: return attn2_launch_t<2, 1>(tm, a, grid, stream);
-    case 6: return attn2_launch_t<3, 0>(tm, a, grid, stream);
-    case 7: return attn2_launch_t<3, 1>(tm, a, grid, stream);
-  }
-  set_error("pf_attn_fwd_masked: bad poly %d", poly);
-  return -1;
+  return a.timeline != nullptr ? attn2_launch_t<1>(tm, a, grid, stream) : attn2_launch_t<0>(tm, a, grid, stream);
 }
 
 }  // namespace pf

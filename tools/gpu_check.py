@@ -426,7 +426,7 @@ def group_attn_perf():
     flops = 4.0 * 64 * H * float(pairs.sum())
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     ref = None
-    for variant in (3, 0x30, 0x0c, 0x08, 0):
+    for variant in (3, 0x10, 0):
         out.zero_()
         ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps), iters=8, warm=2)
         if ref is None:
@@ -524,9 +524,9 @@ def group_attn_trace():
     N, SL = 48, 8
     buf = torch.zeros(3 * N * SL, dtype=torch.int64, device=dev)
     _lib.check(_lib.load().pf_debug_attn_trace(buf.data_ptr()), "trace")
-    variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x30 / 0x10 = two-q-tile kernel
+    variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x10 = two-q-tile kernel
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
-    if variant & 0xdc:
+    if variant & 0x10:
         n_cta = ((((S + 127) // 128) + 1) // 2) * H * B
     for _ in range(2):
         ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps)
@@ -575,9 +575,9 @@ def group_attn_cta_trace():
     buf = torch.zeros(n_cta * 8, dtype=torch.int64, device=dev)
     lib = _lib.load()
     _lib.check(lib.pf_debug_attn_cta_trace(buf.data_ptr(), n_cta), "cta trace")
-    variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x30 / 0x10 = two-q-tile kernel
+    variant = int(os.environ.get("PF_TRACE_VARIANT", "2"), 0)     # 2 = one-tile trace kernel; 0x10 = two-q-tile kernel
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
-    if variant & 0xdc:
+    if variant & 0x10:
         n_cta = ((((S + 127) // 128) + 1) // 2) * H * B
     for _ in range(2):
         ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps)
@@ -615,9 +615,9 @@ def group_attn_cta_trace():
           f"min {float((busy / (2 * span)).min()):.3f}; span mean {float(span.mean()):.0f} cycles, max {float(span.max()):.0f}")
 
 
-def group_attn4_timeline():
-    """clock64 timeline of CTA (0, 0, 0) of the E/C-phase attention kernel (pf_attn4.cu, timeline instantiation) at the bench
-    shape: softmax thread 0 of q tile A / B and the two MMA issuers, first 64 kv tiles."""
+def group_attn_timeline():
+    """clock64 timeline of CTA (0, 0, 0) of the two-q-tile attention kernel (pf_attn2.cu, timeline instantiation) at the bench
+    shape: softmax thread 0 of q tile A / B and the two MMA issuers, first 64 kv tiles; PF_TL_PHASE = PF_OPT_ATTN_TILE_PHASE."""
     import torch
     from pyramid_flow_b200 import ops, _lib
     dev = "cuda"
@@ -634,47 +634,39 @@ def group_attn4_timeline():
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     N, SL = 64, 12
-    phase = int(os.environ.get("PF_TL_PHASE", "0"))
-    _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, phase)
-    print(f"[attn4_timeline] PF_OPT_ATTN_TILE_PHASE = {phase}")
-    for variant in [int(x, 0) for x in os.environ.get("PF_TL_VARIANTS", "0x08").split()]:
-        if variant == 0x08:   # pf_attn5.cu
-            names = ["top", "exp chunk0", "probes+exp chunk1", "pv+st01+ld01", "chunk2", "chunk3", "st wait+p_full", "ld wait+s_free", "max"]
-            s_free_slot, s_free_lag, p_full_slot = 7, 1, 6
-        elif variant & 0x80:  # pf_attn4.cu
-            names = ["top", "S_full", "ld+s_free", "max", "token", "E", "C1+pv", "st1", "C2+st2+wait", "p_full"]
-            s_free_slot, s_free_lag, p_full_slot = 2, 0, 9
-        else:                 # pf_attn2.cu (0x30 default, 0x0c LEAN)
-            names = ["top", "S_full", "ld+s_free", "max+alpha", "exp first half", "pv wait+st", "exp second half", "st+wait+p_full"]
-            s_free_slot, s_free_lag, p_full_slot = 2, 0, 7
-        ns = len(names)
+    names = ["top", "S_full", "ld+s_free", "max+rescale test", "exp first half", "pv wait+st", "exp second half", "st+wait+p_full"]
+    ns = len(names)
+    for phase in [int(x) for x in os.environ.get("PF_TL_PHASE", "-1").split()]:
+        if phase >= 0:
+            _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, phase)
+        print(f"[attn_timeline] PF_OPT_ATTN_TILE_PHASE = {_lib.get_option(_lib.PF_OPT_ATTN_TILE_PHASE)}")
         buf = torch.zeros(4 * N * SL, dtype=torch.int64, device=dev)
         _lib.check(_lib.load().pf_debug_attn_trace(buf.data_ptr()), "trace")
         for _ in range(2):
-            ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps)
+            ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, 0x10, pair_sched=ps)
         torch.cuda.synchronize()
         _lib.check(_lib.load().pf_debug_attn_trace(None), "trace")
         t = buf.cpu().view(4, N, SL).double()
         t0 = float(t[0, 16, 0])
-        print(f"[attn4_timeline] variant {variant:#x}: softmax slots " + " ".join(f"{i}:{n}" for i, n in enumerate(names)) +
+        print("[attn_timeline] softmax slots " + " ".join(f"{i}:{n}" for i, n in enumerate(names)) +
               " | MMA slots 0:s_free seen 1:QK(j+1) issued 2:p_full seen 3:v_full 4:PV issued")
-        for j in range(16, 22):
+        for j in range(16, 19):
             for r, nm in ((0, "sm A"), (1, "sm B"), (2, "mmaA"), (3, "mmaB")):
                 n = ns if r < 2 else 5
-                print(f"[attn4_timeline] {variant:#x} j={j:2d} {nm}: " + " ".join(f"{int(t[r, j, i] - t0):7d}" for i in range(n)))
+                print(f"[attn_timeline] j={j:2d} {nm}: " + " ".join(f"{int(t[r, j, i] - t0):7d}" for i in range(n)))
         lo, hi = 8, 56
         per = float(t[0, hi, 0] - t[0, lo, 0]) / (hi - lo)
         for r, nm in ((0, "A"), (1, "B")):
             d = t[r, lo:hi]
             ph = " | ".join(f"{names[i + 1]} {float((d[:, i + 1] - d[:, i]).mean()):.0f}" for i in range(ns - 1))
             nxt = float((t[r, lo + 1:hi + 1, 0] - t[r, lo:hi, ns - 1]).mean())
-            print(f"[attn4_timeline] {variant:#x} tile {nm}: cycles per kv tile {per:.0f}; mean phase durations: {ph} | loop back {nxt:.0f}")
+            print(f"[attn_timeline] tile {nm}: cycles per kv tile {per:.0f}; mean phase durations: {ph} | loop back {nxt:.0f}")
         for r, nm in ((2, "A"), (3, "B")):
             d = t[r, lo:hi]
             sm = t[r - 2, lo:hi]
-            smf = t[r - 2, lo - s_free_lag:hi - s_free_lag]
-            print(f"[attn4_timeline] {variant:#x} MMA {nm}: s_free arrive->seen {float((d[:, 0] - smf[:, s_free_slot]).mean()):.0f} | QK issue {float((d[:, 1] - d[:, 0]).mean()):.0f} | "
-                  f"p_full arrive->seen {float((d[:, 2] - sm[:, p_full_slot]).mean()):.0f} | v_full wait {float((d[:, 3] - d[:, 2]).mean()):.0f} | PV issue {float((d[:, 4] - d[:, 3]).mean()):.0f}")
+            print(f"[attn_timeline] MMA {nm}: s_free arrive->seen {float((d[:, 0] - sm[:, 2]).mean()):.0f} | QK issue {float((d[:, 1] - d[:, 0]).mean()):.0f} | "
+                  f"p_full arrive->seen {float((d[:, 2] - sm[:, 7]).mean()):.0f} | v_full wait {float((d[:, 3] - d[:, 2]).mean()):.0f} | PV issue {float((d[:, 4] - d[:, 3]).mean()):.0f}")
+    _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, 800)
 
 
 def group_attn_phase_sweep():
@@ -696,8 +688,8 @@ def group_attn_phase_sweep():
     flops = 4.0 * 64 * H * float(pairs.sum())
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     ref = None
-    variants = [int(x, 0) for x in os.environ.get("PF_SWEEP_VARIANTS", "0x30 0x0c").split()]
-    for delay in [int(x) for x in os.environ.get("PF_SWEEP_DELAYS", "0 300 600 900 1200 1500 1800 2400 3000").split()]:
+    variants = [0x10]
+    for delay in [int(x) for x in os.environ.get("PF_SWEEP_DELAYS", "0 300 600 800 1000 1200 1500 1800 2400 3000").split()]:
         _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, delay)
         for variant in variants:
             out.zero_()
@@ -707,7 +699,7 @@ def group_attn_phase_sweep():
             same = bool(torch.equal(out, ref)) if variant == variants[0] else None
             print(f"[attn_phase_sweep] phase {delay:5d} clk, variant {variant:#x}: {ms:.3f} ms, {flops/ms/1e9:.0f} TFLOP/s"
                   + ("" if same is None else f", bits == phase-0 output: {same}"), flush=True)
-    _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, 0)
+    _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, 800)
 
 
 def group_vae_perf():
