@@ -31,7 +31,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-ATTN_TRAFFIC_BYTES = 459.96e6   # profiles/r02_attn2_ncu.txt: dram__bytes_read 357.70 MB + dram__bytes_write 102.26 MB per launch
+ATTN_TRAFFIC_BYTES = 460.71e6   # profiles/r02_attn2_final_ncu.txt: dram__bytes_read 358.04 MB + dram__bytes_write 102.67 MB per launch
 METRIC = "dit_step_latent_tokens_per_sec"
 UNIT = "tokens/s"
 WORKLOAD = ("miniFLUX 768p/10s (BASELINE configs[2]) — one DiT forward at unit 30 / stage 2: CFG batch 2, "
@@ -729,7 +729,7 @@ def run_ours(args):
                      "share_of_step": (attn_avg * n_attn / ms_eager) if ms_eager else None,
                      "algorithmic_flops_per_launch": attn_flops_launch,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
-                     # shape (profiles/r02_attn2_ncu.txt) -- the algorithmic bytes are Q+K+V+O
+                     # shape (profiles/r02_attn2_final_ncu.txt) -- the algorithmic bytes are Q+K+V+O
                      "traffic": ATTN_TRAFFIC_BYTES if lay is None else None, "traffic_unit": "B/launch",
                      "algorithmic_bytes_per_launch": 4.0 * b * plan.seq * cfg.inner_dim * 2},
     }
