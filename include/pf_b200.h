@@ -40,11 +40,13 @@ enum {
   PF_OPT_ATTN_PAIR_KERNEL = 2,  /* variant 0 of pf_attn_fwd_masked = the two-q-tile kernel (needs pair_sched) */
   PF_OPT_ATTN_TILE_PHASE = 3,   /* two-q-tile attention kernel: SM clocks the second q tile's softmax warps are held back once per
                                  * CTA so the two tiles run out of phase (0 = start together) */
-  PF_OPT_COUNT = 4
+  PF_OPT_ATTN_TRIPLE_KERNEL = 4, /* variant 0 of pf_attn_fwd_masked = the three-q-tile kernel when group_sched is given */
+  PF_OPT_COUNT = 5
 };
 #define PF_OPT_DEFAULT_GEMM_STAGED_RESID 1
 #define PF_OPT_DEFAULT_GEMM_WAVE_TILING 1
 #define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 1
+#define PF_OPT_DEFAULT_ATTN_TRIPLE_KERNEL 0
 #define PF_OPT_DEFAULT_ATTN_TILE_PHASE 800   /* measured on B200: 2.84 -> 2.78 ms per launch at the bench shape (tools/gpu_check.py attn_phase_sweep) */
 PF_API int pf_set_option(int key, int value);
 PF_API int pf_get_option(int key);
@@ -180,6 +182,11 @@ typedef struct pf_attn_desc {
    * `out` is ignored. */
   void* peer_out[PF_MAX_PEERS];
   int32_t peer_count, peer_chunk_rows, peer_col_begin;
+  /* three-q-tile kernel (variant 0x20, or variant 0 with PF_OPT_ATTN_TRIPLE_KERNEL): schedule and row masks of groups of three
+   * q tiles from pf_attn_build_group_schedule / pf_attn_build_group_masks (group = 3), same sched_stride */
+  const int32_t* group_sched;
+  const int32_t* group_mask_index;
+  const void* group_mask_bits;
 } pf_attn_desc;
 
 /* Host helper: from host copies of seg/time ids builds, for each (batch, 128-row q tile), the list of 128-wide kv
@@ -201,6 +208,14 @@ PF_API int pf_attn_build_pair_schedule(const int32_t* tile_sched_host, int32_t b
 PF_API int64_t pf_attn_build_pair_masks(const int32_t* seg_host, const int32_t* time_host, const int32_t* pair_sched_host,
                                         int32_t batch, int32_t seq, int32_t sched_stride, int32_t* mask_index,
                                         uint32_t* mask_bits, int64_t capacity_blocks);
+/* Host helpers of the three-q-tile kernel, the pair forms generalised to groups of `group` (2..4) q tiles counted from the end
+ * of the sequence.  Entry = (kv_tile << 8) | flags, 2 flag bits per tile X at bit 2 X (X = 0 the lowest tile of the group);
+ * mask_index[batch, n_groups, group * sched_stride], entry e / tile X at [group e + X]; blocks as in the pair form. */
+PF_API int pf_attn_build_group_schedule(const int32_t* tile_sched_host, int32_t batch, int32_t seq, int32_t sched_stride,
+                                        int32_t group, int32_t* out);
+PF_API int64_t pf_attn_build_group_masks(const int32_t* seg_host, const int32_t* time_host, const int32_t* group_sched_host,
+                                         int32_t batch, int32_t seq, int32_t sched_stride, int32_t group,
+                                         int32_t* mask_index, uint32_t* mask_bits, int64_t capacity_blocks);
 PF_API int pf_attn_fwd_masked(const pf_attn_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm + AdaLN modulate pre-pass (HBM-bound)

@@ -15,7 +15,8 @@ LIB_PATH = _HERE / "lib" / "libpf_b200.so"
 SYMBOLS = [
     "pf_last_error", "pf_version", "pf_device_check", "pf_warmup", "pf_set_option", "pf_get_option", "pf_launch_count",
     "pf_gemm_bf16",
-    "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_build_pair_masks", "pf_attn_fwd_masked",
+    "pf_attn_build_schedule", "pf_attn_build_pair_schedule", "pf_attn_build_pair_masks", "pf_attn_build_group_schedule",
+    "pf_attn_build_group_masks", "pf_attn_fwd_masked",
     "pf_ln_modulate", "pf_small_linear", "pf_timestep_embedding",
     "pf_patchify", "pf_unpatchify", "pf_cfg_euler_step", "pf_stage_hop",
     "pf_causal_conv3d", "pf_groupnorm_stats", "pf_groupnorm_apply", "pf_softmax_rows", "pf_pack_latent", "pf_blend_tiles",
@@ -27,7 +28,7 @@ SYMBOLS = [
     "pf_debug_attn_cta_trace",
 ]
 
-PF_OPT_GEMM_STAGED_RESID, PF_OPT_GEMM_WAVE_TILING, PF_OPT_ATTN_PAIR_KERNEL, PF_OPT_ATTN_TILE_PHASE = range(4)
+PF_OPT_GEMM_STAGED_RESID, PF_OPT_GEMM_WAVE_TILING, PF_OPT_ATTN_PAIR_KERNEL, PF_OPT_ATTN_TILE_PHASE, PF_OPT_ATTN_TRIPLE_KERNEL = range(5)
 PF_EPI_STORE_BF16, PF_EPI_GELU_BF16, PF_EPI_STORE_F32, PF_EPI_GATE_RESID, PF_EPI_QKV_ROPE, PF_EPI_QKV_GELU = range(6)
 
 
@@ -61,6 +62,7 @@ class AttnDesc(C.Structure):
         ("pair_mask_index", C.c_void_p), ("pair_mask_bits", C.c_void_p),
         ("peer_out", C.c_void_p * 8),
         ("peer_count", C.c_int32), ("peer_chunk_rows", C.c_int32), ("peer_col_begin", C.c_int32),
+        ("group_sched", C.c_void_p), ("group_mask_index", C.c_void_p), ("group_mask_bits", C.c_void_p),
     ]
 
 
@@ -119,6 +121,10 @@ def load() -> C.CDLL:
     lib.pf_attn_build_pair_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_int64]
     lib.pf_attn_build_pair_masks.restype = C.c_int64
+    lib.pf_attn_build_group_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.pf_attn_build_group_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_void_p, C.c_void_p, C.c_int64]
+    lib.pf_attn_build_group_masks.restype = C.c_int64
     lib.pf_ctx_create.argtypes = [C.POINTER(C.c_void_p)]
     for name in ("pf_ctx_destroy", "pf_ctx_record_end"):
         getattr(lib, name).argtypes = [C.c_void_p]

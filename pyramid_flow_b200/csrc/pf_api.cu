@@ -111,6 +111,7 @@ static void options_init() {
   g_options[PF_OPT_GEMM_WAVE_TILING].store(PF_OPT_DEFAULT_GEMM_WAVE_TILING);
   g_options[PF_OPT_ATTN_PAIR_KERNEL].store(PF_OPT_DEFAULT_ATTN_PAIR_KERNEL);
   g_options[PF_OPT_ATTN_TILE_PHASE].store(PF_OPT_DEFAULT_ATTN_TILE_PHASE);
+  g_options[PF_OPT_ATTN_TRIPLE_KERNEL].store(PF_OPT_DEFAULT_ATTN_TRIPLE_KERNEL);
 }
 int get_option(int key) {
   std::call_once(g_options_once, options_init);

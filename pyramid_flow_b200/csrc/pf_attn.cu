@@ -500,9 +500,12 @@ void attn2_set_trace(unsigned long long* p, long long cap);
 void attn2_set_timeline(unsigned long long* p);
 
 int attn2_launch(const pf_attn_desc* d, cudaStream_t stream);
+int attn3q_launch(const pf_attn_desc* d, cudaStream_t stream);
+int warmup_attn3q();
 
 int warmup_attn() {
   int rc = warmup_attn2();
+  if (!rc) rc = warmup_attn3q();
 ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,0>");
   if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<1, 0>), ATT_SMEM_BYTES, "attn_fwd_kernel<1,0>");
   if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<0, 1>), ATT_SMEM_BYTES, "attn_fwd_kernel<0,1>");
@@ -580,7 +583,13 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
 
   // variant: 0 = default (the two-q-tile kernel pf_attn2.cu when a pair schedule is given, else the one-tile kernel below);
   // 0x10 = the two-q-tile kernel, explicitly; 1 / 2 / 3 = the one-tile kernel (polynomial mix / clock trace / plain), kept for A/B
-  PF_REQUIRE(d->variant == 0x10 || (d->variant >= 0 && d->variant <= 3), "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
+  PF_REQUIRE(d->variant == 0x10 || d->variant == 0x20 || (d->variant >= 0 && d->variant <= 3), "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
+  // 0x20 = the three-q-tile kernel (pf_attn3q.cu), also variant 0 under PF_OPT_ATTN_TRIPLE_KERNEL when its schedule is given
+  if (d->variant == 0x20 || (d->variant == 0 && d->group_sched != nullptr && get_option(PF_OPT_ATTN_TRIPLE_KERNEL))) {
+    PF_REQUIRE(d->group_sched != nullptr && d->group_mask_index != nullptr && d->group_mask_bits != nullptr,
+               "pf_attn_fwd_masked: variant 0x%x needs group_sched, group_mask_index and group_mask_bits", d->variant);
+    return attn3q_launch(d, stream);
+  }
   const bool use_pair = d->variant == 0x10 || (d->variant == 0 && d->pair_sched != nullptr && (get_option(PF_OPT_ATTN_PAIR_KERNEL) || d->peer_count > 1));
   PF_REQUIRE(d->peer_count <= 1 || use_pair, "pf_attn_fwd_masked: peer stores are implemented by the two-q-tile kernel only");
   if (use_pair) {

@@ -164,17 +164,22 @@ def attn_build_schedule(seg: torch.Tensor, time: torch.Tensor):
 
 class PairSchedule:
     """Schedule of the two-q-tile attention kernel: `sched` int32 [batch, n_pairs, stride] (pf_attn_build_pair_schedule),
-    `mask_index` int32 [batch, n_pairs, 2 * stride] and `mask_bits` int32 [blocks, 128, 4] (pf_attn_build_pair_masks)."""
+    `mask_index` int32 [batch, n_pairs, 2 * stride] and `mask_bits` int32 [blocks, 128, 4] (pf_attn_build_pair_masks).
+    `group3` (optional) = the same three tensors for groups of three q tiles (pf_attn_build_group_schedule / _masks), the
+    schedule of the three-q-tile kernel."""
 
-    def __init__(self, sched: torch.Tensor, mask_index: torch.Tensor, mask_bits: torch.Tensor):
-        self.sched, self.mask_index, self.mask_bits = sched, mask_index, mask_bits
+    def __init__(self, sched: torch.Tensor, mask_index: torch.Tensor, mask_bits: torch.Tensor,
+                 group3: Optional["PairSchedule"] = None):
+        self.sched, self.mask_index, self.mask_bits, self.group3 = sched, mask_index, mask_bits, group3
 
     def to(self, device) -> "PairSchedule":
-        return PairSchedule(self.sched.to(device), self.mask_index.to(device), self.mask_bits.to(device))
+        return PairSchedule(self.sched.to(device), self.mask_index.to(device), self.mask_bits.to(device),
+                            None if self.group3 is None else self.group3.to(device))
 
     def __getitem__(self, idx) -> "PairSchedule":          # batch slice (block indices are global: the bit pool is shared)
         assert isinstance(idx, slice)
-        return PairSchedule(self.sched[idx], self.mask_index[idx], self.mask_bits)
+        return PairSchedule(self.sched[idx], self.mask_index[idx], self.mask_bits,
+                            None if self.group3 is None else self.group3[idx])
 
 
 def attn_build_pair_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, time: torch.Tensor) -> PairSchedule:
@@ -196,7 +201,29 @@ def attn_build_pair_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, t
     n2 = lib.pf_attn_build_pair_masks(seg.data_ptr(), time.data_ptr(), ps.data_ptr(), batch, seq, stride, midx.data_ptr(),
                                       bits.data_ptr(), int(n))
     assert n2 == n
-    return PairSchedule(ps, midx, bits)
+    return PairSchedule(ps, midx, bits, attn_build_group_schedule(sched, seq, seg, time, 3))
+
+
+def attn_build_group_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, time: torch.Tensor, group: int = 3) -> PairSchedule:
+    """The pair schedule generalised to groups of `group` q tiles (the three-q-tile kernel): sched int32 [batch, n_groups,
+    stride] with entries (kv_tile << 8) | 2 flag bits per tile, mask_index [batch, n_groups, group * stride], mask_bits."""
+    sched = sched.to(torch.int32).contiguous().cpu()
+    seg = seg.to(torch.int32).contiguous().cpu()
+    time = time.to(torch.int32).contiguous().cpu()
+    batch, qt, stride = sched.shape
+    n_groups = (qt + group - 1) // group
+    lib = _lib.load()
+    gs = torch.zeros(batch, n_groups, stride, dtype=torch.int32)
+    _lib.check(lib.pf_attn_build_group_schedule(sched.data_ptr(), batch, seq, stride, group, gs.data_ptr()), "pf_attn_build_group_schedule")
+    midx = torch.full((batch, n_groups, group * stride), -1, dtype=torch.int32)
+    n = lib.pf_attn_build_group_masks(seg.data_ptr(), time.data_ptr(), gs.data_ptr(), batch, seq, stride, group, midx.data_ptr(), None, 0)
+    if n < 0:
+        _lib.check(int(n), "pf_attn_build_group_masks")
+    bits = torch.zeros(max(1, int(n)), 128, 4, dtype=torch.int32)
+    n2 = lib.pf_attn_build_group_masks(seg.data_ptr(), time.data_ptr(), gs.data_ptr(), batch, seq, stride, group, midx.data_ptr(),
+                                       bits.data_ptr(), int(n))
+    assert n2 == n
+    return PairSchedule(gs, midx, bits)
 
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, seg: torch.Tensor,
@@ -229,6 +256,11 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
         d.pair_sched = pair_sched.sched.data_ptr()
         d.pair_mask_index = pair_sched.mask_index.data_ptr()
         d.pair_mask_bits = pair_sched.mask_bits.data_ptr()
+        g3 = pair_sched.group3
+        if g3 is not None:
+            assert g3.sched.is_contiguous() and g3.mask_index.is_contiguous() and g3.mask_bits.is_contiguous()
+            assert g3.sched.shape[-1] == sched.shape[-1]
+            d.group_sched, d.group_mask_index, d.group_mask_bits = g3.sched.data_ptr(), g3.mask_index.data_ptr(), g3.mask_bits.data_ptr()
     _lib.check(_lib.load().pf_attn_fwd_masked(C.byref(d), _lib.stream_ptr()), "pf_attn_fwd_masked")
 
 

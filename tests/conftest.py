@@ -14,3 +14,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_options_from_env():
+    """PF_TEST_ATTN_TRIPLE=1 runs the whole suite with the opt-in three-q-tile attention kernel as the default one."""
+    import os
+    if os.environ.get("PF_TEST_ATTN_TRIPLE") == "1":
+        from pyramid_flow_b200 import _lib
+        _lib.set_option(_lib.PF_OPT_ATTN_TRIPLE_KERNEL, 1)
+    yield

@@ -63,11 +63,12 @@ def test_attention_full_size_sampled_rows_and_properties():
     v1 = torch.randn(B, H, S, 64, device=dev).bfloat16()
     v2 = torch.randn(B, H, S, 64, device=dev).bfloat16()
     sched, pairs = ops.attn_build_schedule(seg, tim)
+    ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)      # -> the default (two-q-tile) kernel
     sd, td, scd = seg.to(dev), tim.to(dev), sched.to(dev)
 
     def run(v):
         out = torch.zeros(B, S, H * 64, device=dev, dtype=torch.bfloat16)
-        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125)
+        ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, pair_sched=ps)
         return out.float().view(B, S, H, 64)
 
     o1, o2, o12 = run(v1), run(v2), run((v1.float() + v2.float()).bfloat16())

@@ -1,6 +1,8 @@
 """Per-kernel parity through the C-ABI on B200 (ragged shapes included): GEMM epilogues, attention mask cases,
 elementwise kernels.  The checker for a single floating-point kernel is a plain PyTorch fp32 reference of the same op."""
 import pytest
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -97,7 +99,9 @@ def test_gemm_epilogues_row_ranges():
 
 # pf_attn_desc.variant: 3 = one-q-tile kernel (round 1, kept for A/B), 0x10 = two-q-tile kernel, 0 = default (= 0x10 when a pair
 # schedule is given)
-ATTN_VARIANTS = [3, 0x10, 0]
+# PF_TEST_ATTN_EXTRA = further variant codes to put through the same cases (0x20 = the opt-in three-q-tile kernel)
+ATTN_EXTRA = [int(x, 0) for x in os.environ.get("PF_TEST_ATTN_EXTRA", "").split()]
+ATTN_VARIANTS = [3, 0x10, 0] + ATTN_EXTRA
 
 
 def _attn_ref(q, k, v, sg, tm):
@@ -192,7 +196,7 @@ def test_attention_adversarial_score_jumps():
     ref, _ = _attn_ref(q, k, v, sg, tm)
     # the one-tile kernel (variant 3) exponentiates against a max that is one tile stale and is NOT safe on such inputs (it
     # is kept for A/B timing only); the two-q-tile kernel has an exact per-row max and must be exact here
-    for variant in [0x10, 0]:
+    for variant in [0x10, 0] + ATTN_EXTRA:
         out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
         ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=pso.to(DEV))
         torch.cuda.synchronize()

@@ -426,7 +426,7 @@ def group_attn_perf():
     flops = 4.0 * 64 * H * float(pairs.sum())
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     ref = None
-    for variant in (3, 0x10, 0):
+    for variant in (3, 0x10, 0x20, 0):
         out.zero_()
         ms = _time_cuda(lambda: ops.attn_fwd(q, k, v, out, sd, td, scd, 0.125, variant, pair_sched=ps), iters=8, warm=2)
         if ref is None:
@@ -688,7 +688,7 @@ def group_attn_phase_sweep():
     flops = 4.0 * 64 * H * float(pairs.sum())
     ps = ops.attn_build_pair_schedule(sched, S, seg, tim).to(dev)
     ref = None
-    variants = [0x10]
+    variants = [int(x, 0) for x in os.environ.get("PF_SWEEP_VARIANTS", "0x10").split()]
     for delay in [int(x) for x in os.environ.get("PF_SWEEP_DELAYS", "0 300 600 800 1000 1200 1500 1800 2400 3000").split()]:
         _lib.set_option(_lib.PF_OPT_ATTN_TILE_PHASE, delay)
         for variant in variants:
