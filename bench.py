@@ -693,6 +693,10 @@ def run_ours(args):
     h2d = sum(x.numel() * x.element_size() for x in host["clips"]) + sum(
         host[k].numel() * host[k].element_size() for k in ("enc", "mask", "pooled", "t"))
     d2h = out_host.numel() * out_host.element_size()
+    # which attention kernel the step launched: the three-q-tile kernel unless the launches carry peer stores (SP > 1)
+    triple = bool(_lib.get_option(_lib.PF_OPT_ATTN_TRIPLE_KERNEL)) and (lay is None or lay.sp == 1) and args.attn_variant in (None, 0, 0x20)
+    attn_kernel_name = ("pf::attn3q_fwd_kernel (masked joint attention, three q tiles per CTA, 64-column kv steps, tcgen05)" if triple
+                        else "pf::attn2_fwd_kernel (masked joint attention, two q tiles per CTA, tcgen05)")
     line = {
         "metric": METRIC, "value": tokens / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -722,7 +726,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "parity_vs_n1": parity_vs_n1,
         "vae_decode": vae_leg, "video_e2e": video_leg, "gpu_eager_baseline": eager_leg,
-        "roofline": {"kernel": "pf::attn2_fwd_kernel (masked joint attention, two q tiles per CTA, tcgen05)", "bound": "tensor",
+        "roofline": {"kernel": attn_kernel_name, "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                      "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
                      "launches_timed": len(attn_ms), "avg_launch_ms": attn_avg,
@@ -730,7 +734,9 @@ def run_ours(args):
                      "algorithmic_flops_per_launch": attn_flops_launch,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
                      # shape (profiles/r02_attn2_final_ncu.txt) -- the algorithmic bytes are Q+K+V+O
-                     "traffic": ATTN_TRAFFIC_BYTES if lay is None else None, "traffic_unit": "B/launch",
+                     "traffic": ATTN_TRAFFIC_BYTES if (lay is None and not triple) else None, "traffic_unit": "B/launch",
+                     "traffic_note": ("no ncu capture of the three-q-tile kernel (GPU budget of the round spent); the two-q-tile "
+                                      "kernel at this shape: 460.7 MB = Q+K+V+O once (profiles/r02_attn2_final_ncu.txt)") if triple else None,
                      "algorithmic_bytes_per_launch": 4.0 * b * plan.seq * cfg.inner_dim * 2},
     }
     if args.no_cpu:

@@ -40,13 +40,15 @@ enum {
   PF_OPT_ATTN_PAIR_KERNEL = 2,  /* variant 0 of pf_attn_fwd_masked = the two-q-tile kernel (needs pair_sched) */
   PF_OPT_ATTN_TILE_PHASE = 3,   /* two-q-tile attention kernel: SM clocks the second q tile's softmax warps are held back once per
                                  * CTA so the two tiles run out of phase (0 = start together) */
-  PF_OPT_ATTN_TRIPLE_KERNEL = 4, /* variant 0 of pf_attn_fwd_masked = the three-q-tile kernel when group_sched is given */
+  PF_OPT_ATTN_TRIPLE_KERNEL = 4, /* variant 0 of pf_attn_fwd_masked = the three-q-tile kernel when group_sched is given and the
+                                  * launch has no peer stores (the sequence-parallel path keeps the two-q-tile kernel: the
+                                  * three-q-tile kernel was validated on one GPU only) */
   PF_OPT_COUNT = 5
 };
 #define PF_OPT_DEFAULT_GEMM_STAGED_RESID 1
 #define PF_OPT_DEFAULT_GEMM_WAVE_TILING 1
 #define PF_OPT_DEFAULT_ATTN_PAIR_KERNEL 1
-#define PF_OPT_DEFAULT_ATTN_TRIPLE_KERNEL 0
+#define PF_OPT_DEFAULT_ATTN_TRIPLE_KERNEL 1   /* measured on B200: 2.80 -> 2.60 ms per launch at the bench shape, whole GPU suite green with it */
 #define PF_OPT_DEFAULT_ATTN_TILE_PHASE 800   /* measured on B200: 2.84 -> 2.78 ms per launch at the bench shape (tools/gpu_check.py attn_phase_sweep) */
 PF_API int pf_set_option(int key, int value);
 PF_API int pf_get_option(int key);
@@ -170,7 +172,8 @@ typedef struct pf_attn_desc {
   const int32_t* time;       /* device [batch, seq] */
   const int32_t* tile_sched; /* device; layout documented at pf_attn_build_schedule */
   int32_t sched_stride;      /* int32 entries per (batch, q_tile) row */
-  int32_t variant;           /* 0 = default; 0x10 = the two-q-tile kernel; 1 / 2 / 3 = the one-tile kernel (A/B, see pf_attn.cu) */
+  int32_t variant;           /* 0 = default; 0x20 = the three-q-tile kernel; 0x10 = the two-q-tile kernel; 1 / 2 / 3 = the one-tile
+                              * kernel (A/B, see pf_attn.cu) */
   int32_t q_row_begin;       /* only q rows >= q_row_begin are computed (multiple of 128; 0 = all).  The last single block
                               * needs the current clip's rows only (history outputs are discarded, reference F:380). */
   const int32_t* pair_sched; /* device; built by pf_attn_build_pair_schedule from tile_sched, same sched_stride.  When set (and
@@ -182,7 +185,7 @@ typedef struct pf_attn_desc {
    * `out` is ignored. */
   void* peer_out[PF_MAX_PEERS];
   int32_t peer_count, peer_chunk_rows, peer_col_begin;
-  /* three-q-tile kernel (variant 0x20, or variant 0 with PF_OPT_ATTN_TRIPLE_KERNEL): schedule and row masks of groups of three
+  /* three-q-tile kernel (variant 0x20, or variant 0 under PF_OPT_ATTN_TRIPLE_KERNEL, the default): schedule and row masks of groups of three
    * q tiles from pf_attn_build_group_schedule / pf_attn_build_group_masks (group = 3), same sched_stride */
   const int32_t* group_sched;
   const int32_t* group_mask_index;

@@ -6,6 +6,7 @@ There is no fallback: if the library is missing or the device is not sm_100, cal
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
@@ -114,6 +115,11 @@ def load() -> C.CDLL:
         raise RuntimeError(f"libpf_b200.so does not export: {missing}")
     lib.pf_last_error.restype = C.c_char_p
     lib.pf_launch_count.restype = C.c_int64
+    if int(os.environ.get("WORLD_SIZE", "1")) > 2:
+        # world = CFG(2) x SP(world / 2): with SP > 1 the attention launches carry peer stores and run the two-q-tile kernel (the
+        # three-q-tile kernel has only been validated on one GPU).  Keep the WHOLE process on that kernel, so the single-GPU
+        # reference a sharded step is compared with (bench.py `parity_vs_n1`, tools/sp_check.py) stays bit-identical to it.
+        lib.pf_set_option(PF_OPT_ATTN_TRIPLE_KERNEL, 0)
     lib.pf_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.pf_attn_fwd_masked.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     lib.pf_attn_build_schedule.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]

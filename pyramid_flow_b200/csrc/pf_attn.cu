@@ -585,7 +585,8 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   // 0x10 = the two-q-tile kernel, explicitly; 1 / 2 / 3 = the one-tile kernel (polynomial mix / clock trace / plain), kept for A/B
   PF_REQUIRE(d->variant == 0x10 || d->variant == 0x20 || (d->variant >= 0 && d->variant <= 3), "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
   // 0x20 = the three-q-tile kernel (pf_attn3q.cu), also variant 0 under PF_OPT_ATTN_TRIPLE_KERNEL when its schedule is given
-  if (d->variant == 0x20 || (d->variant == 0 && d->group_sched != nullptr && get_option(PF_OPT_ATTN_TRIPLE_KERNEL))) {
+  if (d->variant == 0x20 ||
+      (d->variant == 0 && d->group_sched != nullptr && d->peer_count <= 1 && get_option(PF_OPT_ATTN_TRIPLE_KERNEL))) {
     PF_REQUIRE(d->group_sched != nullptr && d->group_mask_index != nullptr && d->group_mask_bits != nullptr,
                "pf_attn_fwd_masked: variant 0x%x needs group_sched, group_mask_index and group_mask_bits", d->variant);
     return attn3q_launch(d, stream);

@@ -1,5 +1,6 @@
-// pf_attn3q.cu — masked joint attention forward, THREE q tiles per CTA and 64-column kv steps (head_dim 64).  Opt-in
-// (pf_attn_desc.variant 0x20 / PF_OPT_ATTN_TRIPLE_KERNEL): same contract and the same math as pf_attn2.cu.
+// pf_attn3q.cu — masked joint attention forward, THREE q tiles per CTA and 64-column kv steps (head_dim 64): the default kernel
+// of launches without peer stores (pf_attn_desc.variant 0x20, or variant 0 under PF_OPT_ATTN_TRIPLE_KERNEL).  Same contract and
+// the same math as pf_attn2.cu; 2.80 -> 2.60 ms per launch at the bench shape (profiles/r02_attn3q_validation.txt).
 //
 // Why: the timeline of pf_attn2 shows each softmax warp spending ~1450 clk per kv tile NOT feeding the XU
 // (barrier round trip, TMEM loads, row max, P stores) and only two softmax warps per SMSP to cover for each other -- the XU
@@ -14,7 +15,8 @@
 //     exact thread-local row max, lazy O rescale (branch-free test), every exponential a MUFU.EX2;
 //   * warps 12/13/14 issue the MMAs of tile 0/1/2: S = Q.K_half^T (4 x M128 N64 K16, SS), O += P.V_half (4 x M128 N64 K16, TS);
 //     warp 15 = TMA producer, also owns the TMEM allocation; 64 scores per thread need no setmaxnreg;
-//   * tile X's softmax warps start X * b_delay clocks late, once per CTA (PF_OPT_ATTN_TILE_PHASE), as in pf_attn2.
+//   * tile X's softmax warps start 0.7 X b_delay clocks late, once per CTA (PF_OPT_ATTN_TILE_PHASE) -- measured: no effect here,
+//     three warps per SMSP drift apart by themselves.
 #include <algorithm>
 
 #include "pf_attn_pair.cuh"

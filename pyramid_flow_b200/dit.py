@@ -361,6 +361,8 @@ class B200FluxTransformer(torch.nn.Module):
         epilogues + flag barriers (csrc/pf_peer.cu): no NCCL call in the step, CUDA-graph capturable.  "nccl": the
         all_to_all_single formulation (kept for A/B measurements)."""
         assert exchange in ("peer", "nccl")
+        if layout.sp > 1:   # see _lib.load(): one attention kernel for the whole process once sequence parallelism is in play
+            _lib.set_option(_lib.PF_OPT_ATTN_TRIPLE_KERNEL, 0)
         self.layout = layout
         self.exchange = exchange
         self._px = None

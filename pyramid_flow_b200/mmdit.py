@@ -205,6 +205,8 @@ class B200MMDiT(torch.nn.Module):
         in B200FluxTransformer.  The reference runs this model with sp 2 or 4 (scripts/inference_multigpu.sh:9); 24 heads
         divide by both, so no head padding is needed."""
         assert self.cfg.num_attention_heads % max(1, layout.sp) == 0, "heads must divide by the SP degree"
+        if layout.sp > 1:   # see _lib.load(): one attention kernel for the whole process once sequence parallelism is in play
+            _lib.set_option(_lib.PF_OPT_ATTN_TRIPLE_KERNEL, 0)
         self.layout = layout
         self._px = None
         self._ws.clear()

@@ -18,9 +18,11 @@ def golden_dir():
 
 @pytest.fixture(scope="session", autouse=True)
 def _library_options_from_env():
-    """PF_TEST_ATTN_TRIPLE=1 runs the whole suite with the opt-in three-q-tile attention kernel as the default one."""
+    """PF_TEST_ATTN_TRIPLE=0 / 1 runs the whole suite with the two-q-tile / three-q-tile attention kernel as the default one
+    (unset: the library default, the three-q-tile kernel)."""
     import os
-    if os.environ.get("PF_TEST_ATTN_TRIPLE") == "1":
+    v = os.environ.get("PF_TEST_ATTN_TRIPLE")
+    if v in ("0", "1"):
         from pyramid_flow_b200 import _lib
-        _lib.set_option(_lib.PF_OPT_ATTN_TRIPLE_KERNEL, 1)
+        _lib.set_option(_lib.PF_OPT_ATTN_TRIPLE_KERNEL, int(v))
     yield

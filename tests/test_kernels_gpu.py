@@ -97,11 +97,11 @@ def test_gemm_epilogues_row_ranges():
     assert _rel(cat[..., D:], F.gelu(x.float() @ wm.float().t() + bm, approximate="tanh")) < 8e-3
 
 
-# pf_attn_desc.variant: 3 = one-q-tile kernel (round 1, kept for A/B), 0x10 = two-q-tile kernel, 0 = default (= 0x10 when a pair
-# schedule is given)
-# PF_TEST_ATTN_EXTRA = further variant codes to put through the same cases (0x20 = the opt-in three-q-tile kernel)
+# pf_attn_desc.variant: 3 = one-q-tile kernel (round 1, kept for A/B), 0x10 = two-q-tile kernel, 0x20 = three-q-tile kernel, 0 =
+# default (= 0x20 when the schedules are given; 0x10 for launches with peer stores)
+# PF_TEST_ATTN_EXTRA = further variant codes to put through the same cases
 ATTN_EXTRA = [int(x, 0) for x in os.environ.get("PF_TEST_ATTN_EXTRA", "").split()]
-ATTN_VARIANTS = [3, 0x10, 0] + ATTN_EXTRA
+ATTN_VARIANTS = [3, 0x10, 0x20, 0] + ATTN_EXTRA
 
 
 def _attn_ref(q, k, v, sg, tm):
@@ -196,7 +196,7 @@ def test_attention_adversarial_score_jumps():
     ref, _ = _attn_ref(q, k, v, sg, tm)
     # the one-tile kernel (variant 3) exponentiates against a max that is one tile stale and is NOT safe on such inputs (it
     # is kept for A/B timing only); the two-q-tile kernel has an exact per-row max and must be exact here
-    for variant in [0x10, 0] + ATTN_EXTRA:
+    for variant in [0x10, 0x20, 0] + ATTN_EXTRA:
         out = torch.zeros(B, S, H * 64, device=DEV, dtype=torch.bfloat16)
         ops.attn_fwd(q, k, v, out, sg, tm, sched.to(DEV), 0.125, variant=variant, pair_sched=pso.to(DEV))
         torch.cuda.synchronize()
