@@ -581,7 +581,8 @@ extern "C" int pf_attn_fwd_masked(const pf_attn_desc* d, void* stream_) {
   PF_REQUIRE(d->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "pf_attn_fwd_masked: out must be 16-byte aligned");
   PF_REQUIRE(d->peer_count <= 1 || d->pair_sched != nullptr, "pf_attn_fwd_masked: peer stores need the two-q-tile kernel (pair_sched)");
 
-  // variant: 0 = default (the two-q-tile kernel pf_attn2.cu when a pair schedule is given, else the one-tile kernel below);
+  // variant: 0 = default (the three-q-tile kernel pf_attn3q.cu when its group schedule is given and the launch has no peer stores,
+  // else the two-q-tile kernel pf_attn2.cu when a pair schedule is given, else the one-tile kernel below);
   // 0x10 = the two-q-tile kernel, explicitly; 1 / 2 / 3 = the one-tile kernel (polynomial mix / clock trace / plain), kept for A/B
   PF_REQUIRE(d->variant == 0x10 || d->variant == 0x20 || (d->variant >= 0 && d->variant <= 3), "pf_attn_fwd_masked: bad variant 0x%x", d->variant);
   // 0x20 = the three-q-tile kernel (pf_attn3q.cu), also variant 0 under PF_OPT_ATTN_TRIPLE_KERNEL when its schedule is given
