@@ -183,8 +183,6 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int row = quarter * 32 + lane;
       const int qpos = qt * A2_BM + row;
       const bool q_valid = qpos < a.seq;
-      const int seg_q = q_valid ? a.seg[static_cast<size_t>(b) * a.seq + qpos] : -0x7fffffff;
-      const int time_q = q_valid ? a.time[static_cast<size_t>(b) * a.seq + qpos] : -0x7fffffff;
       const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t t_s = tmem_base + lane_base + X * A2_TM_TILE + A2_TM_S;
       const uint32_t t_o = tmem_base + lane_base + X * A2_TM_TILE + A2_TM_O;
@@ -212,7 +210,6 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
       for (int j = 0; j < n_kv; ++j) {
         tl(j, 0);
-        const int kt = entry >> 4;
         const int fl = (entry >> (2 * X)) & 3;              // bit0: this tile has allowed pairs here, bit1: element mask
         const bool own = (fl & 1) != 0;
         const bool masked = !own || (fl & 2) != 0;
