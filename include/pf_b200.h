@@ -213,12 +213,17 @@ PF_API int64_t pf_attn_build_pair_masks(const int32_t* seg_host, const int32_t* 
                                         uint32_t* mask_bits, int64_t capacity_blocks);
 /* Host helpers of the three-q-tile kernel, the pair forms generalised to groups of `group` (2..4) q tiles counted from the end
  * of the sequence.  Entry = (kv_tile << 8) | flags, 2 flag bits per tile X at bit 2 X (X = 0 the lowest tile of the group);
- * mask_index[batch, n_groups, group * sched_stride], entry e / tile X at [group e + X]; blocks as in the pair form. */
+ * mask_index[batch, n_groups, group * sched_stride], entry e / tile X at [group e + X]; blocks as in the pair form.  With
+ * pair_sched_host / pair_mask_index_host (the pair schedule of the same tile_sched) no bits are built: the indices point into
+ * the PAIR schedule's block pool (a block depends on (q tile, kv tile) only), mask_bits is ignored, and the return value is
+ * the number of pool blocks referenced. */
 PF_API int pf_attn_build_group_schedule(const int32_t* tile_sched_host, int32_t batch, int32_t seq, int32_t sched_stride,
                                         int32_t group, int32_t* out);
 PF_API int64_t pf_attn_build_group_masks(const int32_t* seg_host, const int32_t* time_host, const int32_t* group_sched_host,
                                          int32_t batch, int32_t seq, int32_t sched_stride, int32_t group,
-                                         int32_t* mask_index, uint32_t* mask_bits, int64_t capacity_blocks);
+                                         int32_t* mask_index, uint32_t* mask_bits, int64_t capacity_blocks,
+                                         const int32_t* pair_sched_host /* or NULL */,
+                                         const int32_t* pair_mask_index_host /* or NULL */);
 PF_API int pf_attn_fwd_masked(const pf_attn_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm + AdaLN modulate pre-pass (HBM-bound)

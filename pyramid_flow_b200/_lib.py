@@ -129,7 +129,7 @@ def load() -> C.CDLL:
     lib.pf_attn_build_pair_masks.restype = C.c_int64
     lib.pf_attn_build_group_schedule.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.pf_attn_build_group_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                              C.c_void_p, C.c_void_p, C.c_int64]
+                                              C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.pf_attn_build_group_masks.restype = C.c_int64
     lib.pf_ctx_create.argtypes = [C.POINTER(C.c_void_p)]
     for name in ("pf_ctx_destroy", "pf_ctx_record_end"):

@@ -437,7 +437,8 @@ extern "C" int pf_attn_build_group_schedule(const int32_t* tile_sched, int32_t b
 
 extern "C" int64_t pf_attn_build_group_masks(const int32_t* seg, const int32_t* time, const int32_t* group_sched, int32_t batch,
                                              int32_t seq, int32_t sched_stride, int32_t group, int32_t* mask_index,
-                                             uint32_t* mask_bits, int64_t capacity_blocks) {
+                                             uint32_t* mask_bits, int64_t capacity_blocks, const int32_t* pair_sched,
+                                             const int32_t* pair_mask_index) {
   using namespace pf;
   if (!seg || !time || !group_sched || !mask_index || batch <= 0 || seq <= 0 || group < 2 || group > 4) {
     set_error("pf_attn_build_group_masks: bad arguments");
@@ -445,6 +446,8 @@ extern "C" int64_t pf_attn_build_group_masks(const int32_t* seg, const int32_t* 
   }
   const int q_tiles = (seq + 127) / 128;
   const int n_groups = (q_tiles + group - 1) / group;
+  const int n_pairs = (q_tiles + 1) / 2;
+  const bool share = pair_sched != nullptr && pair_mask_index != nullptr;   // reuse the pair schedule's blocks: same (q tile, kv tile) masks
   int64_t blocks = 0;
   for (int b = 0; b < batch; ++b) {
     const int32_t* sg = seg + static_cast<size_t>(b) * seq;
@@ -460,6 +463,26 @@ extern "C" int64_t pf_attn_build_group_masks(const int32_t* seg, const int32_t* 
           const int fl = (ent >> (2 * x)) & 3;
           if (fl != 3) continue;                       // needs bits only when the tile owns the entry AND is partial
           const int qt = top - (group - 1 - x);
+          if (share) {
+            // q tile qt is tile x_p of pair p; its partial (qt, kt) block was numbered by pf_attn_build_pair_masks
+            const int p = (q_tiles - 1 - qt) / 2;
+            const int x_p = (qt == q_tiles - 1 - 2 * p) ? 1 : 0;
+            const int32_t* prow = pair_sched + (static_cast<size_t>(b) * n_pairs + p) * sched_stride;
+            int lo = 0, hi = prow[0] - 1, at = -1;
+            while (lo <= hi) {
+              const int mid = (lo + hi) / 2, k2 = prow[1 + mid] >> 4;
+              if (k2 == kt) { at = mid; break; }
+              if (k2 < kt) lo = mid + 1; else hi = mid - 1;
+            }
+            const int32_t blk = at < 0 ? -1 : pair_mask_index[(static_cast<size_t>(b) * n_pairs + p) * 2 * sched_stride + 2 * at + x_p];
+            if (blk < 0) {
+              set_error("pf_attn_build_group_masks: no pair block for q tile %d, kv tile %d (batch %d)", qt, kt, b);
+              return -1;
+            }
+            mi[group * e + x] = blk;
+            blocks = std::max<int64_t>(blocks, static_cast<int64_t>(blk) + 1);
+            continue;
+          }
           if (mask_bits != nullptr && blocks < capacity_blocks) {
             uint32_t* blk = mask_bits + static_cast<size_t>(blocks) * 128 * 4;
             for (int r = 0; r < 128; ++r) {

@@ -173,8 +173,11 @@ class PairSchedule:
         self.sched, self.mask_index, self.mask_bits, self.group3 = sched, mask_index, mask_bits, group3
 
     def to(self, device) -> "PairSchedule":
-        return PairSchedule(self.sched.to(device), self.mask_index.to(device), self.mask_bits.to(device),
-                            None if self.group3 is None else self.group3.to(device))
+        bits = self.mask_bits.to(device)
+        g3 = self.group3
+        if g3 is not None:     # the group schedule indexes the SAME block pool when it was built from this pair schedule
+            g3 = PairSchedule(g3.sched.to(device), g3.mask_index.to(device), bits if g3.mask_bits is self.mask_bits else g3.mask_bits.to(device))
+        return PairSchedule(self.sched.to(device), self.mask_index.to(device), bits, g3)
 
     def __getitem__(self, idx) -> "PairSchedule":          # batch slice (block indices are global: the bit pool is shared)
         assert isinstance(idx, slice)
@@ -201,12 +204,17 @@ def attn_build_pair_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, t
     n2 = lib.pf_attn_build_pair_masks(seg.data_ptr(), time.data_ptr(), ps.data_ptr(), batch, seq, stride, midx.data_ptr(),
                                       bits.data_ptr(), int(n))
     assert n2 == n
-    return PairSchedule(ps, midx, bits, attn_build_group_schedule(sched, seq, seg, time, 3))
+    pso = PairSchedule(ps, midx, bits)
+    pso.group3 = attn_build_group_schedule(sched, seq, seg, time, 3, share=pso)
+    return pso
 
 
-def attn_build_group_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, time: torch.Tensor, group: int = 3) -> PairSchedule:
+def attn_build_group_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, time: torch.Tensor, group: int = 3,
+                              share: Optional[PairSchedule] = None) -> PairSchedule:
     """The pair schedule generalised to groups of `group` q tiles (the three-q-tile kernel): sched int32 [batch, n_groups,
-    stride] with entries (kv_tile << 8) | 2 flag bits per tile, mask_index [batch, n_groups, group * stride], mask_bits."""
+    stride] with entries (kv_tile << 8) | 2 flag bits per tile, mask_index [batch, n_groups, group * stride], mask_bits.
+    `share` = the pair schedule of the same tile schedule: its block pool is reused (a block depends on (q tile, kv tile) only),
+    no bits are built and `mask_bits` IS `share.mask_bits`."""
     sched = sched.to(torch.int32).contiguous().cpu()
     seg = seg.to(torch.int32).contiguous().cpu()
     time = time.to(torch.int32).contiguous().cpu()
@@ -216,12 +224,21 @@ def attn_build_group_schedule(sched: torch.Tensor, seq: int, seg: torch.Tensor, 
     gs = torch.zeros(batch, n_groups, stride, dtype=torch.int32)
     _lib.check(lib.pf_attn_build_group_schedule(sched.data_ptr(), batch, seq, stride, group, gs.data_ptr()), "pf_attn_build_group_schedule")
     midx = torch.full((batch, n_groups, group * stride), -1, dtype=torch.int32)
-    n = lib.pf_attn_build_group_masks(seg.data_ptr(), time.data_ptr(), gs.data_ptr(), batch, seq, stride, group, midx.data_ptr(), None, 0)
+    if share is not None:
+        assert share.sched.shape[-1] == stride and share.sched.is_contiguous() and share.mask_index.is_contiguous()
+        n = lib.pf_attn_build_group_masks(seg.data_ptr(), time.data_ptr(), gs.data_ptr(), batch, seq, stride, group, midx.data_ptr(),
+                                          None, 0, share.sched.data_ptr(), share.mask_index.data_ptr())
+        if n < 0:
+            _lib.check(int(n), "pf_attn_build_group_masks")
+        assert n <= share.mask_bits.shape[0]
+        return PairSchedule(gs, midx, share.mask_bits)
+    n = lib.pf_attn_build_group_masks(seg.data_ptr(), time.data_ptr(), gs.data_ptr(), batch, seq, stride, group, midx.data_ptr(), None, 0,
+                                      None, None)
     if n < 0:
         _lib.check(int(n), "pf_attn_build_group_masks")
     bits = torch.zeros(max(1, int(n)), 128, 4, dtype=torch.int32)
     n2 = lib.pf_attn_build_group_masks(seg.data_ptr(), time.data_ptr(), gs.data_ptr(), batch, seq, stride, group, midx.data_ptr(),
-                                       bits.data_ptr(), int(n))
+                                       bits.data_ptr(), int(n), None, None)
     assert n2 == n
     return PairSchedule(gs, midx, bits)
 

@@ -196,35 +196,38 @@ def test_group_schedule_is_the_union_of_the_three_tile_rows():
         seg = torch.ones(2, seq, dtype=torch.int32)
         seg[1, 10:int(torch.randint(20, 60, (1,), generator=g_))] = 0
         sched, pairs = ops.attn_build_schedule(seg, tim)
-        gs = ops.attn_build_group_schedule(sched, seq, seg, tim, 3)
+        pso = ops.attn_build_pair_schedule(sched, seq, seg, tim)
+        assert pso.group3.mask_bits is pso.mask_bits, "the plan's group schedule indexes the pair schedule's block pool"
         qt = (seq + 127) // 128
         n_groups = (qt + 2) // 3
-        assert gs.sched.shape == (2, n_groups, sched.shape[-1]) and gs.mask_index.shape == (2, n_groups, 3 * sched.shape[-1])
-        for b in range(2):
-            for gi in range(n_groups):
-                top = qt - 1 - 3 * gi
-                n = int(gs.sched[b, gi, 0])
-                ent = gs.sched[b, gi, 1:1 + n].tolist()
-                kts = [e >> 8 for e in ent]
-                assert kts == sorted(set(kts)), "union must be strictly increasing"
-                assert all((e & 0x3F) != 0 for e in ent), "every entry is needed by at least one tile"
-                assert bool((gs.sched[b, gi, 1 + n:] == 0).all())
-                for x in range(3):
-                    t = top - (2 - x)
-                    own = [((e >> 8) << 1) | (((e >> (2 * x)) & 2) >> 1) for e in ent if (e >> (2 * x)) & 1]
-                    want = [] if t < 0 else sched[b, t, 1:1 + int(sched[b, t, 0])].tolist()
-                    assert own == want, (seq, b, gi, x)
-                    for e_i, e in enumerate(ent):
-                        blk = int(gs.mask_index[b, gi, 3 * e_i + x])
-                        if ((e >> (2 * x)) & 3) != 3:
-                            assert blk == -1
-                            continue
-                        words = gs.mask_bits[blk].to(torch.int64) & 0xFFFFFFFF            # [128, 4]
-                        bits = ((words[:, :, None] >> torch.arange(32)[None, None, :]) & 1).reshape(128, 128).bool()
-                        q = torch.arange(t * 128, t * 128 + 128)
-                        kv = torch.arange((e >> 8) * 128, (e >> 8) * 128 + 128)
-                        qv, kvv = q < seq, kv < seq
-                        qc, kc = q.clamp(max=seq - 1), kv.clamp(max=seq - 1)
-                        dense = (seg[b][qc][:, None] == seg[b][kc][None, :]) & (tim[b][qc][:, None] >= tim[b][kc][None, :])
-                        dense &= qv[:, None] & kvv[None, :]
-                        assert torch.equal(bits, dense), (seq, b, gi, e_i, x)
+        # both forms: standalone (own block pool) and the one every plan carries (blocks shared with the pair schedule)
+        for gs in (ops.attn_build_group_schedule(sched, seq, seg, tim, 3), pso.group3):
+          assert gs.sched.shape == (2, n_groups, sched.shape[-1]) and gs.mask_index.shape == (2, n_groups, 3 * sched.shape[-1])
+          for b in range(2):
+              for gi in range(n_groups):
+                  top = qt - 1 - 3 * gi
+                  n = int(gs.sched[b, gi, 0])
+                  ent = gs.sched[b, gi, 1:1 + n].tolist()
+                  kts = [e >> 8 for e in ent]
+                  assert kts == sorted(set(kts)), "union must be strictly increasing"
+                  assert all((e & 0x3F) != 0 for e in ent), "every entry is needed by at least one tile"
+                  assert bool((gs.sched[b, gi, 1 + n:] == 0).all())
+                  for x in range(3):
+                      t = top - (2 - x)
+                      own = [((e >> 8) << 1) | (((e >> (2 * x)) & 2) >> 1) for e in ent if (e >> (2 * x)) & 1]
+                      want = [] if t < 0 else sched[b, t, 1:1 + int(sched[b, t, 0])].tolist()
+                      assert own == want, (seq, b, gi, x)
+                      for e_i, e in enumerate(ent):
+                          blk = int(gs.mask_index[b, gi, 3 * e_i + x])
+                          if ((e >> (2 * x)) & 3) != 3:
+                              assert blk == -1
+                              continue
+                          words = gs.mask_bits[blk].to(torch.int64) & 0xFFFFFFFF            # [128, 4]
+                          bits = ((words[:, :, None] >> torch.arange(32)[None, None, :]) & 1).reshape(128, 128).bool()
+                          q = torch.arange(t * 128, t * 128 + 128)
+                          kv = torch.arange((e >> 8) * 128, (e >> 8) * 128 + 128)
+                          qv, kvv = q < seq, kv < seq
+                          qc, kc = q.clamp(max=seq - 1), kv.clamp(max=seq - 1)
+                          dense = (seg[b][qc][:, None] == seg[b][kc][None, :]) & (tim[b][qc][:, None] >= tim[b][kc][None, :])
+                          dense &= qv[:, None] & kvv[None, :]
+                          assert torch.equal(bits, dense), (seq, b, gi, e_i, x)
