@@ -1,3 +1,5 @@
+// NOTE: the softmax-stream modes of this probe spill (512-thread launch bound = 128 registers for 128 live scores); their
+// "one MUFU per 16 clk per warp" result is an artefact -- see exp_sched_probe.cu for the re-measurement.  The LDTM modes stand.
 // Micro-probe (not part of the product): tcgen05.ld throughput per SM as a function of how many warps load at once, alone and
 // mixed with the softmax instruction stream (FFMA2 + MUFU.EX2 + FADD2 + F2FP), in SM clocks (clock64), so the answer does not
 // depend on the clock the box happens to run at.
