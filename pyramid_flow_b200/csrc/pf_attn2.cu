@@ -505,18 +505,7 @@ extern "C" int64_t pf_attn_build_pair_masks(const int32_t* seg, const int32_t* t
           if (fl != 3) continue;                       // needs bits only when the tile owns the entry AND is partial
           const int qt = x ? hi : hi - 1;
           if (mask_bits != nullptr && blocks < capacity_blocks) {
-            uint32_t* blk = mask_bits + static_cast<size_t>(blocks) * 128 * 4;
-            for (int r = 0; r < 128; ++r) {
-              const int q = qt * 128 + r;
-              uint32_t w[4] = {0u, 0u, 0u, 0u};
-              if (q < seq) {
-                for (int c = 0; c < 128; ++c) {
-                  const int kv = kt * 128 + c;
-                  if (kv < seq && sg[kv] == sg[q] && tm[kv] <= tm[q]) w[c >> 5] |= 1u << (c & 31);
-                }
-              }
-              for (int k = 0; k < 4; ++k) blk[r * 4 + k] = w[k];
-            }
+            attn_build_mask_block(sg, tm, seq, qt, kt, mask_bits + static_cast<size_t>(blocks) * 128 * 4);
           }
           mi[2 * e + x] = static_cast<int32_t>(blocks);
           ++blocks;

@@ -484,18 +484,7 @@ extern "C" int64_t pf_attn_build_group_masks(const int32_t* seg, const int32_t* 
             continue;
           }
           if (mask_bits != nullptr && blocks < capacity_blocks) {
-            uint32_t* blk = mask_bits + static_cast<size_t>(blocks) * 128 * 4;
-            for (int r = 0; r < 128; ++r) {
-              const int q = qt * 128 + r;
-              uint32_t w[4] = {0u, 0u, 0u, 0u};
-              if (q < seq) {
-                for (int cidx = 0; cidx < 128; ++cidx) {
-                  const int kv = kt * 128 + cidx;
-                  if (kv < seq && sg[kv] == sg[q] && tm[kv] <= tm[q]) w[cidx >> 5] |= 1u << (cidx & 31);
-                }
-              }
-              for (int k = 0; k < 4; ++k) blk[r * 4 + k] = w[k];
-            }
+            attn_build_mask_block(sg, tm, seq, qt, kt, mask_bits + static_cast<size_t>(blocks) * 128 * 4);
           }
           mi[group * e + x] = static_cast<int32_t>(blocks);
           ++blocks;

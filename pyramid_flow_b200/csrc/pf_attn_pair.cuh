@@ -4,6 +4,9 @@
 
 #include "../../include/pf_b200.h"
 #include "pf_common.cuh"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace pf {
 
@@ -102,6 +105,42 @@ __device__ __forceinline__ void a2_exp64(const uint32_t (&va)[32], const uint32_
     else l01 = f2_add(l01, f2_pack(p0, p1));
     if (i < 16) pka[i] = pack_bf16x2(p0, p1);
     else pkb[i - 16] = pack_bf16x2(p0, p1);
+  }
+}
+
+
+// Host: the 128 x 128 allow bits of one (q tile, kv tile) block: bit i of word w of row r = q row qt*128 + r may attend kv column
+// kt*128 + 32 w + i  <=>  both inside the sequence, same segment, time_kv <= time_q (mask definition F:318-350).  A plan of the
+// 768p run holds a few hundred such blocks; four columns per SSE2 compare (a scalar loop was 0.2 ms per block).
+inline void attn_build_mask_block(const int32_t* sg, const int32_t* tm, int seq, int qt, int kt, uint32_t* blk) {
+  alignas(16) int32_t sgk[128], tmk[128];
+  uint32_t valid[4] = {0u, 0u, 0u, 0u};
+  for (int c = 0; c < 128; ++c) {
+    const int kv = kt * 128 + c;
+    const bool in = kv < seq;
+    sgk[c] = in ? sg[kv] : 0;
+    tmk[c] = in ? tm[kv] : 0;
+    if (in) valid[c >> 5] |= 1u << (c & 31);
+  }
+  for (int r = 0; r < 128; ++r) {
+    const int q = qt * 128 + r;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (q < seq) {
+      const int32_t sq = sg[q], tq = tm[q];
+#if defined(__SSE2__)
+      const __m128i sq4 = _mm_set1_epi32(sq), tq4 = _mm_set1_epi32(tq);
+      for (int c = 0; c < 128; c += 4) {
+        const __m128i eq = _mm_cmpeq_epi32(_mm_load_si128(reinterpret_cast<const __m128i*>(sgk + c)), sq4);
+        const __m128i gt = _mm_cmpgt_epi32(_mm_load_si128(reinterpret_cast<const __m128i*>(tmk + c)), tq4);
+        const uint32_t m = static_cast<uint32_t>(_mm_movemask_ps(_mm_castsi128_ps(_mm_andnot_si128(gt, eq))));
+        w[c >> 5] |= m << (c & 31);
+      }
+#else
+      for (int c = 0; c < 128; ++c) w[c >> 5] |= static_cast<uint32_t>(sgk[c] == sq && tmk[c] <= tq) << (c & 31);
+#endif
+      for (int k = 0; k < 4; ++k) w[k] &= valid[k];
+    }
+    for (int k = 0; k < 4; ++k) blk[r * 4 + k] = w[k];
   }
 }
 
